@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""Headline benchmark: message-passing layer forward+backward throughput in GEdge-feat/s
+ on synthetic graphs of the shapes BASELINE.json names, through the reference's own
+layer API (layer_dict[name](dim_in, dim_out, bias) + forward(batch) + backward).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+  value     device-resident: inputs and the graph layout already in HBM, K timed steps (CUDA events)
+  e2e       host buffers in, result out: pinned-host -> device copies of node_feature and edge_index,
+            layout build, layer fwd+bwd, device -> host read of the bias gradient, every step
+  roofline  the aggregation (SpMM) kernel: algorithmic bytes / CUDA-event time inside the timed steps
+  cpu_baseline / --impl reference: the oracle restatement of the reference's CPU op sequence
+            (gather -> scale -> index_add_ -> matmul) on a bounded sample, all host threads
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[3] graph (ogbn-products shape) under the GCN layer: the 62M-edge graph the
+    # north star's scaling target is stated on.  L2 (126 MB) << feature matrix (1.25 GB).
+    'products_gcn': dict(layer='gcnconv', graph='powerlaw', n=2_449_029, e_und=30_929_570, fin=100,
+                         fout=128, max_deg=17_481, desc='gcnconv 100->128 on products-shaped power-law '
+                         'graph (2.45M nodes, 61.9M directed edges)'),
+    'products_gat': dict(layer='gatconv', graph='powerlaw', n=2_449_029, e_und=30_929_570, fin=100,
+                         fout=128, max_deg=17_481, desc='gatconv 100->128 (H=1) on products-shaped '
+                         'power-law graph (2.45M nodes, 61.9M directed edges)'),
+    # configs[2]: BA 1M nodes / 10M directed edges, 256 hidden
+    'ba1m_sage': dict(layer='sageconv', graph='ba', n=1_000_000, m=5, fin=256, fout=256,
+                      desc='sageconv 256->256 on BA graph (1M nodes, 10M directed edges)'),
+    'ba1m_gcn': dict(layer='gcnconv', graph='ba', n=1_000_000, m=5, fin=256, fout=256,
+                     desc='gcnconv 256->256 on BA graph (1M nodes, 10M directed edges)'),
+    # configs[1]: Cora-shaped, fits L2 entirely -> launch-bound, reported for completeness
+    'cora_gcn': dict(layer='gcnconv', graph='uniform', n=2708, e_und=5278, fin=1433, fout=128,
+                     desc='gcnconv 1433->128 on Cora-shaped graph (2708 nodes, 10556 directed edges)'),
+}
+DEFAULT_WORKLOAD = 'products_gcn'
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic graphs (seeded; torch ops so the big ones can be drawn on the GPU in < 1 s)
+# ------------------------------------------------------------------------------------------------
+def gen_graph(spec, device, seed=0, scale=1.0):
+    """-> edge_index [2,E] int64 on `device` (symmetric: both directions of every undirected edge).
+    `scale` < 1 shrinks nodes and edges together (the CPU-baseline sample of the same family)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    n = max(8, int(spec['n'] * scale))
+    if spec['graph'] == 'powerlaw':
+        m = max(8, int(spec['e_und'] * scale))
+        w = torch.arange(1, n + 1, device=device, dtype=torch.float64).pow(-1.0 / 1.1)  # exponent 2.1
+        cap = min(float(spec['max_deg']), n / 8.0)
+        for _ in range(4):  # expected degree sequence: mean 2m/n, clipped at max_deg
+            w = (w * (2.0 * m / w.sum())).clamp(max=cap)
+        cdf = torch.cumsum(w / w.sum(), 0)
+        a = torch.searchsorted(cdf, torch.rand(m, device=device, dtype=torch.float64, generator=g)).clamp(max=n - 1)
+        b = torch.searchsorted(cdf, torch.rand(m, device=device, dtype=torch.float64, generator=g)).clamp(max=n - 1)
+        perm = torch.randperm(n, device=device, generator=g)  # hubs are not the low ids
+        a, b = perm[a], perm[b]
+    elif spec['graph'] == 'ba':
+        m0 = spec['m']
+        k = torch.arange(m0 * (n - m0), device=device)
+        t = m0 + k // m0
+        limit = 2 * m0 * (t - m0)  # endpoint-list entries that exist before node t arrives
+        r = (torch.rand(k.numel(), device=device, dtype=torch.float64, generator=g) * limit.clamp(min=1)).long()
+        ptr, even = r // 2, (r % 2 == 0)
+        tgt = torch.full_like(k, -1)
+        first = limit == 0
+        tgt[first] = torch.randint(0, m0, (int(first.sum()),), device=device, generator=g)
+        sel = even & ~first
+        tgt[sel] = m0 + ptr[sel] // m0
+        while True:  # odd entries point at an earlier edge's target: pointer-jump until resolved
+            idx = torch.nonzero(tgt < 0).flatten()
+            if idx.numel() == 0:
+                break
+            tgt[idx] = tgt[ptr[idx]]
+        a, b = t, tgt
+    else:  # 'uniform': distinct undirected pairs, uniformly at random
+        m = max(4, int(spec['e_und'] * scale))
+        a = torch.randint(0, n, (4 * m,), device=device, generator=g)
+        b = torch.randint(0, n, (4 * m,), device=device, generator=g)
+        keep = a < b
+        code = torch.unique(a[keep] * n + b[keep])
+        code = code[torch.randperm(code.numel(), device=device, generator=g)[:m]]
+        a, b = code // n, code % n
+    return n, torch.stack([torch.cat([a, b]), torch.cat([b, a])]).contiguous()
+
+
+def gen_features(n, f, device, seed=0):
+    g = torch.Generator(device=device).manual_seed(seed + 1)
+    return torch.randn(n, f, device=device, generator=g)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, s[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the measured step
+# ------------------------------------------------------------------------------------------------
+def edge_feat_per_step(layer_name, n, num_slots, fin, fout):
+    """E' x F_agg x 2 passes: GCN/GAT aggregate F_out-wide, SAGE/GIN F_in-wide."""
+    f_agg = fout if layer_name in ('gcnconv', 'gatconv', 'gcnidconv', 'gatidconv', 'idconv') else fin
+    return num_slots * f_agg * 2, f_agg
+
+
+def spmm_bytes(n, slots, f, weighted):
+    """Algorithmic bytes of one aggregation launch: gathered rows + output rows + nbr
+    indices + rowptr (+ per-slot weights)."""
+    return slots * f * 4 + n * f * 4 + slots * 4 + (n + 1) * 4 + (slots * 4 if weighted else 0)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def loop_policy_for(layer_name):
+    from graphgym_b200 import ops
+    return {'gcnconv': ops.LOOPS_ADD_REMAINING, 'gcnidconv': ops.LOOPS_ADD_REMAINING,
+            'gatconv': ops.LOOPS_REMOVE_ADD, 'gatidconv': ops.LOOPS_REMOVE_ADD,
+            'ginidconv': ops.LOOPS_REMOVE}.get(layer_name, ops.LOOPS_KEEP)
+
+
+def run_ours(args, spec, rank, world, dev):
+    import torch.distributed as dist
+
+    from graphgym_b200 import ops
+    from graphgym_b200.graph import clear_cache, get_layout
+    from graphgym_b200.models.layer import Batch, layer_dict
+    if world > 1:
+        raise SystemExit('multi-GPU bench: see bench_dist path (not wired in this build)')
+    name, fin, fout = spec['layer'], spec['fin'], spec['fout']
+    t0 = time.time()
+    n, ei = gen_graph(spec, dev, seed=0)
+    x = gen_features(n, fin, dev)
+    torch.manual_seed(0)
+    layer = layer_dict[name](fin, fout, bias=True).to(dev)
+    gy = gen_features(n, fout, dev, seed=7)
+    ids = torch.arange(0, n, 64, device=dev) if 'id' in name else None
+    torch.cuda.synchronize()
+    gen_s = time.time() - t0
+
+    # ---- device-resident steps -------------------------------------------------------------
+    spmm_events = []
+    orig_spmm = ops.spmm
+
+    def timed_spmm(*a, **k):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = orig_spmm(*a, **k)
+        e.record()
+        spmm_events.append((s, e))
+        return out
+
+    def step(x_dev, ei_dev):
+        layer.zero_grad(set_to_none=True)
+        b = layer(Batch(x_dev, ei_dev, ids))
+        b.node_feature.backward(gy)
+        return layer.model.bias.grad if getattr(layer.model, 'bias', None) is not None else b.node_feature
+
+    t0 = time.time()
+    lay = get_layout(ei, n, loop_policy_for(name))
+    slots = lay.csr.num_slots
+    _ = lay.csc
+    torch.cuda.synchronize()
+    layout_first_s = time.time() - t0
+    for _ in range(args.warmup):
+        step(x, ei)
+    torch.cuda.synchronize()
+    import graphgym_b200.functional as F_
+    F_.ops.spmm = timed_spmm
+    launches0 = ops.launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev.index or 0) as clocks:
+        torch.cuda.synchronize()
+        start.record()
+        for _ in range(args.steps):
+            step(x, ei)
+        end.record()
+        torch.cuda.synchronize()
+    F_.ops.spmm = orig_spmm
+    launches = ops.launch_count() - launches0
+    ms = start.elapsed_time(end) / args.steps
+    ef, f_agg = edge_feat_per_step(name, n, slots, fin, fout)
+    value = ef / (ms * 1e-3) / 1e9
+
+    spmm_ms = [s.elapsed_time(e) for s, e in spmm_events]
+    weighted = name in ('gcnconv', 'gcnidconv', 'gatconv', 'gatidconv')
+    per_launch_bytes = spmm_bytes(n, slots, f_agg, weighted)
+    avg_spmm_ms = float(np.mean(spmm_ms)) if spmm_ms else float('nan')
+    peak, peak_src = load_peaks()
+    achieved = per_launch_bytes / (avg_spmm_ms * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'kernel': 'spmm_vec_kernel (CSR aggregation, fwd and bwd launches)',
+                'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
+                'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': per_launch_bytes,
+                'avg_launch_ms': round(avg_spmm_ms, 4), 'launches_timed': len(spmm_ms),
+                'share_of_step': round(sum(spmm_ms) / args.steps / ms, 3)}
+
+    # ---- layout build alone (amortised over layers/epochs in training; reported, not in `value`) ---
+    clear_cache()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    lay = get_layout(ei, n, loop_policy_for(name))
+    _ = lay.csr, lay.csc
+    lay.weights('gcn_tgt' if name == 'gcnconv' else 'sum')
+    e.record()
+    torch.cuda.synchronize()
+    layout_ms = s.elapsed_time(e)
+
+    # ---- end to end: host buffers in, result out, every step ------------------------------------
+    x_host = x.cpu().pin_memory()
+    ei_host = ei.cpu().pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+    res_host = torch.empty(fout, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        eid = ei_host.to(dev, non_blocking=True)
+        r = step(xd, eid)
+        res_host.copy_(r.detach().reshape(-1)[:fout], non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e.record()
+    torch.cuda.synchronize()
+    e2e_ms = s.elapsed_time(e) / e2e_steps
+    e2e = {'value': round(ef / (e2e_ms * 1e-3) / 1e9, 3), 'unit': 'GEdge-feat/s',
+           'ms_per_step': round(e2e_ms, 3), 'steps': e2e_steps,
+           'h2d_bytes_per_step': int(x_host.numel() * 4 + ei_host.numel() * 8),
+           'd2h_bytes_per_step': int(fout * 4),
+           'includes': 'H2D of node_feature+edge_index from pinned memory, CSR+CSC layout build, layer '
+                       'fwd+bwd via layer_dict API, D2H of the bias gradient'}
+    del x_host, ei_host
+
+    cpu = cpu_baseline(spec, seconds=args.cpu_seconds) if rank == 0 and not args.no_cpu else None
+    out = {
+        'metric': 'layer fwd+bwd GEdge-feat/s', 'value': round(value, 3), 'unit': 'GEdge-feat/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms, 4),
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic (seeded power-law / BA / uniform generators in bench.py; random-init glorot weights)',
+        'config': {'workload': spec['desc'], 'layer': name, 'nodes': n, 'edges_directed': int(ei.size(1)),
+                   'slots_after_loop_policy': slots, 'f_in': fin, 'f_out': fout, 'f_aggregated': f_agg,
+                   'l2_policy': 'inputs larger than L2 (feature matrix %.0f MB vs 126 MB L2)' % (n * f_agg * 4 / 1e6)
+                   if n * f_agg * 4 > 126e6 else 'inputs fit L2: launch-bound workload, no flush',
+                   'layout_cached_across_steps': True},
+        'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': int(launches),
+        'roofline': roofline, 'cpu_baseline': cpu,
+        'layout_build_ms': round(layout_ms, 3), 'graph_gen_s': round(gen_s, 2),
+        'layout_first_call_s': round(layout_first_s, 3),
+    }
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference's op sequence, all host threads
+# ------------------------------------------------------------------------------------------------
+def cpu_layer_step(name, x, ei, params, gy):
+    from oracle import layers as olayers
+    xg = x.requires_grad_(True)
+    for p in params.values():
+        p.grad = None
+    if name == 'gcnconv':
+        y = olayers.gcnconv(xg, ei, params['weight'], params['bias'])
+    elif name == 'sageconv':
+        y = olayers.sageconv(xg, ei, params['w_l'], params['bias'], params['w_r'])
+    elif name == 'gatconv':
+        y = olayers.gatconv(xg, ei, params['weight'], params['att'], params['bias'])
+    else:
+        raise KeyError(name)
+    y.backward(gy)
+    return y
+
+
+def cpu_baseline(spec, seconds=15.0, steps=None, warmup=1):
+    """Oracle (kind 'port': PyG is not installable here) on a bounded sample of the same graph
+    family: same generator, nodes and edges scaled down together so one step is ~1-2 s of CPU."""
+    name, fin, fout = spec['layer'], spec['fin'], spec['fout']
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    target_edges = 4_000_000
+    full_edges = 2 * (spec.get('e_und') or spec['m'] * spec['n'])
+    scale = min(1.0, target_edges / full_edges)
+    cpu = torch.device('cpu')
+    n, ei = gen_graph(spec, cpu, seed=1, scale=scale)
+    x = gen_features(n, fin, cpu)
+    gy = gen_features(n, fout, cpu, seed=7)
+    g = torch.Generator().manual_seed(0)
+    mk = lambda *s: (torch.randn(*s, generator=g) * 0.1).requires_grad_(True)
+    params = {'weight': mk(fin, fout), 'bias': mk(fout), 'w_l': mk(fout, fin), 'w_r': mk(fout, fin),
+              'att': mk(1, 1, 2 * fout)}
+    slots = int(ei.size(1)) + (n if name in ('gcnconv', 'gatconv') else 0)
+    ef, _ = edge_feat_per_step(name, n, slots, fin, fout)
+    for _ in range(warmup):
+        cpu_layer_step(name, x, ei, params, gy)
+    times = []
+    t_end = time.time() + seconds
+    while (steps is None and time.time() < t_end) or (steps is not None and len(times) < steps):
+        t0 = time.time()
+        cpu_layer_step(name, x, ei, params, gy)
+        times.append(time.time() - t0)
+        if steps is None and len(times) >= 50:
+            break
+    t = float(np.median(times))
+    return {'value': round(ef / t / 1e9, 4), 'unit': 'GEdge-feat/s', 'cores': cores, 'kind': 'port',
+            'ms_per_step': round(t * 1e3, 2), 'steps': len(times), 'torch_threads': torch.get_num_threads(),
+            'sample': f'same generator scaled x{scale:.4f}: {n} nodes, {int(ei.size(1))} directed edges, '
+                      f'{name} {fin}->{fout}, fwd+bwd, fp32, oracle restatement of the PyG op sequence '
+                      '(index_select gather, per-edge scale, index_add_ scatter, matmul)'}
+
+
+def run_reference(args, spec, rank, world):
+    if rank != 0:
+        return None
+    cpu = cpu_baseline(spec, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    return {'impl': 'reference', 'metric': 'layer fwd+bwd GEdge-feat/s', 'value': cpu['value'],
+            'unit': 'GEdge-feat/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': cpu['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (bounded sample, see cpu_baseline.sample)',
+            'config': {'workload': spec['desc'], 'layer': spec['layer']},
+            'cpu_baseline': cpu,
+            'e2e': {'value': cpu['value'], 'unit': 'GEdge-feat/s', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0},
+            'note': 'torch_geometric / torch_scatter are not installable offline: this is the oracle '
+                    'restatement of the reference CPU path (oracle/layers.py), all host threads'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    spec = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        out = run_reference(args, spec, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback '
+                         '(use --impl reference for the CPU arm)')
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    out = run_ours(args, spec, rank, world, dev)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == '__main__':
+    main()

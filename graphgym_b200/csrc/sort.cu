@@ -1,0 +1,283 @@
+// Stable LSD radix sort of (key, value) u32 pairs + a device-wide exclusive scan.
+//
+// This is the integer engine under the COO -> CSR/CSC build (layout.cu).  "Bit-exact" for the
+// layout means the STABLE counting sort of the edited edge list, so no atomics decide
+// an output position anywhere in this file:
+//   * every warp owns a contiguous chunk of the input;
+//   * pass p: (1) per-warp digit histogram, (2) exclusive scan of the digit-major table
+//     counts[digit][warp] -> the first output slot of every (digit, warp) pair, (3) each warp
+//     replays its chunk in order, ranks equal digits inside a 32-key round with
+//     __match_any_sync (lower lane = earlier key) and bumps its private per-digit cursor.
+// Traffic per pass: 4 B (hist) + 8 B read + 8 B written per pair; HBM-bound integer work.
+#include "common.cuh"
+
+namespace gg {
+
+constexpr int kRadixBits = 8;
+constexpr int kRadix = 1 << kRadixBits;
+constexpr int kSortWarps = 8;  // warps per CTA
+constexpr int kSortThreads = kSortWarps * 32;
+constexpr int kSortUnroll = 4;  // rounds of 32 keys loaded ahead per warp
+
+struct SortPlan {
+    int64_t n;
+    int grid;           // CTAs
+    int64_t warps;      // grid * kSortWarps
+    int64_t chunk;      // keys per warp (multiple of 32)
+    int64_t table;      // kRadix * warps
+};
+
+static SortPlan make_plan(int64_t n) {
+    SortPlan p;
+    p.n = n;
+    // at least 32*kSortUnroll*4 keys per warp so tiny inputs do not fan out into empty warps
+    int64_t min_chunk = 32 * kSortUnroll * 4;
+    int64_t want_warps = ceil_div(n > 0 ? n : 1, min_chunk);
+    int64_t max_warps = (int64_t)kNumSMs * 4 * kSortWarps;  // 4 CTAs of 8 warps per SM
+    int64_t warps = want_warps < max_warps ? want_warps : max_warps;
+    p.grid = (int)ceil_div(warps, kSortWarps);
+    p.warps = (int64_t)p.grid * kSortWarps;
+    p.chunk = ceil_div(ceil_div(n > 0 ? n : 1, p.warps), 32) * 32;
+    p.table = (int64_t)kRadix * p.warps;
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan (u32), reduce-then-scan over up to kScanMaxBlocks contiguous chunks
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr int kScanMaxBlocks = 592;  // 4 x 148
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// Block-wide exclusive scan of one value per thread; returns the exclusive prefix, *total = sum.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* smem_warp /*[32]*/,
+                                                    uint32_t* total) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = warp_incl_scan(v, lane);
+    if (lane == 31) smem_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < (blockDim.x >> 5) ? smem_warp[lane] : 0;
+        uint32_t wi = warp_incl_scan(w, lane);
+        smem_warp[lane] = wi - w;  // exclusive warp offsets
+        if (lane == 31) smem_warp[32] = wi;
+    }
+    __syncthreads();
+    uint32_t r = smem_warp[warp] + incl - v;
+    *total = smem_warp[32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t* __restrict__ in,
+                                                                   int64_t n, int64_t chunk,
+                                                                   uint32_t* __restrict__ partial) {
+    __shared__ uint32_t sw[33];
+    int64_t beg = (int64_t)blockIdx.x * chunk;
+    int64_t end = beg + chunk < n ? beg + chunk : n;
+    uint32_t s = 0;
+    for (int64_t i = beg + threadIdx.x; i < end; i += kScanThreads) s += in[i];
+    uint32_t total;
+    block_excl_scan(s, sw, &total);
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_partials_kernel(uint32_t* partial, int nb) {
+    __shared__ uint32_t sw[33];
+    uint32_t v = (int)threadIdx.x < nb ? partial[threadIdx.x] : 0;
+    uint32_t total;
+    uint32_t ex = block_excl_scan(v, sw, &total);
+    if ((int)threadIdx.x < nb) partial[threadIdx.x] = ex;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in,
+                                                                  uint32_t* __restrict__ out,
+                                                                  int64_t n, int64_t chunk,
+                                                                  const uint32_t* __restrict__ partial) {
+    __shared__ uint32_t sw[33];
+    int64_t beg = (int64_t)blockIdx.x * chunk;
+    int64_t end = beg + chunk < n ? beg + chunk : n;
+    uint32_t carry = partial ? partial[blockIdx.x] : 0;
+    for (int64_t t0 = beg; t0 < end; t0 += kScanTile) {
+        int64_t i0 = t0 + (int64_t)threadIdx.x * kScanItems;
+        uint32_t v[kScanItems];
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            v[k] = (i0 + k < end) ? in[i0 + k] : 0;
+            s += v[k];
+        }
+        uint32_t total;
+        uint32_t ex = block_excl_scan(s, sw, &total) + carry;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) {
+            if (i0 + k < end) out[i0 + k] = ex;
+            ex += v[k];
+        }
+        carry += total;
+    }
+}
+
+size_t scan_workspace_bytes() { return 256 + kScanMaxBlocks * sizeof(uint32_t); }
+
+// in/out may alias. ws: scan_workspace_bytes().
+int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, void* ws, cudaStream_t st) {
+    if (n <= 0) return GG_OK;
+    if (n <= 8 * kScanTile) {
+        scan_apply_kernel<<<1, kScanThreads, 0, st>>>(in, out, n, n, nullptr);
+        GG_LAUNCHED();
+        return GG_OK;
+    }
+    int64_t nb = ceil_div(n, (int64_t)kScanTile * 2);
+    if (nb > kScanMaxBlocks) nb = kScanMaxBlocks;
+    int64_t chunk = ceil_div(ceil_div(n, nb), kScanTile) * kScanTile;
+    nb = ceil_div(n, chunk);
+    uint32_t* partial = static_cast<uint32_t*>(ws);
+    scan_reduce_kernel<<<(int)nb, kScanThreads, 0, st>>>(in, n, chunk, partial);
+    GG_LAUNCHED();
+    scan_partials_kernel<<<1, kScanThreads, 0, st>>>(partial, (int)nb);
+    GG_LAUNCHED();
+    scan_apply_kernel<<<(int)nb, kScanThreads, 0, st>>>(in, out, n, chunk, partial);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// radix passes
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t* __restrict__ keys,
+                                                                  int64_t n, int shift,
+                                                                  uint32_t mask, int64_t chunk,
+                                                                  int64_t warps,
+                                                                  uint32_t* __restrict__ counts) {
+    __shared__ uint32_t hist[kSortWarps][kRadix];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t gw = (int64_t)blockIdx.x * kSortWarps + w;
+    for (int d = lane; d < kRadix; d += 32) hist[w][d] = 0;
+    __syncwarp();
+    int64_t beg = gw * chunk;
+    int64_t end = beg + chunk < n ? beg + chunk : n;
+    for (int64_t i = beg + lane; i < end; i += 32) {
+        uint32_t d = (keys[i] >> shift) & mask;
+        atomicAdd(&hist[w][d], 1u);  // counts only: the total is order-independent
+    }
+    __syncwarp();
+    for (int d = lane; d < kRadix; d += 32) counts[(int64_t)d * warps + gw] = hist[w][d];
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+    radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                         uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
+                         int shift, uint32_t mask, int64_t chunk, int64_t warps,
+                         const uint32_t* __restrict__ offsets) {
+    __shared__ uint32_t cursor[kSortWarps][kRadix];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t gw = (int64_t)blockIdx.x * kSortWarps + w;
+    for (int d = lane; d < kRadix; d += 32) cursor[w][d] = offsets[(int64_t)d * warps + gw];
+    __syncwarp();
+    int64_t beg = gw * chunk;
+    int64_t end = beg + chunk < n ? beg + chunk : n;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    for (int64_t i = beg; i < end; i += 32 * kSortUnroll) {
+        uint32_t k[kSortUnroll], v[kSortUnroll];
+#pragma unroll
+        for (int u = 0; u < kSortUnroll; ++u) {
+            int64_t idx = i + u * 32 + lane;
+            bool ok = idx < end;
+            k[u] = ok ? keys_in[idx] : 0u;
+            // vals_in == nullptr: the value is the input position (first pass of an argsort)
+            v[u] = ok ? (vals_in ? vals_in[idx] : (uint32_t)idx) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < kSortUnroll; ++u) {
+            int64_t idx = i + u * 32 + lane;
+            bool ok = idx < end;
+            uint32_t d = (k[u] >> shift) & mask;
+            // lanes past the end get a digit nobody else has, so they never join a peer group
+            uint32_t peers = __match_any_sync(0xffffffffu, ok ? d : (uint32_t)(kRadix + lane));
+            uint32_t rank = __popc(peers & lt_mask);
+            uint32_t pos = ok ? cursor[w][d] + rank : 0u;
+            __syncwarp();
+            if (ok) {
+                keys_out[pos] = k[u];
+                vals_out[pos] = v[u];
+                if (rank == 0) cursor[w][d] += __popc(peers);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+size_t gg_sort_pairs_workspace_bytes(int64_t n) {
+    SortPlan p = make_plan(n);
+    size_t b = 0;
+    b += align_up((size_t)(n > 0 ? n : 1) * 4, 256) * 2;  // ping-pong keys / vals
+    b += align_up((size_t)p.table * 4, 256);
+    b += align_up(scan_workspace_bytes(), 256);
+    return b + 256;
+}
+
+int gg_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
+                      uint32_t* vals_out, int64_t n, int key_bits, void* workspace,
+                      size_t workspace_bytes, gg_stream_t stream) {
+    GG_REQUIRE(n >= 0 && n < (int64_t)1 << 31, "gg_sort_pairs_u32: n=%lld out of range", (long long)n);
+    GG_REQUIRE(key_bits >= 0 && key_bits <= 32, "gg_sort_pairs_u32: key_bits=%d", key_bits);
+    if (n == 0) return GG_OK;
+    GG_REQUIRE(keys_in && keys_out && vals_out && workspace, "gg_sort_pairs_u32: null pointer");
+    if (workspace_bytes < gg_sort_pairs_workspace_bytes(n)) {
+        set_error("gg_sort_pairs_u32: workspace %zu < %zu", workspace_bytes,
+                  gg_sort_pairs_workspace_bytes(n));
+        return GG_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    SortPlan p = make_plan(n);
+    Carver c(workspace);
+    uint32_t* tmp_k = c.take<uint32_t>(n);
+    uint32_t* tmp_v = c.take<uint32_t>(n);
+    uint32_t* counts = c.take<uint32_t>(p.table);
+    void* scan_ws = c.take<char>(scan_workspace_bytes());
+
+    int passes = (key_bits + kRadixBits - 1) / kRadixBits;
+    if (passes < 1) passes = 1;
+    int bits = (key_bits + passes - 1) / passes;
+    if (bits < 1) bits = 1;
+    uint32_t mask = (1u << bits) - 1u;
+
+    const uint32_t* src_k = keys_in;
+    const uint32_t* src_v = vals_in;
+    for (int pass = 0; pass < passes; ++pass) {
+        bool to_out = ((passes - pass) & 1) != 0;
+        uint32_t* dst_k = to_out ? keys_out : tmp_k;
+        uint32_t* dst_v = to_out ? vals_out : tmp_v;
+        int shift = pass * bits;
+        radix_hist_kernel<<<p.grid, kSortThreads, 0, st>>>(src_k, n, shift, mask, p.chunk, p.warps,
+                                                          counts);
+        GG_LAUNCHED();
+        int rc = exclusive_scan_u32(counts, counts, p.table, scan_ws, st);
+        if (rc != GG_OK) return rc;
+        radix_scatter_kernel<<<p.grid, kSortThreads, 0, st>>>(src_k, src_v, dst_k, dst_v, n, shift,
+                                                             mask, p.chunk, p.warps, counts);
+        GG_LAUNCHED();
+        src_k = dst_k;
+        src_v = dst_v;
+    }
+    return GG_OK;
+}
+
+}  // extern "C"

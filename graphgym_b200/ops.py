@@ -1,0 +1,290 @@
+"""Tensor-level wrappers over the C-ABI (include/gg_b200.h).
+
+torch is used for device memory and streams only: every function checks its tensors, pulls raw
+device pointers and calls one ``gg_*`` entry point on the current CUDA stream.  CPU tensors are
+rejected — there is no CPU path in this package.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GemmSegment, check, lib
+
+LOOPS_KEEP, LOOPS_ADD_REMAINING, LOOPS_REMOVE_ADD, LOOPS_REMOVE, LOOPS_ADD = range(5)
+BY_TARGET, BY_SOURCE = 0, 1
+SUM, MEAN = 0, 1
+ACT_NONE, ACT_RELU = 0, 1
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("graphgym_b200 ops run on CUDA tensors only (no CPU fallback); "
+                               f"got a tensor on {t.device}")
+
+
+def _rows(t, name):
+    """(tensor, leading dimension) of a 2-D fp32 matrix with unit inner stride."""
+    if t.dtype != torch.float32 or t.dim() != 2:
+        raise ValueError(f"{name}: expected a 2-D float32 tensor, got {tuple(t.shape)} {t.dtype}")
+    if t.size(1) > 1 and t.stride(1) != 1:
+        t = t.contiguous()
+    if t.size(0) > 1 and t.stride(0) < t.size(1):
+        t = t.contiguous()
+    ld = t.stride(0) if t.size(0) > 1 else max(t.size(1), 1)
+    return t, ld
+
+
+def launch_count():
+    return int(lib().gg_launch_count())
+
+
+# --------------------------------------------------------------------------------------------
+# layout
+# --------------------------------------------------------------------------------------------
+class Csr:
+    """One compressed layout of an (edited) edge list: segments grouped by target or by source."""
+    __slots__ = ("rowptr", "nbr", "perm", "rowid", "num_slots", "num_nodes", "num_edges", "policy",
+                 "group_by")
+
+    def __init__(self, rowptr, nbr, perm, rowid, num_slots, num_nodes, num_edges, policy, group_by):
+        self.rowptr, self.nbr, self.perm, self.rowid = rowptr, nbr, perm, rowid
+        self.num_slots, self.num_nodes, self.num_edges = num_slots, num_nodes, num_edges
+        self.policy, self.group_by = policy, group_by
+
+
+def layout_build(edge_index, num_nodes, policy=LOOPS_KEEP, group_by=BY_TARGET):
+    """COO ``edge_index[2,E]`` (int64, row 0 = source, row 1 = target) -> Csr.  One host sync to
+    read E' (self-loop removal makes it data dependent)."""
+    _need_cuda(edge_index)
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError(f"edge_index must be int64 [2,E], got {tuple(edge_index.shape)} {edge_index.dtype}")
+    ei = edge_index.contiguous()
+    E, N = ei.size(1), int(num_nodes)
+    L = lib()
+    cap = int(L.gg_layout_capacity(E, N, policy))
+    dev = ei.device
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    nbr = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    perm = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    rowid = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    ws_bytes = int(L.gg_layout_build_workspace_bytes(E, N, policy))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(L.gg_layout_build(_ptr(ei), E, N, policy, group_by, _ptr(rowptr), _ptr(nbr), _ptr(perm),
+                            _ptr(rowid), _ptr(ws), ws_bytes, _stream()), "gg_layout_build")
+    bad = int(ws[:4].view(torch.int32).item())
+    if bad:
+        raise ValueError(f"edge_index holds {bad} edge(s) with an endpoint outside [0, {N})")
+    num_slots = int(rowptr[N].item())
+    return Csr(rowptr, nbr[:num_slots], perm[:num_slots], rowid[:num_slots], num_slots, N, E, policy,
+               group_by)
+
+
+def sort_pairs(keys, vals, key_bits):
+    """Stable sort of u32 pairs (int32 tensors reinterpret as u32)."""
+    _need_cuda(keys, vals)
+    n = keys.numel()
+    L = lib()
+    ko, vo = torch.empty_like(keys), torch.empty_like(keys)
+    ws_bytes = int(L.gg_sort_pairs_workspace_bytes(n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+    check(L.gg_sort_pairs_u32(_ptr(keys), _ptr(vals), _ptr(ko), _ptr(vo), n, key_bits, _ptr(ws),
+                              ws_bytes, _stream()), "gg_sort_pairs_u32")
+    return ko, vo
+
+
+def slot_map(a, b):
+    """map[t] = slot of layout ``a`` that holds the same edge as slot t of layout ``b``."""
+    assert a.num_slots == b.num_slots
+    scratch = torch.empty(a.num_edges + a.num_nodes + 1, dtype=torch.int32, device=a.perm.device)
+    out = torch.empty(max(b.num_slots, 1), dtype=torch.int32, device=a.perm.device)[:b.num_slots]
+    check(lib().gg_layout_slot_map(_ptr(a.perm), _ptr(b.perm), a.num_slots, a.num_edges, a.num_nodes,
+                                   _ptr(scratch), _ptr(out), _stream()), "gg_layout_slot_map")
+    return out
+
+
+def slot_weights(csr, edge_index=None, edge_weight=None, loop_fill=1.0):
+    dev = csr.perm.device
+    out = torch.empty(max(csr.num_slots, 1), dtype=torch.float32, device=dev)[:csr.num_slots]
+    scratch = None
+    ei = None
+    if edge_weight is not None:
+        _need_cuda(edge_weight, edge_index)
+        edge_weight = edge_weight.contiguous().float()
+        ei = edge_index.contiguous()
+        scratch = torch.empty(max(csr.num_nodes, 1), dtype=torch.int32, device=dev)
+    check(lib().gg_layout_slot_weights(_ptr(csr.perm), csr.num_slots, _ptr(ei), _ptr(edge_weight),
+                                       csr.num_edges, csr.num_nodes, csr.policy, float(loop_fill),
+                                       _ptr(scratch), _ptr(out), _stream()), "gg_layout_slot_weights")
+    return out
+
+
+def segment_degree(csr, w_slot=None):
+    deg = torch.empty(max(csr.num_nodes, 1), dtype=torch.float32, device=csr.rowptr.device)[:csr.num_nodes]
+    check(lib().gg_segment_degree(_ptr(csr.rowptr), _ptr(w_slot), csr.num_nodes, _ptr(deg), _stream()),
+          "gg_segment_degree")
+    return deg
+
+
+def gcn_norm(csr, deg, w_slot=None):
+    out = torch.empty(max(csr.num_slots, 1), dtype=torch.float32, device=deg.device)[:csr.num_slots]
+    check(lib().gg_gcn_norm(_ptr(csr.rowid), _ptr(csr.nbr), _ptr(w_slot), _ptr(deg), csr.num_slots,
+                            _ptr(out), _stream()), "gg_gcn_norm")
+    return out
+
+
+def mean_weights(csr_t, deg):
+    """1/deg[nbr[s]] per slot of the transposed layout (backward of a mean aggregation)."""
+    out = torch.empty(max(csr_t.num_slots, 1), dtype=torch.float32, device=deg.device)[:csr_t.num_slots]
+    check(lib().gg_mean_weights(_ptr(csr_t.nbr), _ptr(deg), csr_t.num_slots, _ptr(out), _stream()),
+          "gg_mean_weights")
+    return out
+
+
+def id_count(ids, num_nodes):
+    _need_cuda(ids)
+    ids = ids.contiguous().long()
+    cnt = torch.empty(max(num_nodes, 1), dtype=torch.float32, device=ids.device)[:num_nodes]
+    check(lib().gg_id_count(_ptr(ids), ids.numel(), num_nodes, _ptr(cnt), _stream()), "gg_id_count")
+    return cnt
+
+
+# --------------------------------------------------------------------------------------------
+# aggregation
+# --------------------------------------------------------------------------------------------
+def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None, out=None):
+    """out[i,:] = reduce_{s in segment i} w[s]*x[nbr[s],:] + self_scale*x_self[i,:] + bias."""
+    _need_cuda(x, w_slot, x_self, bias, csr.rowptr)
+    x, ldx = _rows(x, "x")
+    n, f = csr.num_nodes, x.size(1)
+    if out is None:
+        out = torch.empty((n, f), dtype=torch.float32, device=x.device)
+    out_t, ldo = _rows(out, "out")
+    assert out_t is out, "out must have unit inner stride"
+    ld_self = 0
+    if x_self is not None:
+        x_self, ld_self = _rows(x_self, "x_self")
+    if bias is not None:
+        bias = bias.contiguous()
+    check(lib().gg_spmm_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(x), ldx, _ptr(out), ldo,
+                            n, f, reduce, _ptr(x_self), ld_self, float(self_scale), _ptr(bias),
+                            _stream()), "gg_spmm_f32")
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# dense transform
+# --------------------------------------------------------------------------------------------
+def id_gemm(segments, n, f, b_trans=False, bias=None, act=ACT_NONE, relu_mask=None, out=None):
+    """out = act(sum_g diag(scale_g) A_g B_g + bias) .* (relu_mask > 0).
+
+    ``segments``: list of (a [n,k], b [k,f] or [f,k] if b_trans, scale [n] or None)."""
+    if not 1 <= len(segments) <= _lib.GG_GEMM_MAX_SEGMENTS:
+        raise ValueError("id_gemm takes 1..4 K-segments")
+    arr = (GemmSegment * len(segments))()
+    keep = []
+    dev = None
+    for i, (a, b, scale) in enumerate(segments):
+        _need_cuda(a, b, scale)
+        a, lda = _rows(a, "a")
+        b, ldb = _rows(b, "b")
+        k = a.size(1)
+        if a.size(0) != n or (b.size(1) if b_trans else b.size(0)) != k or \
+                (b.size(0) if b_trans else b.size(1)) != f:
+            raise ValueError(f"id_gemm segment {i}: a {tuple(a.shape)} b {tuple(b.shape)} "
+                             f"b_trans={b_trans} do not give [{n},{f}]")
+        if scale is not None:
+            scale = scale.contiguous()
+            assert scale.dtype == torch.float32 and scale.numel() == n
+        keep += [a, b, scale]
+        arr[i] = GemmSegment(a.data_ptr(), lda, b.data_ptr(), ldb,
+                             scale.data_ptr() if scale is not None else None, k)
+        dev = a.device
+    if out is None:
+        out = torch.empty((n, f), dtype=torch.float32, device=dev)
+    out_t, ldo = _rows(out, "out")
+    assert out_t is out
+    ld_mask = 0
+    if relu_mask is not None:
+        relu_mask, ld_mask = _rows(relu_mask, "relu_mask")
+    if bias is not None:
+        bias = bias.contiguous()
+    check(lib().gg_id_gemm_f32(arr, len(segments), int(b_trans), n, f, _ptr(bias), act, _ptr(relu_mask),
+                               ld_mask, _ptr(out), ldo, _stream()), "gg_id_gemm_f32")
+    return out
+
+
+def gemm_tn(a, g, row_index=None):
+    """out[K,F] = sum_r a[row(r),:]^T g[row(r),:]."""
+    _need_cuda(a, g, row_index)
+    a, lda = _rows(a, "a")
+    g, ldg = _rows(g, "g")
+    k, f = a.size(1), g.size(1)
+    if row_index is not None:
+        row_index = row_index.contiguous().long()
+        n = row_index.numel()
+    else:
+        n = a.size(0)
+        assert g.size(0) == n
+    L = lib()
+    out = torch.empty((k, f), dtype=torch.float32, device=a.device)
+    ws_bytes = int(L.gg_gemm_tn_workspace_bytes(n, k, f))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+    check(L.gg_gemm_tn_f32(_ptr(a), lda, _ptr(row_index), _ptr(g), ldg, n, k, f, _ptr(out), max(f, 1),
+                           _ptr(ws), ws_bytes, _stream()), "gg_gemm_tn_f32")
+    return out
+
+
+def colsum(g):
+    _need_cuda(g)
+    g, ldg = _rows(g, "g")
+    n, f = g.shape
+    L = lib()
+    out = torch.empty(f, dtype=torch.float32, device=g.device)
+    ws_bytes = int(L.gg_colsum_workspace_bytes(n, f))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
+    check(L.gg_colsum_f32(_ptr(g), ldg, n, f, _ptr(out), _ptr(ws), ws_bytes, _stream()), "gg_colsum_f32")
+    return out
+
+
+def gather_rows(x, ids):
+    _need_cuda(x, ids)
+    x, ldx = _rows(x, "x")
+    ids = ids.contiguous().long()
+    m, f = ids.numel(), x.size(1)
+    out = torch.empty((m, f), dtype=torch.float32, device=x.device)
+    check(lib().gg_gather_rows_f32(_ptr(x), ldx, _ptr(ids), m, f, _ptr(out), max(f, 1), _stream()),
+          "gg_gather_rows_f32")
+    return out
+
+
+def scatter_add_rows_(out, ids, x):
+    """out[ids[r],:] += x[r,:] in place."""
+    _need_cuda(out, ids, x)
+    x, ldx = _rows(x, "x")
+    out_t, ldo = _rows(out, "out")
+    assert out_t is out
+    ids = ids.contiguous().long()
+    check(lib().gg_scatter_add_rows_f32(_ptr(x), ldx, _ptr(ids), ids.numel(), x.size(1), _ptr(out), ldo,
+                                        _stream()), "gg_scatter_add_rows_f32")
+    return out
+
+
+def relu_grad(g, y):
+    _need_cuda(g, y)
+    g, ldg = _rows(g, "g")
+    y, ldy = _rows(y, "y")
+    n, f = g.shape
+    out = torch.empty((n, f), dtype=torch.float32, device=g.device)
+    check(lib().gg_relu_grad_f32(_ptr(g), ldg, _ptr(y), ldy, n, f, _ptr(out), max(f, 1), _stream()),
+          "gg_relu_grad_f32")
+    return out

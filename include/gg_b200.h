@@ -1,0 +1,203 @@
+/*
+ * gg_b200.h — C-ABI of the B200-native GraphGym message-passing hot path.
+ *
+ * This is the drop-in boundary: everything the reference's layer code obtains from
+ * torch_geometric / torch_scatter / tf_geometric on the hot path is served by the
+ * entry points below (plain pointers and sizes, no torch types). The Python host
+ * side (graphgym_b200/) binds them with ctypes and keeps the reference's own layer
+ * API (`register_layer` / `layer_dict`, `forward(batch)`) on top.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name ends in `_host`;
+ *   - matrices are row-major fp32 with an explicit leading dimension (in elements);
+ *   - graph indices are int32 on the device (N, E' < 2^31); the COO input is the
+ *     reference's int64 `edge_index[2,E]` (row 0 = source j, row 1 = target i,
+ *     PyG `source_to_target` flow, graphgym/contrib/layer/idconv.py:177);
+ *   - `stream` is a `cudaStream_t` (passed as void* so C callers need no CUDA headers);
+ *   - return value 0 = OK, negative = gg_status; `gg_last_error()` returns the
+ *     thread-local message of the last failure; no exceptions cross the boundary;
+ *   - the caller allocates all outputs and workspaces (`*_workspace_bytes` queries);
+ *   - nothing here runs on the CPU: there is no fallback path.
+ *
+ * Citations `ref:` are relative to the reference repository root (JBanks/GraphGym).
+ */
+#ifndef GG_B200_H
+#define GG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+typedef void* gg_stream_t;
+
+enum gg_status {
+    GG_OK = 0,
+    GG_ERR_INVALID = -1,   /* bad argument (null pointer, negative size, misaligned row) */
+    GG_ERR_CUDA = -2,      /* a CUDA runtime call or launch failed                        */
+    GG_ERR_WORKSPACE = -3, /* workspace too small                                          */
+    GG_ERR_UNSUPPORTED = -4
+};
+
+int gg_version(void);
+const char* gg_last_error(void);
+/* Number of kernels this library has launched in this process (all threads). */
+int64_t gg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph layout.  The reference keeps COO and edits it with PyG helpers on
+ * every forward; we build CSR (grouped by target) / CSC (grouped by source) once per edge_index.
+ *
+ * Self-loop policy = the PyG helper the reference layer calls before propagate:
+ *   KEEP           nothing                                   (SAGEConv, GeneralIDConv w/o norm)
+ *   ADD_REMAINING  add_remaining_self_loops                  ref: idconv.py:52-53,140-141,232-233, identity.py:14-15
+ *   REMOVE_ADD     remove_self_loops + add_self_loops        ref: idconv.py:302-304 (GAT)
+ *   REMOVE         remove_self_loops                         ref: idconv.py:370 (GIN-ID)
+ *   ADD            add_self_loops / tfg add_self_loop_edge   ref: sparse_adj.py:58-63, TfgIDLayer.py:298
+ * The edited edge list is: kept original edges in their original order, then one (i,i) per node
+ * i = 0..N-1 (policies that add).  The layout is the STABLE counting sort of that list by the
+ * group key (ties keep list order; duplicates are kept; nothing is coalesced).
+ *
+ * Outputs (caller-allocated; cap = gg_layout_capacity(E, N, policy)):
+ *   rowptr[N+1]  segment offsets; rowptr[N] = E' (number of slots actually used)
+ *   nbr[cap]     the other endpoint of each slot (source if grouped by target, and vice versa)
+ *   perm[cap]    id of the slot's edge: e in [0,E) = original column of edge_index,
+ *                E + i = the appended self loop of node i
+ *   rowid[cap]   group key of each slot (nullable)
+ * ------------------------------------------------------------------------------------------ */
+enum gg_loop_policy {
+    GG_LOOPS_KEEP = 0,
+    GG_LOOPS_ADD_REMAINING = 1,
+    GG_LOOPS_REMOVE_ADD = 2,
+    GG_LOOPS_REMOVE = 3,
+    GG_LOOPS_ADD = 4
+};
+enum gg_group_by { GG_BY_TARGET = 0, GG_BY_SOURCE = 1 };
+
+int64_t gg_layout_capacity(int64_t num_edges, int64_t num_nodes, int policy);
+size_t gg_layout_build_workspace_bytes(int64_t num_edges, int64_t num_nodes, int policy);
+int gg_layout_build(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int policy,
+                    int group_by, int32_t* rowptr, int32_t* nbr, int32_t* perm, int32_t* rowid,
+                    void* workspace, size_t workspace_bytes, gg_stream_t stream);
+
+/* Stable LSD radix sort of (key,value) u32 pairs on keys < 2^key_bits (the engine under
+ * gg_layout_build, exported for the ego-net and halo code). */
+size_t gg_sort_pairs_workspace_bytes(int64_t n);
+int gg_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
+                      uint32_t* vals_out, int64_t n, int key_bits, void* workspace,
+                      size_t workspace_bytes, gg_stream_t stream);
+
+/* inv[perm_a[s]] = s, then map[t] = inv[perm_b[t]]: slot of layout A holding the same edge as slot t
+ * of layout B (CSC slot -> CSR slot).  `scratch` holds num_edges + num_nodes int32. */
+int gg_layout_slot_map(const int32_t* perm_a, const int32_t* perm_b, int64_t num_slots,
+                       int64_t num_edges, int64_t num_nodes, int32_t* scratch, int32_t* map,
+                       gg_stream_t stream);
+
+/* Per-slot edge weights of the edited list: w_slot[s] = w_edge[perm[s]] for original edges (1 when
+ * w_edge is null), `loop_fill` for appended loops; with ADD_REMAINING and w_edge given, an appended
+ * loop inherits the weight of the LAST removed (i,i) edge (PyG add_remaining_self_loops).
+ * `edge_index` may be null when w_edge is null. */
+int gg_layout_slot_weights(const int32_t* perm, int64_t num_slots, const int64_t* edge_index,
+                           const float* w_edge, int64_t num_edges, int64_t num_nodes, int policy,
+                           float loop_fill, int32_t* scratch_nodes, float* w_slot,
+                           gg_stream_t stream);
+
+/* Weighted degree per group: deg[i] = sum_{s in segment i} w_slot[s] (w_slot null => segment length),
+ * summed in slot order (deterministic).  ref: scatter_add(edge_weight,row) idconv.py:56,144;
+ * SparseAdj.reduce_sum sparse_adj.py:84-85. */
+int gg_segment_degree(const int32_t* rowptr, const float* w_slot, int64_t num_nodes, float* deg,
+                      gg_stream_t stream);
+
+/* Symmetric GCN normalisation per slot: w_out[s] = dis[rowid[s]] * w_in[s] * dis[nbr[s]],
+ * dis = deg^-1/2 with inf -> 0.  `deg` is the degree the reference uses: summed over
+ * edge_index[0] (source) in idconv.py:143-148 / identity.py:17-22, over the target in PyG>=1.6
+ * GCNConv (layer.py:138); the caller passes whichever applies.  w_in null => 1. */
+int gg_gcn_norm(const int32_t* rowid, const int32_t* nbr, const float* w_in, const float* deg,
+                int64_t num_slots, float* w_out, gg_stream_t stream);
+
+/* Transposed weights of a mean aggregation: w_out[s] = 1/deg[nbr[s]] (0 when deg is 0); with the
+ * CSC layout and deg = in-degree this is d(mean_i)/d(x_j) per slot (ref: aggr='mean', idconv.py:195). */
+int gg_mean_weights(const int32_t* nbr, const float* deg, int64_t num_slots, float* w_out,
+                    gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Aggregation:  out[i,:] = epi( sum_{s in segment i} w[s] * x[nbr[s],:] )
+ *   ref: MessagePassing.propagate + message idconv.py:89-92,177-180,235-239,371,378-379;
+ *        SparseAdj.matmul sparse_adj.py:91-97.
+ *   reduce: 0 = sum, 1 = mean (divide by segment length; empty segment -> 0).
+ *   epilogue: out = agg + self_scale * x_self[i,:] (x_self nullable; GIN's (1+eps)*x, idconv.py:371)
+ *                       + bias[:] (nullable).
+ * The backward wrt x is the same call on the transposed layout (CSC) with the transposed weights.
+ * Rows of x / out / x_self must be 16-byte aligned when f % 4 == 0 (vector path); any f works.
+ * ------------------------------------------------------------------------------------------ */
+enum gg_reduce { GG_SUM = 0, GG_MEAN = 1 };
+int gg_spmm_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, const float* x,
+                int64_t ldx, float* out, int64_t ldo, int64_t num_rows, int64_t f, int reduce,
+                const float* x_self, int64_t ld_self, float self_scale, const float* bias,
+                gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense transform with ID-GNN heterogeneous weights:
+ *   out[N,F] = act( sum_g diag(scale_g) * A_g[N,K_g] * B_g  + bias ) (.* mask>0)
+ * up to GG_GEMM_MAX_SEGMENTS K-segments accumulate into the same output tile, so
+ *   X*W + onehot(id)*(X*W_id)   (ref: idconv.py:64-67,152-155,248-251,307-310,372-375)
+ * is ONE pass: segment 0 = (X, W, scale null), segment 1 = (X, W_id, scale = multiplicity of the
+ * row in `id`, 0 for non-centres; tiles whose rows all have scale 0 skip the segment).
+ *   b_trans = 0: B_g is [K_g, F] row-major;  1: B_g is [F, K_g] row-major (used for dX = dH * W^T).
+ * ------------------------------------------------------------------------------------------ */
+#define GG_GEMM_MAX_SEGMENTS 4
+typedef struct gg_gemm_segment {
+    const float* a;     /* [n, k] */
+    int64_t lda;
+    const float* b;     /* [k, f] or [f, k] if b_trans */
+    int64_t ldb;
+    const float* scale; /* [n] row multipliers, nullable */
+    int64_t k;
+} gg_gemm_segment;
+enum gg_act { GG_ACT_NONE = 0, GG_ACT_RELU = 1 };
+int gg_id_gemm_f32(const gg_gemm_segment* segments_host, int num_segments, int b_trans, int64_t n,
+                   int64_t f, const float* bias, int act, const float* relu_mask, int64_t ld_mask,
+                   float* out, int64_t ldo, gg_stream_t stream);
+
+/* Weight gradient: out[K,F] = sum_{r<n} A[row(r),:]^T * G[row(r),:], row(r) = row_index ? row_index[r] : r
+ * (dW = X^T dH over all N rows; dW_id = X[id]^T dH[id] over the M centre rows, duplicates counted
+ * like index_add_, ref: idconv.py:64-67).  Deterministic two-stage split over rows. */
+size_t gg_gemm_tn_workspace_bytes(int64_t n, int64_t k, int64_t f);
+int gg_gemm_tn_f32(const float* a, int64_t lda, const int64_t* row_index, const float* g, int64_t ldg,
+                   int64_t n, int64_t k, int64_t f, float* out, int64_t ldo, void* workspace,
+                   size_t workspace_bytes, gg_stream_t stream);
+
+/* Column sums (bias gradient): out[f] = sum_r g[r,f], fixed-order two-stage reduction.
+ * workspace: gg_colsum_workspace_bytes. */
+size_t gg_colsum_workspace_bytes(int64_t n, int64_t f);
+int gg_colsum_f32(const float* g, int64_t ldg, int64_t n, int64_t f, float* out, void* workspace,
+                  size_t workspace_bytes, gg_stream_t stream);
+
+/* centre multiplicity: count[r] = number of occurrences of r in id[0..m) (index_add_ semantics:
+ * duplicates add twice, idconv.py:67). count must hold n floats. */
+int gg_id_count(const int64_t* id, int64_t m, int64_t n, float* count, gg_stream_t stream);
+
+/* Row gather / scatter-add / ReLU gradient used by the GIN-ID branch (ref: idconv.py:372-375):
+ *   gather:      out[r,:]      = x[id[r],:]
+ *   scatter_add: out[id[r],:] += x[r,:]      (atomicAdd: exact order-independence only for unique id,
+ *                                             which node_id_index is, transform.py:38)
+ *   relu_grad:   out = g .* (y > 0) */
+int gg_gather_rows_f32(const float* x, int64_t ldx, const int64_t* id, int64_t m, int64_t f, float* out,
+                       int64_t ldo, gg_stream_t stream);
+int gg_scatter_add_rows_f32(const float* x, int64_t ldx, const int64_t* id, int64_t m, int64_t f,
+                            float* out, int64_t ldo, gg_stream_t stream);
+int gg_relu_grad_f32(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t n, int64_t f,
+                     float* out, int64_t ldo, gg_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* GG_B200_H */

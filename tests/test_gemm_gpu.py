@@ -1,0 +1,85 @@
+"""Multi-segment ID GEMM, weight-gradient GEMM and column sums vs fp64 torch on the CPU."""
+import pytest
+import torch
+
+from graphgym_b200 import ops
+from util import FP32_TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('n,k,f', [(1, 1, 1), (37, 12, 16), (300, 1433, 128), (1000, 100, 128),
+                                   (513, 128, 256), (129, 7, 130), (64, 1, 128), (2000, 256, 256)])
+@pytest.mark.parametrize('b_trans', [False, True])
+def test_id_gemm_two_segments(cuda, n, k, f, b_trans):
+    g = torch.Generator().manual_seed(n + k + f)
+    x = torch.randn(n, k, generator=g)
+    w = torch.randn(f, k, generator=g) if b_trans else torch.randn(k, f, generator=g)
+    w_id = torch.randn(f, k, generator=g) if b_trans else torch.randn(k, f, generator=g)
+    ids = torch.randint(0, n, (max(1, n // 7),), generator=g)  # duplicates on purpose
+    cnt = ops.id_count(ids.to(cuda), n)
+    assert torch.equal(cnt.cpu(), torch.bincount(ids, minlength=n).float())
+    bias = torch.randn(f, generator=g)
+    got = ops.id_gemm([(x.to(cuda), w.to(cuda), None), (x.to(cuda), w_id.to(cuda), cnt)], n, f,
+                      b_trans=b_trans, bias=bias.to(cuda))
+    wd, wid = (w.double().t(), w_id.double().t()) if b_trans else (w.double(), w_id.double())
+    want = x.double() @ wd
+    want.index_add_(0, ids, x.double()[ids] @ wid)
+    want += bias.double()
+    assert rel_err(got, want) < FP32_TOL
+
+
+def test_id_gemm_relu_and_mask(cuda):
+    g = torch.Generator().manual_seed(0)
+    n, k, f = 333, 64, 96
+    x, w = torch.randn(n, k, generator=g), torch.randn(k, f, generator=g)
+    m = torch.randn(n, f, generator=g)
+    got = ops.id_gemm([(x.to(cuda), w.to(cuda), None)], n, f, act=ops.ACT_RELU)
+    assert rel_err(got, (x.double() @ w.double()).relu()) < FP32_TOL
+    got = ops.id_gemm([(x.to(cuda), w.to(cuda), None)], n, f, relu_mask=m.to(cuda))
+    assert rel_err(got, (x.double() @ w.double()) * (m > 0)) < FP32_TOL
+
+
+def test_id_gemm_skips_tiles_without_centres(cuda):
+    """Centres only in the first rows (the ego-net batch layout): later tiles skip the ID segment."""
+    g = torch.Generator().manual_seed(1)
+    n, k, f = 1000, 32, 64
+    x, w, w_id = torch.randn(n, k, generator=g), torch.randn(k, f, generator=g), torch.randn(k, f, generator=g)
+    ids = torch.arange(40)
+    cnt = ops.id_count(ids.to(cuda), n)
+    got = ops.id_gemm([(x.to(cuda), w.to(cuda), None), (x.to(cuda), w_id.to(cuda), cnt)], n, f)
+    want = x.double() @ w.double()
+    want[:40] += x.double()[:40] @ w_id.double()
+    assert rel_err(got, want) < FP32_TOL
+
+
+@pytest.mark.parametrize('n,k,f', [(1, 3, 5), (1000, 12, 16), (5000, 1433, 128), (100000, 128, 128),
+                                   (777, 100, 256)])
+def test_gemm_tn(cuda, n, k, f):
+    g = torch.Generator().manual_seed(n)
+    a, gr = torch.randn(n, k, generator=g), torch.randn(n, f, generator=g)
+    got = ops.gemm_tn(a.to(cuda), gr.to(cuda))
+    assert rel_err(got, a.double().t() @ gr.double()) < FP32_TOL
+    ids = torch.randint(0, n, (max(1, n // 9),), generator=g)
+    got = ops.gemm_tn(a.to(cuda), gr.to(cuda), ids.to(cuda))
+    assert rel_err(got, a.double()[ids].t() @ gr.double()[ids]) < FP32_TOL
+    assert torch.equal(got, ops.gemm_tn(a.to(cuda), gr.to(cuda), ids.to(cuda)))  # deterministic
+
+
+@pytest.mark.parametrize('n,f', [(1, 1), (1000, 128), (100000, 256), (333, 1433)])
+def test_colsum(cuda, n, f):
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(n))
+    assert rel_err(ops.colsum(x.to(cuda)), x.double().sum(0)) < FP32_TOL
+
+
+def test_row_helpers(cuda):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(50, 20, generator=g)
+    ids = torch.randperm(50, generator=g)[:13]
+    assert torch.equal(ops.gather_rows(x.to(cuda), ids.to(cuda)).cpu(), x[ids])
+    base = torch.randn(50, 20, generator=g)
+    upd = torch.randn(13, 20, generator=g)
+    got = ops.scatter_add_rows_(base.clone().to(cuda), ids.to(cuda), upd.to(cuda)).cpu()
+    assert torch.equal(got, base.index_add(0, ids, upd))
+    y = torch.randn(50, 20, generator=g)
+    assert torch.equal(ops.relu_grad(x.to(cuda), y.to(cuda)).cpu(), x * (y > 0))

@@ -1,0 +1,90 @@
+"""Host-side logic that needs no GPU: registry contract, config loading, parameter naming, the
+no-CPU-fallback rule."""
+import os
+
+import pytest
+import torch
+
+from graphgym_b200 import register
+from graphgym_b200.config import cfg, load_cfg, reset_cfg
+from graphgym_b200.models.layer import Batch, GeneralLayer, TFG_ALIASES, layer_dict, resolve_layer
+
+
+def test_registry_names_and_duplicate_key_error():
+    for name in ('gcnconv', 'sageconv', 'ginconv', 'idconv', 'gcnidconv', 'sageidconv', 'ginidconv'):
+        assert name in layer_dict
+    with pytest.raises(KeyError, match='Key gcnidconv is already pre-defined.'):
+        register.register_layer('gcnidconv', object)
+    register.register_layer('my_test_layer', object)
+    assert register.layer_dict['my_test_layer'] is object
+    del register.layer_dict['my_test_layer']
+
+
+def test_tfg_aliases_cover_main_zd_names():
+    assert set(TFG_ALIASES) == {'Tfg-gcnconv', 'Tfg-sageconv', 'Tfg-gatconv', 'Tfg-ginconv', 'Tfg-idgcn',
+                                'Tfg-idsage', 'Tfg-idgat', 'Tfg-idgin'}
+    assert resolve_layer('Tfg-idsage') is layer_dict['sageidconv']
+
+
+def test_parameter_names_match_reference_state_dict():
+    """checkpoint round-trip contract: weight / weight_id / bias / nn.* names."""
+    reset_cfg()
+    l = layer_dict['gcnidconv'](5, 7, bias=True)
+    assert sorted(dict(l.named_parameters())) == ['model.bias', 'model.weight', 'model.weight_id']
+    assert l.model.weight.shape == (5, 7) and l.model.bias.abs().sum() == 0
+    a = (6.0 / 12) ** 0.5
+    assert l.model.weight.abs().max() <= a
+    l = layer_dict['sageidconv'](5, 7, bias=False)
+    assert l.model.weight.shape == (10, 7) and l.model.bias is None
+    l = layer_dict['ginidconv'](5, 7)
+    assert 'model.nn_id.2.weight' in dict(l.named_parameters()) and 'model.eps' in l.state_dict()
+    l = layer_dict['sageconv'](5, 7, bias=True)
+    assert sorted(dict(l.named_parameters())) == ['model.lin_l.bias', 'model.lin_l.weight', 'model.lin_r.weight']
+
+
+def test_general_idconv_reads_cfg_at_construction():
+    reset_cfg()
+    cfg.gnn.agg, cfg.gnn.normalize_adj = 'mean', True
+    l = layer_dict['idconv'](3, 3)
+    assert l.model.aggr == 'mean' and l.model.normalize is True
+    cfg.gnn.agg = 'max'
+    with pytest.raises(NotImplementedError):
+        layer_dict['idconv'](3, 3)
+    reset_cfg()
+
+
+def test_general_layer_bias_follows_batchnorm():
+    reset_cfg()
+    assert GeneralLayer('gcnconv', 4, 4).layer.model.bias is None
+    cfg.gnn.batchnorm = False
+    assert GeneralLayer('gcnconv', 4, 4).layer.model.bias is not None
+    reset_cfg()
+
+
+def test_load_reference_yaml(tmp_path):
+    p = tmp_path / 'c.yaml'
+    p.write_text('gnn:\n  layers_mp: 3\n  dim_inner: 128\n  layer_type: Tfg-idgcn\n  agg: add\n'
+                 'dataset:\n  transform: ego\n  augment_feature: [node_identity]\n  augment_feature_dims: [10]\n')
+    reset_cfg()
+    load_cfg(str(p))
+    assert cfg.gnn.dim_inner == 128 and cfg.gnn.layer_type == 'Tfg-idgcn' and cfg.gnn.batchnorm is True
+    assert cfg.dataset.transform == 'ego' and cfg.dataset.augment_feature_dims == [10]
+    reset_cfg()
+
+
+def test_no_cpu_fallback():
+    """CPU tensors must fail loudly — the oracle is never reachable from the product path."""
+    reset_cfg()
+    l = layer_dict['gcnconv'](4, 4)
+    b = Batch(torch.randn(5, 4), torch.tensor([[0, 1], [1, 0]]))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        l(b)
+
+
+def test_product_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for dirpath, _, files in os.walk(os.path.join(root, 'graphgym_b200')):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, f

@@ -1,0 +1,160 @@
+"""Layer parity, forward and backward, through the reference's own layer API (layer_dict[name](dim_in,
+dim_out, bias) + forward(batch)):
+  * against the golden vectors produced by the REFERENCE'S OWN idconv.py (tests/golden/),
+  * against the CPU oracle on larger seeded graphs, for the built-in and the ID layers.
+Tolerance: 1e-5 relative (north_star, fp32), norm-wise (util.rel_err)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from graphgym_b200.config import cfg, reset_cfg
+from graphgym_b200.models.layer import Batch, GeneralLayer, layer_dict, resolve_layer
+from oracle import layers as olayers
+from util import FP32_TOL, powerlaw_graph, random_graph, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ours(layer, x, ei, ids, gy, dev):
+    layer = layer.to(dev)
+    xg = x.clone().to(dev).requires_grad_(True)
+    b = Batch(xg, ei.to(dev), ids.to(dev) if ids is not None else None)
+    out = layer(b)
+    assert out is b
+    y = b.node_feature
+    y.backward(gy.to(dev))
+    grads = {k: p.grad.detach().cpu() for k, p in layer.named_parameters()}
+    return y.detach().cpu(), xg.grad.detach().cpu(), grads
+
+
+GOLDEN_LAYERS = {'idconv': 'idconv', 'gcnidconv': 'gcnidconv', 'sageidconv': 'sageidconv',
+                 'ginidconv': 'ginidconv', 'gatidconv': 'gatidconv'}
+
+
+def test_golden_reference_id_layers(cuda, golden_dir):
+    d = np.load(os.path.join(golden_dir, 'idconv_layers.npz'))
+    checked = 0
+    for tag in [str(t) for t in d['tags']]:
+        name = tag.split('_')[0]
+        if name not in layer_dict:
+            continue
+        reset_cfg()
+        cfg.gnn.agg = 'mean' if 'agg-mean' in tag else 'add'
+        cfg.gnn.normalize_adj = 'normalize_adj-True' in tag
+        x = torch.from_numpy(d[tag + '/x'])
+        ei = torch.from_numpy(d[tag + '/edge_index'])
+        ids = torch.from_numpy(d[tag + '/ids'])
+        layer = layer_dict[name](x.size(1), d[tag + '/y'].shape[1], bias=True)
+        params = {k.split('/param/')[1]: torch.from_numpy(d[k]) for k in d.files
+                  if k.startswith(tag + '/param/')}
+        missing, unexpected = layer.load_state_dict(params, strict=False)
+        assert not unexpected and all(m.endswith('eps') for m in missing), (tag, missing, unexpected)
+        y, gx, grads = run_ours(layer, x, ei, ids, torch.from_numpy(d[tag + '/gy']), cuda)
+        assert rel_err(y, d[tag + '/y']) < FP32_TOL, tag
+        assert rel_err(gx, d[tag + '/gx']) < FP32_TOL, tag
+        for k, g in grads.items():
+            assert rel_err(g, d[tag + '/grad/' + k]) < FP32_TOL, (tag, k)
+        checked += 1
+    reset_cfg()
+    assert checked >= 8
+
+
+def _oracle(name, x, ei, ids, p):
+    P = {k: v.detach().clone().double().requires_grad_(True) for k, v in p.items()}
+    xd = x.double().requires_grad_(True)
+    if name == 'gcnconv':
+        y = olayers.gcnconv(xd, ei, P['model.weight'], P.get('model.bias'))
+    elif name == 'sageconv':
+        y = olayers.sageconv(xd, ei, P['model.lin_l.weight'], P.get('model.lin_l.bias'), P['model.lin_r.weight'])
+    elif name == 'ginconv':
+        y = olayers.ginconv(xd, ei, P['model.nn.0.weight'], P['model.nn.0.bias'], P['model.nn.2.weight'],
+                            P['model.nn.2.bias'])
+    elif name == 'gatconv':
+        y = olayers.gatconv(xd, ei, P['model.weight'], P['model.att'], P.get('model.bias'))
+    elif name == 'gcnidconv':
+        y = olayers.gcn_idconv(xd, ei, ids, P['model.weight'], P['model.weight_id'], P.get('model.bias'))
+    elif name == 'sageidconv':
+        y = olayers.sage_idconv(xd, ei, ids, P['model.weight'], P['model.weight_id'], P.get('model.bias'))
+    elif name == 'gatidconv':
+        y = olayers.gat_idconv(xd, ei, ids, P['model.weight'], P['model.weight_id'], P['model.att'],
+                               P.get('model.bias'))
+    elif name == 'ginidconv':
+        nn = [P['model.nn.%d.%s' % (i, w)] for i in (0, 2) for w in ('weight', 'bias')]
+        nn_id = [P['model.nn_id.%d.%s' % (i, w)] for i in (0, 2) for w in ('weight', 'bias')]
+        y = olayers.gin_idconv(xd, ei, ids, nn, nn_id)
+    else:
+        y = olayers.general_idconv(xd, ei, ids, P['model.weight'], P['model.weight_id'], P.get('model.bias'))
+    return xd, y, P
+
+
+@pytest.mark.parametrize('name', ['gcnconv', 'sageconv', 'ginconv', 'gatconv', 'idconv', 'gcnidconv',
+                                  'sageidconv', 'ginidconv', 'gatidconv'])
+@pytest.mark.parametrize('shape', [(500, 33, 64), (3000, 100, 128), (2708, 1433, 128)])
+def test_layers_against_oracle(cuda, name, shape):
+    if name not in layer_dict:
+        pytest.skip(f'{name} not built yet')
+    reset_cfg()
+    n, fin, fout = shape
+    torch.manual_seed(hash((name, shape)) % 1000)
+    ei = powerlaw_graph(n, n, 8) if n >= 2708 else random_graph(n, n, 6 * n, loops=n // 20, dups=n // 10)
+    g = torch.Generator().manual_seed(n + fin)
+    x = torch.randn(n, fin, generator=g)
+    ids = torch.randperm(n, generator=g)[: n // 10].sort().values
+    layer = layer_dict[name](fin, fout, bias=True)
+    with torch.no_grad():
+        for p in layer.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.3, 0.3)
+    params = {k: v.detach().clone() for k, v in layer.named_parameters()}
+    xd, yo, P = _oracle(name, x, ei, ids, params)
+    gy = torch.randn(n, fout, generator=g)
+    yo.backward(gy.double())
+    y, gx, grads = run_ours(layer, x, ei, ids, gy, cuda)
+    assert rel_err(y, yo.detach()) < FP32_TOL
+    assert rel_err(gx, xd.grad) < FP32_TOL
+    for k, gk in grads.items():
+        assert rel_err(gk, P[k].grad) < FP32_TOL, k
+
+
+def test_layout_cache_follows_in_place_edits(cuda):
+    """The layout cache is keyed on the tensor's version counter: an in-place edit rebuilds it."""
+    reset_cfg()
+    n = 50
+    ei = random_graph(1, n, 200).to(cuda)
+    x = torch.randn(n, 8).to(cuda)
+    layer = layer_dict['gcnconv'](8, 8, bias=False).to(cuda)
+    y1 = layer(Batch(x, ei)).node_feature.detach().clone()
+    ei[1, :50] = (ei[1, :50] + 1) % n
+    y2 = layer(Batch(x, ei)).node_feature.detach()
+    _, yo, _ = _oracle('gcnconv', x.cpu(), ei.cpu(), None, {k: v.detach().cpu() for k, v in layer.named_parameters()})
+    assert rel_err(y2, yo.detach()) < FP32_TOL and not torch.equal(y1, y2)
+
+
+def test_general_layer_harness_and_tfg_aliases(cuda):
+    """GeneralLayer(name, ...) drives the layers exactly as GraphGym does (BN -> act -> L2)."""
+    reset_cfg()
+    n = 300
+    ei = random_graph(2, n, 1500, symmetric=True).to(cuda)
+    x = torch.randn(n, 16).to(cuda)
+    ids = torch.arange(30).to(cuda)
+    for name in ('gcnconv', 'gcnidconv', 'sageidconv', 'ginidconv'):
+        gl = GeneralLayer(name, 16, 32, has_l2norm=True).to(cuda)
+        assert gl.layer.model.__dict__.get('bias', None) is None  # bias = not has_bn
+        out = gl(Batch(x, ei, ids)).node_feature
+        assert out.shape == (n, 32) and torch.isfinite(out).all()
+        out.sum().backward()
+    assert resolve_layer('Tfg-idgcn') is layer_dict['gcnidconv']
+    assert resolve_layer('Tfg-gcnconv') is layer_dict['gcnconv']
+
+
+def test_cached_layer_raises_on_edge_count_change(cuda):
+    from graphgym_b200.contrib.layer.idconv import GCNIDConvLayer
+    reset_cfg()
+    layer = GCNIDConvLayer(4, 4, cached=True).to(cuda)
+    x = torch.randn(10, 4).to(cuda)
+    ids = torch.arange(2).to(cuda)
+    layer(x, random_graph(0, 10, 20).to(cuda), ids)
+    with pytest.raises(RuntimeError, match='Cached 20 number of edges, but found 30'):
+        layer(x, random_graph(0, 10, 30).to(cuda), ids)

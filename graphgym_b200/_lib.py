@@ -54,6 +54,16 @@ SIGNATURES = {
     "gg_colsum_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_size, c_ptr]),
     "gg_id_count": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
     "gg_mean_weights": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "gg_gat_scores_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr]),
+    "gg_gat_fwd_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_f32, c_ptr,
+                               c_ptr, c_ptr, c_i64, c_ptr]),
+    "gg_gat_bwd_edge_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr,
+                                    c_i64, c_ptr, c_i64, c_int, c_int, c_f32, c_ptr, c_ptr, c_ptr]),
+    "gg_gat_bwd_src_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64,
+                                   c_int, c_int, c_ptr, c_ptr, c_i64, c_ptr]),
+    "gg_gat_att_grad_workspace_bytes": (c_size, [c_i64, c_int, c_int]),
+    "gg_gat_att_grad_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_size,
+                                    c_ptr]),
     "gg_gather_rows_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_scatter_add_rows_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_relu_grad_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr]),

@@ -138,6 +138,41 @@ class SAGEIDConvLayer(_IDBase):
         return out
 
 
+class GATIDConvLayer(_IDBase):
+    """ref: idconv.py:266-347 — heterogeneous transform, then additive attention with the edge-softmax
+    fused into the aggregation (functional.gat_aggregate).  Dropout on alpha is p=0 in GraphGym."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0,
+                 bias=True, **kwargs):
+        super().__init__()
+        if not concat or dropout != 0:
+            raise NotImplementedError('concat=False / attention dropout are never used by GraphGym '
+                                      '(ref: idconv.py:421); not on the accelerated path')
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.heads, self.concat, self.negative_slope, self.dropout = heads, concat, negative_slope, dropout
+        self._make_params(in_channels, heads * out_channels, bias)
+        self.att = Parameter(torch.empty(1, heads, 2 * out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        super().reset_parameters()
+        if hasattr(self, 'att'):
+            glorot_(self.att)
+
+    def forward(self, x, edge_index, id, size=None):
+        if size is not None:
+            raise NotImplementedError('bipartite GATID is not used by GraphGym')
+        n = x.size(0)
+        h = F_.id_linear(x, self.weight, self.weight_id, get_id_index(id, n))
+        # remove_self_loops + add_self_loops (ref: idconv.py:302-304)
+        layout = get_layout(edge_index, n, ops.LOOPS_REMOVE_ADD)
+        return F_.gat_aggregate(h, self.att, self.bias, layout, self.heads, self.negative_slope)
+
+    def __repr__(self):
+        return '{}({}, {}, heads={})'.format(self.__class__.__name__, self.in_channels,
+                                             self.out_channels, self.heads)
+
+
 class GINIDConvLayer(nn.Module):
     """ref: idconv.py:350-382 — z = (1+eps) x + sum_j x_j on the loop-free graph; nn(z) everywhere,
     nn_id(z[id]) added on the centre rows."""
@@ -203,6 +238,12 @@ class SAGEIDConv(_BatchWrapper):
         self.model = SAGEIDConvLayer(dim_in, dim_out, bias=bias, concat=True)
 
 
+class GATIDConv(_BatchWrapper):
+    def __init__(self, dim_in, dim_out, bias=False, **kwargs):
+        super().__init__()
+        self.model = GATIDConvLayer(dim_in, dim_out, bias=bias)
+
+
 class GINIDConv(_BatchWrapper):
     def __init__(self, dim_in, dim_out, bias=False, **kwargs):
         super().__init__()
@@ -216,4 +257,5 @@ class GINIDConv(_BatchWrapper):
 register_layer('idconv', GeneralIDConv)
 register_layer('gcnidconv', GCNIDConv)
 register_layer('sageidconv', SAGEIDConv)
+register_layer('gatidconv', GATIDConv)
 register_layer('ginidconv', GINIDConv)

@@ -172,3 +172,29 @@ def gather_rows(x, ids):
 
 def scatter_add_rows(base, ids, x):
     return _ScatterAddRows.apply(base, ids, x)
+
+
+class _GatAggregate(torch.autograd.Function):
+    """out[i] = sum_{j->i} softmax_i(leaky_relu(a_i.h_i + a_j.h_j)) h_j + bias  (ref: idconv.py:317-342)."""
+
+    @staticmethod
+    def forward(ctx, h, att, bias, layout, heads, slope):
+        h = h.contiguous()
+        out, alpha, a_tgt, a_src = ops.gat_forward(layout.csr, h, att, heads, slope, bias)
+        ctx.layout, ctx.heads, ctx.slope = layout, heads, slope
+        ctx.save_for_backward(h, att, bias, alpha, a_tgt, a_src, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, att, bias, alpha, a_tgt, a_src, out = ctx.saved_tensors
+        g = g.contiguous()
+        lay = ctx.layout
+        dh, datt = ops.gat_backward(lay.csr, lay.csc, lay.csc2csr, h, att, ctx.heads, ctx.slope, bias, alpha,
+                                    a_tgt, a_src, out, g)
+        gb = ops.colsum(g) if (bias is not None and ctx.needs_input_grad[2]) else None
+        return dh, datt.view_as(att), gb, None, None, None
+
+
+def gat_aggregate(h, att, bias, layout, heads=1, slope=0.2):
+    return _GatAggregate.apply(h, att, bias, layout, int(heads), float(slope))

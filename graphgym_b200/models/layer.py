@@ -8,7 +8,8 @@ neither vendored nor a dependency here, so each layer restates the PyG module's 
     GCNConv   add_remaining_self_loops, deg over the target, X W then propagate, + bias
     SAGEConv  lin_l(mean_j x_j) + lin_r(x_i), no self loops            (PyG >= 1.6 SAGEConv)
     GINConv   nn((1 + eps) x_i + sum_j x_j), eps = 0 buffer, loops kept
-    GATConv   see graphgym_b200/models/gat.py
+    GATConv   remove + add self loops, additive attention (slope 0.2, heads=1), edge-softmax fused
+              into the aggregation (parameters weight / att / bias as in PyG <= 1.5 and idconv.py)
 """
 import torch
 import torch.nn as nn
@@ -72,6 +73,31 @@ class _GINConvLayer(nn.Module):
         return _mlp(self.nn, z)
 
 
+class _GATConvLayer(nn.Module):
+    def __init__(self, in_channels, out_channels, heads=1, negative_slope=0.2, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.heads, self.negative_slope = heads, negative_slope
+        self.weight = Parameter(torch.empty(in_channels, heads * out_channels))
+        self.att = Parameter(torch.empty(1, heads, 2 * out_channels))
+        if bias:
+            self.bias = Parameter(torch.empty(heads * out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        glorot_(self.weight)
+        glorot_(self.att)
+        zeros_(self.bias)
+
+    def forward(self, x, edge_index):
+        n = x.size(0)
+        h = F_.seg_linear([x], [self.weight], [(0, 0, False)])
+        layout = get_layout(edge_index, n, ops.LOOPS_REMOVE_ADD)
+        return F_.gat_aggregate(h, self.att, self.bias, layout, self.heads, self.negative_slope)
+
+
 class _EdgeIndexWrapper(nn.Module):
     def forward(self, batch):
         batch.node_feature = self.model(batch.node_feature, batch.edge_index)
@@ -88,6 +114,12 @@ class SAGEConv(_EdgeIndexWrapper):
     def __init__(self, dim_in, dim_out, bias=False, **kwargs):
         super().__init__()
         self.model = _SAGEConvLayer(dim_in, dim_out, bias=bias)
+
+
+class GATConv(_EdgeIndexWrapper):
+    def __init__(self, dim_in, dim_out, bias=False, **kwargs):
+        super().__init__()
+        self.model = _GATConvLayer(dim_in, dim_out, bias=bias)
 
 
 class GINConv(_EdgeIndexWrapper):
@@ -138,6 +170,7 @@ class GeneralLayer(nn.Module):
 _builtin = {
     'gcnconv': GCNConv,
     'sageconv': SAGEConv,
+    'gatconv': GATConv,
     'ginconv': GINConv,
 }
 

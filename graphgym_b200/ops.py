@@ -288,3 +288,61 @@ def relu_grad(g, y):
     check(lib().gg_relu_grad_f32(_ptr(g), ldg, _ptr(y), ldy, n, f, _ptr(out), max(f, 1), _stream()),
           "gg_relu_grad_f32")
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# GAT
+# --------------------------------------------------------------------------------------------
+def _f32(shape, dev):
+    n = 1
+    for d in shape:
+        n *= d
+    return torch.empty(max(n, 1), dtype=torch.float32, device=dev)[:n].view(*shape)
+
+
+def gat_forward(csr, h, att, heads, slope, bias):
+    """-> out [n, heads*c], alpha [E', heads], a_tgt, a_src [n, heads]."""
+    _need_cuda(h, att, bias)
+    h, ldh = _rows(h, "h")
+    n, f = h.shape
+    c = f // heads
+    att = att.contiguous().view(heads, 2 * c)
+    a_tgt, a_src = _f32((n, heads), h.device), _f32((n, heads), h.device)
+    L = lib()
+    check(L.gg_gat_scores_f32(_ptr(h), ldh, _ptr(att), n, heads, c, _ptr(a_tgt), _ptr(a_src), _stream()),
+          "gg_gat_scores_f32")
+    alpha = _f32((csr.num_slots, heads), h.device)
+    out = torch.empty((n, f), dtype=torch.float32, device=h.device)
+    if bias is not None:
+        bias = bias.contiguous()
+    check(L.gg_gat_fwd_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(h), ldh, _ptr(a_tgt), _ptr(a_src), n,
+                           heads, c, float(slope), _ptr(bias), _ptr(alpha), _ptr(out), max(f, 1),
+                           _stream()), "gg_gat_fwd_f32")
+    return out, alpha, a_tgt, a_src
+
+
+def gat_backward(csr, csc, csc2csr, h, att, heads, slope, bias, alpha, a_tgt, a_src, out, g):
+    """-> dh [n, f], datt [heads, 2c]."""
+    h, ldh = _rows(h, "h")
+    g, ldg = _rows(g, "g")
+    out, ldo = _rows(out, "out")
+    n, f = h.shape
+    c = f // heads
+    att = att.contiguous().view(heads, 2 * c)
+    dev = h.device
+    dz = _f32((csr.num_slots, heads), dev)
+    da_tgt, da_src = _f32((n, heads), dev), _f32((n, heads), dev)
+    L = lib()
+    check(L.gg_gat_bwd_edge_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(h), ldh, _ptr(a_tgt), _ptr(a_src),
+                                _ptr(alpha), _ptr(g), ldg, _ptr(out), ldo, _ptr(bias), n, heads, c,
+                                float(slope), _ptr(dz), _ptr(da_tgt), _stream()), "gg_gat_bwd_edge_f32")
+    dh = torch.empty((n, f), dtype=torch.float32, device=dev)
+    check(L.gg_gat_bwd_src_f32(_ptr(csc.rowptr), _ptr(csc.nbr), _ptr(csc2csr), _ptr(alpha), _ptr(dz),
+                               _ptr(g), ldg, _ptr(da_tgt), _ptr(att), n, heads, c, _ptr(da_src), _ptr(dh),
+                               max(f, 1), _stream()), "gg_gat_bwd_src_f32")
+    datt = torch.empty((heads, 2 * c), dtype=torch.float32, device=dev)
+    ws_bytes = int(L.gg_gat_att_grad_workspace_bytes(n, heads, c))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(L.gg_gat_att_grad_f32(_ptr(h), ldh, _ptr(da_tgt), _ptr(da_src), n, heads, c, _ptr(datt), _ptr(ws),
+                                ws_bytes, _stream()), "gg_gat_att_grad_f32")
+    return dh, datt

@@ -182,6 +182,38 @@ int gg_colsum_f32(const float* g, int64_t ldg, int64_t n, int64_t f, float* out,
  * duplicates add twice, idconv.py:67). count must hold n floats. */
 int gg_id_count(const int64_t* id, int64_t m, int64_t n, float* count, gg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * GAT: edge-softmax fused into the aggregation.
+ *   ref: GATIDConvLayer.message/update idconv.py:317-342 (same math as pyg.nn.GATConv, layer.py:158);
+ *        PyG softmax(alpha, edge_index_i) idconv.py:327; SparseAdj.softmax sparse_adj.py:136-151.
+ * h is the transformed feature matrix [n, heads*c]; att is the reference's [1, heads, 2c] parameter
+ * (first c = target half a_i, last c = source half a_j).  Needs c % 4 == 0, heads <= 8, heads*c <= 1024.
+ *   scores   a_tgt[n,heads], a_src[n,heads]: per-node halves of the logit (z_e = a_tgt[i] + a_src[j])
+ *   fwd      alpha[E',heads] = softmax_i(leaky_relu(z)) (max-shifted, denominator + 1e-16), written for
+ *            the backward; out[i] = sum_e alpha_e h[j_e] + bias
+ *   bwd_edge per target row: dz[E',heads] (gradient of the pre-activation logit), da_tgt[n,heads]
+ *   bwd_src  on the CSC layout (slot_map = CSC slot -> CSR slot from gg_layout_slot_map):
+ *            dh[j] = sum_e alpha_e g[i_e] + da_src[j] att_src + da_tgt[j] att_tgt; da_src[n,heads]
+ *   att_grad datt[heads,2c] = [da_tgt^T h | da_src^T h] per head
+ * ------------------------------------------------------------------------------------------ */
+int gg_gat_scores_f32(const float* h, int64_t ldh, const float* att, int64_t n, int heads, int c,
+                      float* a_tgt, float* a_src, gg_stream_t stream);
+int gg_gat_fwd_f32(const int32_t* rowptr, const int32_t* nbr, const float* h, int64_t ldh,
+                   const float* a_tgt, const float* a_src, int64_t n, int heads, int c, float slope,
+                   const float* bias, float* alpha, float* out, int64_t ldo, gg_stream_t stream);
+int gg_gat_bwd_edge_f32(const int32_t* rowptr, const int32_t* nbr, const float* h, int64_t ldh,
+                        const float* a_tgt, const float* a_src, const float* alpha, const float* g,
+                        int64_t ldg, const float* out, int64_t ldo, const float* bias, int64_t n,
+                        int heads, int c, float slope, float* dz, float* da_tgt, gg_stream_t stream);
+int gg_gat_bwd_src_f32(const int32_t* rowptr_t, const int32_t* nbr_t, const int32_t* slot_map,
+                       const float* alpha, const float* dz, const float* g, int64_t ldg,
+                       const float* da_tgt, const float* att, int64_t n, int heads, int c,
+                       float* da_src, float* dh, int64_t lddh, gg_stream_t stream);
+size_t gg_gat_att_grad_workspace_bytes(int64_t n, int heads, int c);
+int gg_gat_att_grad_f32(const float* h, int64_t ldh, const float* da_tgt, const float* da_src,
+                        int64_t n, int heads, int c, float* datt, void* workspace,
+                        size_t workspace_bytes, gg_stream_t stream);
+
 /* Row gather / scatter-add / ReLU gradient used by the GIN-ID branch (ref: idconv.py:372-375):
  *   gather:      out[r,:]      = x[id[r],:]
  *   scatter_add: out[id[r],:] += x[r,:]      (atomicAdd: exact order-independence only for unique id,

@@ -11,7 +11,7 @@ from graphgym_b200.models.layer import Batch, GeneralLayer, TFG_ALIASES, layer_d
 
 
 def test_registry_names_and_duplicate_key_error():
-    for name in ('gcnconv', 'sageconv', 'ginconv', 'idconv', 'gcnidconv', 'sageidconv', 'ginidconv'):
+    for name in ('gcnconv', 'sageconv', 'ginconv', 'gatconv', 'idconv', 'gcnidconv', 'sageidconv', 'ginidconv', 'gatidconv'):
         assert name in layer_dict
     with pytest.raises(KeyError, match='Key gcnidconv is already pre-defined.'):
         register.register_layer('gcnidconv', object)

@@ -158,3 +158,32 @@ def test_cached_layer_raises_on_edge_count_change(cuda):
     layer(x, random_graph(0, 10, 20).to(cuda), ids)
     with pytest.raises(RuntimeError, match='Cached 20 number of edges, but found 30'):
         layer(x, random_graph(0, 10, 30).to(cuda), ids)
+
+
+@pytest.mark.parametrize('heads,c', [(1, 64), (2, 32), (4, 16), (8, 64)])
+def test_gat_multi_head(cuda, heads, c):
+    """heads > 1 is outside GraphGym's wrappers (heads=1) but inside the reference layer's signature
+    (ref: idconv.py:267)."""
+    from graphgym_b200.contrib.layer.idconv import GATIDConvLayer
+    reset_cfg()
+    n, fin = 700, 24
+    ei = random_graph(heads, n, 5000, loops=30, dups=50)
+    g = torch.Generator().manual_seed(heads)
+    x = torch.randn(n, fin, generator=g)
+    ids = torch.randperm(n, generator=g)[:70]
+    torch.manual_seed(0)
+    layer = GATIDConvLayer(fin, c, heads=heads, bias=True).to(cuda)
+    with torch.no_grad():
+        layer.bias.uniform_(-0.3, 0.3)
+    P = {k: v.detach().cpu().double().requires_grad_(True) for k, v in layer.named_parameters()}
+    xd = x.double().requires_grad_(True)
+    yo = olayers.gat_idconv(xd, ei, ids, P['weight'], P['weight_id'], P['att'], P['bias'], heads=heads)
+    gy = torch.randn(n, heads * c, generator=g)
+    yo.backward(gy.double())
+    xg = x.to(cuda).requires_grad_(True)
+    y = layer(xg, ei.to(cuda), ids.to(cuda))
+    y.backward(gy.to(cuda))
+    assert rel_err(y.detach(), yo.detach()) < FP32_TOL
+    assert rel_err(xg.grad, xd.grad) < FP32_TOL
+    for k, p in layer.named_parameters():
+        assert rel_err(p.grad, P[k].grad) < FP32_TOL, k

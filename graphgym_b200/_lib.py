@@ -45,6 +45,12 @@ SIGNATURES = {
     "gg_gcn_norm": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
     "gg_spmm_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_int,
                             c_ptr, c_i64, c_f32, c_ptr, c_ptr]),
+    "gg_spmm_plan_units": (c_int, [c_i64, c_i64]),
+    "gg_spmm_plan_items": (c_i64, [c_i64, c_i64, c_int]),
+    "gg_spmm_plan_build": (c_int, [c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
+    "gg_spmm_mp_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "gg_spmm_mp_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64,
+                               c_i64, c_int, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_size, c_int, c_ptr]),
     "gg_id_gemm_f32": (c_int, [ctypes.POINTER(GemmSegment), c_int, c_int, c_i64, c_i64, c_ptr, c_int,
                                c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_gemm_tn_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),

@@ -1,0 +1,406 @@
+// Merge-path CSR aggregation (SpMM v2) — the load-balanced, persistent version of spmm.cu.
+//
+// Why: on power-law graphs (hub rows of 10^4 slots next to rows of 3) one-warp-per-row leaves the SMs
+// 18 % idle and the resident warps at 24 % of peak (profiles/r01_spmm_v1_ncu_raw.csv): the kernel is
+// latency/imbalance-bound at 57 % of the HBM roofline, DRAM only 35 % busy.
+//
+// How: the rows' slots and one end-of-row marker per row form one merged sequence of E' + N units
+// (Merrill & Garland merge-path).  The plan (built once per layout, gg_spmm_plan_build) cuts it into
+// items of `units` consecutive units; item k starts at (item_row[k], item_slot[k]).  A persistent grid
+// of warps pulls items from an atomic counter.  Per item a warp
+//   1. stages the item's neighbour indices, weights and row pointers in its private shared-memory
+//      tile — the 16-byte-aligned interior with ONE cp.async.bulk (TMA 1-D bulk copy) per array,
+//      completion on an mbarrier;
+//   2. streams the slots: batches of independent 128-bit feature-row gathers (indices come from
+//      shared memory, so the gather addresses never wait on a global load), accumulating in slot order;
+//   3. at every marker writes the finished row (epilogue fused), except for the two rows an item can
+//      share with its neighbours: their partial sums go to head[k] / carry[k].
+// A second tiny kernel adds the partials of split rows in item order.  No atomics touch the data, the
+// sum order per row is fixed => bitwise run-to-run deterministic, like v1.
+#include "common.cuh"
+
+namespace gg {
+
+constexpr int kMpWarps = 8;
+constexpr int kMpThreads = kMpWarps * 32;
+constexpr int kMpMaxUnits = 480;           // units per item (slots + markers)
+constexpr int kMpTile = kMpMaxUnits + 8;   // + alignment slack
+
+struct MpArgs {
+    const int32_t* rowptr;
+    const int32_t* nbr;
+    const float* w;
+    const int32_t* item_row;   // [items + 1]
+    const int32_t* item_slot;  // [items + 1]
+    int items;
+    const float* x;
+    int64_t ldx;
+    float* out;
+    int64_t ldo;
+    int64_t n;
+    int f;
+    int reduce;
+    const float* x_self;
+    int64_t ld_self;
+    float self_scale;
+    const float* bias;
+    int* counter;
+    float* carry;  // [items, f]
+    float* head;   // [items, f]
+};
+
+// ---- mbarrier / bulk-copy PTX -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (spin > (1 << 22)) __trap();  // a lost copy must fail the launch, never hang the GPU
+    }
+}
+
+// Stage global[s0, s1) into tile so that tile[s - sa] holds element s, sa = s0 & ~3.
+template <typename T, bool TMA>
+__device__ __forceinline__ uint32_t stage_begin(T* tile, const T* __restrict__ g, int s0, int s1, int lane,
+                                                uint64_t* bar) {
+    const int sa = s0 & ~3;
+    const int ea = s1 & ~3;  // interior [sa, ea) is 16-byte aligned on both sides
+    uint32_t bytes = 0;
+    if (TMA) {
+        if (ea > sa) {
+            bytes = (uint32_t)(ea - sa) * 4u;
+            if (lane == 0) bulk_g2s(tile, g + sa, bytes, bar);
+        }
+        const int t = ea + lane;  // <= 3 tail elements past the aligned interior (ea >= sa always)
+        if (lane < 4 && t < s1) tile[t - sa] = g[t];
+    } else {
+        for (int q = s0 + lane; q < s1; q += 32) tile[q - sa] = g[q];
+    }
+    return bytes;
+}
+
+template <int VPL> struct MpUnroll { static constexpr int value = VPL == 1 ? 8 : (VPL == 2 ? 4 : 2); };
+
+template <int VPL, bool WEIGHTED, bool TMA>
+__global__ void __launch_bounds__(kMpThreads, VPL == 1 ? 4 : 2) spmm_mp_kernel(MpArgs a) {
+    constexpr int U = MpUnroll<VPL>::value;
+    __shared__ __align__(16) int32_t s_nbr_all[kMpWarps][kMpTile];
+    __shared__ __align__(16) float s_w_all[WEIGHTED ? kMpWarps : 1][WEIGHTED ? kMpTile : 4];
+    __shared__ __align__(16) int32_t s_rp_all[kMpWarps][kMpTile];
+    __shared__ __align__(8) uint64_t s_bar[kMpWarps];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int32_t* s_nbr = s_nbr_all[wid];
+    float* s_w = s_w_all[WEIGHTED ? wid : 0];
+    int32_t* s_rp = s_rp_all[wid];
+    uint64_t* bar = &s_bar[wid];
+    if (TMA) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+    }
+    uint32_t phase = 0;
+
+    const int nvec = a.f >> 2;
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(a.x);
+    const int64_t ldx4 = a.ldx >> 2;
+    bool act[VPL];
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) act[q] = lane + q * 32 < nvec;
+
+    int item = 0;
+    if (lane == 0) item = atomicAdd(a.counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+
+    while (item < a.items) {
+        int next = 0;
+        if (lane == 0) next = atomicAdd(a.counter, 1);  // in flight while this item is processed
+        const int r0 = __ldg(a.item_row + item), s0 = __ldg(a.item_slot + item);
+        const int r1 = __ldg(a.item_row + item + 1), s1 = __ldg(a.item_slot + item + 1);
+        const int sa = s0 & ~3;
+
+        // ---- stage: neighbour ids, weights (TMA bulk copies) and row pointers r0 .. r1+1 ----
+        __syncwarp();  // everyone is done with the previous item's tiles
+        uint32_t bytes = 0;
+        if (TMA && lane == 0) {
+            const int ea = s1 & ~3;
+            if (ea > sa) mbar_expect_tx(bar, (uint32_t)(ea - sa) * 4u * (WEIGHTED ? 2u : 1u));
+        }
+        bytes += stage_begin<int32_t, TMA>(s_nbr, a.nbr, s0, s1, lane, bar);
+        if (WEIGHTED) bytes += stage_begin<float, TMA>(s_w, a.w, s0, s1, lane, bar);
+        const int nrp = (r1 < a.n ? r1 + 1 : (int)a.n) - r0 + 1;  // rowptr[r0 .. min(r1+1, n)]
+        for (int i = lane; i < nrp; i += 32) s_rp[i] = __ldg(a.rowptr + r0 + i);
+        __syncwarp();
+        if (TMA && bytes) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        }
+
+        // ---- stream the item's slots ----
+        const bool cont_first = s0 > s_rp[0];
+        int cur = r0;
+        int re = r0 < a.n ? s_rp[1] : 0x7fffffff;  // slot index at which the current row ends
+        float4 acc[VPL];
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        auto finalize = [&](int row) {
+            if (row == r0 && cont_first) {  // the row began in an earlier item: partial only
+#pragma unroll
+                for (int q = 0; q < VPL; ++q)
+                    if (act[q]) reinterpret_cast<float4*>(a.head + (int64_t)item * a.f)[lane + q * 32] = acc[q];
+            } else {
+                const int deg = s_rp[row - r0 + 1] - s_rp[row - r0];
+                const float inv = (a.reduce == GG_MEAN && deg > 0) ? 1.0f / (float)deg : 1.0f;
+#pragma unroll
+                for (int q = 0; q < VPL; ++q) {
+                    if (!act[q]) continue;
+                    const int vi = lane + q * 32;
+                    float4 r = acc[q];
+                    if (a.reduce == GG_MEAN) { r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv; }
+                    if (a.x_self)
+                        fma4(r, a.self_scale,
+                             __ldg(reinterpret_cast<const float4*>(a.x_self + (int64_t)row * a.ld_self) + vi));
+                    if (a.bias) add4(r, __ldg(reinterpret_cast<const float4*>(a.bias) + vi));
+                    reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[vi] = r;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < VPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+
+        for (int s = s0; s < s1; s += U) {
+            float4 v[U][VPL];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool ok = s + u < s1;
+                const int j = ok ? s_nbr[s + u - sa] : 0;
+                const float4* p = x4 + (int64_t)j * ldx4 + lane;
+#pragma unroll
+                for (int q = 0; q < VPL; ++q)
+                    v[u][q] = (ok && act[q]) ? ldg_nc_f4(p + q * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (s + u < s1) {  // warp-uniform
+                    while (s + u == re) {  // markers in front of this slot (also empty rows)
+                        finalize(cur);
+                        ++cur;
+                        re = s_rp[cur - r0 + 1];
+                    }
+                    const float wv = WEIGHTED ? s_w[s + u - sa] : 1.f;
+#pragma unroll
+                    for (int q = 0; q < VPL; ++q) {
+                        if (WEIGHTED) fma4(acc[q], wv, v[u][q]);
+                        else add4(acc[q], v[u][q]);
+                    }
+                }
+            }
+        }
+        while (cur < r1) {  // markers after the last slot of the item
+            finalize(cur);
+            ++cur;
+        }
+        // the row still open at the end of the item (row r1): its partial, possibly all zero
+#pragma unroll
+        for (int q = 0; q < VPL; ++q)
+            if (act[q]) reinterpret_cast<float4*>(a.carry + (int64_t)item * a.f)[lane + q * 32] = acc[q];
+
+        item = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+// Rows split over several items: out[row] = epi( carry[k0] + ... + carry[f-1] + head[f] ), f = the item
+// that consumed the row's marker.  One warp per item f; almost all exit at once.
+template <int VPL>
+__global__ void __launch_bounds__(kMpThreads) spmm_mp_fixup_kernel(MpArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int f_item = blockIdx.x * kMpWarps + (threadIdx.x >> 5);
+    if (f_item < 1 || f_item >= a.items) return;
+    const int r0 = __ldg(a.item_row + f_item), s0 = __ldg(a.item_slot + f_item);
+    const int r1 = __ldg(a.item_row + f_item + 1);
+    if (r0 >= a.n || r0 >= r1) return;  // the item does not finish its first row
+    const int rb = __ldg(a.rowptr + r0);
+    if (s0 <= rb) return;                // the row starts with the item: written directly
+    int k0 = f_item - 1;
+    while (k0 >= 1 && __ldg(a.item_row + k0) == r0 && __ldg(a.item_slot + k0) > rb) --k0;
+    const int nvec = a.f >> 2;
+    const int deg = __ldg(a.rowptr + r0 + 1) - rb;
+    const float inv = (a.reduce == GG_MEAN && deg > 0) ? 1.0f / (float)deg : 1.0f;
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) {
+        const int vi = lane + q * 32;
+        if (vi >= nvec) continue;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = k0; k < f_item; ++k) add4(r, reinterpret_cast<const float4*>(a.carry + (int64_t)k * a.f)[vi]);
+        add4(r, reinterpret_cast<const float4*>(a.head + (int64_t)f_item * a.f)[vi]);
+        if (a.reduce == GG_MEAN) { r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv; }
+        if (a.x_self)
+            fma4(r, a.self_scale, __ldg(reinterpret_cast<const float4*>(a.x_self + (int64_t)r0 * a.ld_self) + vi));
+        if (a.bias) add4(r, __ldg(reinterpret_cast<const float4*>(a.bias) + vi));
+        reinterpret_cast<float4*>(a.out + (int64_t)r0 * a.ldo)[vi] = r;
+    }
+}
+
+// item k starts at diagonal d = k * units of the merged (slots + markers) sequence:
+//   row  = number of markers before d = first r with rowptr[r+1] + r >= d,   slot = d - row
+__global__ void __launch_bounds__(256) spmm_plan_kernel(const int32_t* __restrict__ rowptr, int64_t n,
+                                                        int64_t slots, int units, int items,
+                                                        int32_t* __restrict__ item_row,
+                                                        int32_t* __restrict__ item_slot) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= items; k += gridDim.x * blockDim.x) {
+        int64_t d = (int64_t)k * units;
+        if (d > n + slots) d = n + slots;
+        int64_t lo = 0, hi = n;  // answer in [0, n]
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if ((int64_t)rowptr[mid + 1] + mid >= d) hi = mid;
+            else lo = mid + 1;
+        }
+        item_row[k] = (int32_t)lo;
+        item_slot[k] = (int32_t)(d - lo);
+    }
+}
+
+static inline bool mp_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int VPL, bool WEIGHTED, bool TMA>
+static void prefer_smem() {
+    static bool done = false;  // 4 CTAs x 47 KB of tiles per SM: ask for the large carve-out once
+    if (!done) {
+        cudaFuncSetAttribute(spmm_mp_kernel<VPL, WEIGHTED, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        done = true;
+    }
+}
+
+template <int VPL>
+static void launch_mp(const MpArgs& a, bool tma, int grid, cudaStream_t st) {
+    prefer_smem<VPL, true, true>();
+    prefer_smem<VPL, true, false>();
+    prefer_smem<VPL, false, true>();
+    prefer_smem<VPL, false, false>();
+    if (a.w) {
+        if (tma) spmm_mp_kernel<VPL, true, true><<<grid, kMpThreads, 0, st>>>(a);
+        else spmm_mp_kernel<VPL, true, false><<<grid, kMpThreads, 0, st>>>(a);
+    } else {
+        if (tma) spmm_mp_kernel<VPL, false, true><<<grid, kMpThreads, 0, st>>>(a);
+        else spmm_mp_kernel<VPL, false, false><<<grid, kMpThreads, 0, st>>>(a);
+    }
+    count_launch();
+    spmm_mp_fixup_kernel<VPL><<<(int)ceil_div(a.items, kMpWarps), kMpThreads, 0, st>>>(a);
+    count_launch();
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+int gg_spmm_plan_units(int64_t num_rows, int64_t num_slots) {
+    // enough items to give every resident warp (148 SMs x 32) a few, capped by the shared-memory tile
+    int64_t total = num_rows + num_slots;
+    int64_t u = total / ((int64_t)kNumSMs * 32 * 4);
+    if (u > kMpMaxUnits) u = kMpMaxUnits;
+    if (u < 64) u = 64;
+    return (int)(u / 32 * 32);
+}
+
+int64_t gg_spmm_plan_items(int64_t num_rows, int64_t num_slots, int units) {
+    if (units <= 0) return 0;
+    int64_t it = ceil_div(num_rows + num_slots, units);
+    return it < 1 ? 1 : it;
+}
+
+int gg_spmm_plan_build(const int32_t* rowptr, int64_t num_rows, int64_t num_slots, int units,
+                       int32_t* item_row, int32_t* item_slot, gg_stream_t stream) {
+    GG_REQUIRE(num_rows >= 0 && num_slots >= 0, "gg_spmm_plan_build: negative size");
+    GG_REQUIRE(units >= 32 && units <= kMpMaxUnits, "gg_spmm_plan_build: units=%d not in [32, %d]", units,
+               kMpMaxUnits);
+    GG_REQUIRE(rowptr && item_row && item_slot, "gg_spmm_plan_build: null pointer");
+    int64_t items = gg_spmm_plan_items(num_rows, num_slots, units);
+    GG_REQUIRE(items < ((int64_t)1 << 31) - 1, "gg_spmm_plan_build: too many items");
+    int grid = (int)ceil_div(items + 1, 256);
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    spmm_plan_kernel<<<grid, 256, 0, as_stream(stream)>>>(rowptr, num_rows, num_slots, units, (int)items,
+                                                         item_row, item_slot);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
+size_t gg_spmm_mp_workspace_bytes(int64_t items, int64_t f) {
+    return 256 + 2 * align_up((size_t)items * (size_t)f * sizeof(float), 256);
+}
+
+int gg_spmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot,
+                   const int32_t* item_row, const int32_t* item_slot, int64_t items, const float* x,
+                   int64_t ldx, float* out, int64_t ldo, int64_t num_rows, int64_t f, int reduce,
+                   const float* x_self, int64_t ld_self, float self_scale, const float* bias,
+                   void* workspace, size_t workspace_bytes, int stage_mode, gg_stream_t stream) {
+    GG_REQUIRE(num_rows >= 0 && f >= 0 && items >= 0, "gg_spmm_mp_f32: negative size");
+    GG_REQUIRE(reduce == GG_SUM || reduce == GG_MEAN, "gg_spmm_mp_f32: reduce=%d", reduce);
+    if (num_rows == 0 || f == 0) return GG_OK;
+    GG_REQUIRE(rowptr && item_row && item_slot && x && out && workspace, "gg_spmm_mp_f32: null pointer");
+    GG_REQUIRE(items >= 1 && items < ((int64_t)1 << 31) - 1, "gg_spmm_mp_f32: items out of range");
+    bool vec = (f % 4 == 0) && f <= 1024 && (ldx % 4 == 0) && (ldo % 4 == 0) && mp_aligned16(x) &&
+               mp_aligned16(out) && (!x_self || (ld_self % 4 == 0 && mp_aligned16(x_self))) &&
+               (!bias || mp_aligned16(bias));
+    if (!vec) {
+        set_error("gg_spmm_mp_f32: needs f %% 4 == 0, f <= 1024 and 16-byte aligned rows (use gg_spmm_f32)");
+        return GG_ERR_UNSUPPORTED;
+    }
+    if (workspace_bytes < gg_spmm_mp_workspace_bytes(items, f)) {
+        set_error("gg_spmm_mp_f32: workspace %zu < %zu", workspace_bytes, gg_spmm_mp_workspace_bytes(items, f));
+        return GG_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    Carver c(workspace);
+    int* counter = c.take<int>(64);
+    float* carry = c.take<float>((size_t)items * f);
+    float* head = c.take<float>((size_t)items * f);
+    GG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    MpArgs a{rowptr, nbr, w_slot, item_row, item_slot, (int)items, x, ldx, out, ldo, num_rows, (int)f,
+             reduce, x_self, ld_self, self_scale, bias, counter, carry, head};
+    // TMA staging needs 16-byte aligned index / weight arrays; otherwise plain loads
+    bool tma = stage_mode != 1 && mp_aligned16(nbr) && (!w_slot || mp_aligned16(w_slot));
+    const int nvec = (int)(f / 4);
+    int per_sm = nvec <= 32 ? 4 : 2;
+    int grid = (int)ceil_div(items, kMpWarps);
+    if (grid > kNumSMs * per_sm) grid = kNumSMs * per_sm;
+    if (nvec <= 32) launch_mp<1>(a, tma, grid, st);
+    else if (nvec <= 64) launch_mp<2>(a, tma, grid, st);
+    else if (nvec <= 128) launch_mp<4>(a, tma, grid, st);
+    else launch_mp<8>(a, tma, grid, st);
+    GG_CUDA(cudaPeekAtLastError());
+    return GG_OK;
+}
+
+}  // extern "C"

@@ -17,6 +17,11 @@ SUM, MEAN = 0, 1
 ACT_NONE, ACT_RELU = 0, 1
 
 
+import os as _os
+SPMM_ALGO = _os.environ.get("GG_SPMM_ALGO", "auto")    # auto | mp | row
+SPMM_STAGE = _os.environ.get("GG_SPMM_STAGE", "tma")   # tma | ldg
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -54,12 +59,27 @@ def launch_count():
 class Csr:
     """One compressed layout of an (edited) edge list: segments grouped by target or by source."""
     __slots__ = ("rowptr", "nbr", "perm", "rowid", "num_slots", "num_nodes", "num_edges", "policy",
-                 "group_by")
+                 "group_by", "_plan")
 
     def __init__(self, rowptr, nbr, perm, rowid, num_slots, num_nodes, num_edges, policy, group_by):
         self.rowptr, self.nbr, self.perm, self.rowid = rowptr, nbr, perm, rowid
         self.num_slots, self.num_nodes, self.num_edges = num_slots, num_nodes, num_edges
         self.policy, self.group_by = policy, group_by
+        self._plan = None
+
+    @property
+    def plan(self):
+        """Merge-path work plan of the load-balanced SpMM: (item_row, item_slot, items), built once."""
+        if self._plan is None:
+            L = lib()
+            units = int(L.gg_spmm_plan_units(self.num_nodes, self.num_slots))
+            items = int(L.gg_spmm_plan_items(self.num_nodes, self.num_slots, units))
+            item_row = torch.empty(items + 1, dtype=torch.int32, device=self.rowptr.device)
+            item_slot = torch.empty(items + 1, dtype=torch.int32, device=self.rowptr.device)
+            check(L.gg_spmm_plan_build(_ptr(self.rowptr), self.num_nodes, self.num_slots, units,
+                                       _ptr(item_row), _ptr(item_slot), _stream()), "gg_spmm_plan_build")
+            self._plan = (item_row, item_slot, items)
+        return self._plan
 
 
 def layout_build(edge_index, num_nodes, policy=LOOPS_KEEP, group_by=BY_TARGET):
@@ -175,6 +195,21 @@ def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None
         x_self, ld_self = _rows(x_self, "x_self")
     if bias is not None:
         bias = bias.contiguous()
+    algo = SPMM_ALGO
+    if algo == "auto":
+        # merge-path kernel for wide rows on graphs big enough to need balancing; one-warp-per-row
+        # (with sub-warp groups for narrow features) otherwise
+        algo = "mp" if (f % 4 == 0 and 64 < f <= 1024 and n + csr.num_slots >= 1 << 14) else "row"
+    if algo == "mp" and f % 4 == 0 and f <= 1024 and n > 0:
+        item_row, item_slot, items = csr.plan
+        L = lib()
+        ws_bytes = int(L.gg_spmm_mp_workspace_bytes(items, f))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        check(L.gg_spmm_mp_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(item_row), _ptr(item_slot),
+                               items, _ptr(x), ldx, _ptr(out), ldo, n, f, reduce, _ptr(x_self), ld_self,
+                               float(self_scale), _ptr(bias), _ptr(ws), ws_bytes,
+                               1 if SPMM_STAGE == "ldg" else 0, _stream()), "gg_spmm_mp_f32")
+        return out
     check(lib().gg_spmm_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(x), ldx, _ptr(out), ldo,
                             n, f, reduce, _ptr(x_self), ld_self, float(self_scale), _ptr(bias),
                             _stream()), "gg_spmm_f32")

@@ -141,6 +141,26 @@ int gg_spmm_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, 
                 const float* x_self, int64_t ld_self, float self_scale, const float* bias,
                 gg_stream_t stream);
 
+/* Load-balanced variant for large / skewed graphs (merge-path over slots + row markers, persistent
+ * warps, neighbour-index tiles staged in shared memory by TMA bulk copies; see csrc/spmm_mp.cu).
+ * The plan depends only on rowptr and is built once per layout:
+ *   units  = gg_spmm_plan_units(N, E')                  merged units (slots + rows) per work item
+ *   items  = gg_spmm_plan_items(N, E', units)
+ *   gg_spmm_plan_build -> item_row[items+1], item_slot[items+1]
+ * gg_spmm_mp_f32 has the semantics of gg_spmm_f32; it needs f % 4 == 0, f <= 1024, 16-byte aligned rows
+ * (GG_ERR_UNSUPPORTED otherwise) and a workspace of gg_spmm_mp_workspace_bytes(items, f).
+ * stage_mode: 0 = cp.async.bulk staging, 1 = plain loads.  Same fixed summation order per row. */
+int gg_spmm_plan_units(int64_t num_rows, int64_t num_slots);
+int64_t gg_spmm_plan_items(int64_t num_rows, int64_t num_slots, int units);
+int gg_spmm_plan_build(const int32_t* rowptr, int64_t num_rows, int64_t num_slots, int units,
+                       int32_t* item_row, int32_t* item_slot, gg_stream_t stream);
+size_t gg_spmm_mp_workspace_bytes(int64_t items, int64_t f);
+int gg_spmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot,
+                   const int32_t* item_row, const int32_t* item_slot, int64_t items, const float* x,
+                   int64_t ldx, float* out, int64_t ldo, int64_t num_rows, int64_t f, int reduce,
+                   const float* x_self, int64_t ld_self, float self_scale, const float* bias,
+                   void* workspace, size_t workspace_bytes, int stage_mode, gg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Dense transform with ID-GNN heterogeneous weights:
  *   out[N,F] = act( sum_g diag(scale_g) * A_g[N,K_g] * B_g  + bias ) (.* mask>0)

@@ -1,0 +1,127 @@
+"""Merge-path (load-balanced, TMA-staged) aggregation kernel: parity against the oracle and against the
+one-warp-per-row kernel, on the shapes that stress the plan — hub rows split over many items, long runs
+of empty rows, items that contain only markers, tiny graphs with a single item."""
+import numpy as np
+import pytest
+import torch
+
+from graphgym_b200 import ops
+from oracle import pyg_utils as U
+from util import FP32_TOL, powerlaw_graph, random_graph, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle(ei, x, w_edge, reduce, self_scale, bias):
+    xj = x.double().index_select(0, ei[0])
+    if w_edge is not None:
+        xj = xj * w_edge.double().view(-1, 1)
+    out = U.propagate(ei, xj, x.size(0), 'mean' if reduce == ops.MEAN else 'add')
+    if self_scale:
+        out = out + self_scale * x.double()
+    if bias is not None:
+        out = out + bias.double()
+    return out
+
+
+def run(csr, x, w, reduce, self_scale, bias, algo, stage, monkeypatch):
+    monkeypatch.setattr(ops, 'SPMM_ALGO', algo)
+    monkeypatch.setattr(ops, 'SPMM_STAGE', stage)
+    return ops.spmm(csr, x, w, reduce, x if self_scale else None, self_scale, bias)
+
+
+def check_plan(csr):
+    item_row, item_slot, items = csr.plan
+    L = ops.lib()
+    units = int(L.gg_spmm_plan_units(csr.num_nodes, csr.num_slots))
+    rp = csr.rowptr.cpu().numpy().astype(np.int64)
+    ir, isl = item_row.cpu().numpy().astype(np.int64), item_slot.cpu().numpy().astype(np.int64)
+    n, e = csr.num_nodes, csr.num_slots
+    d = np.minimum(np.arange(items + 1, dtype=np.int64) * units, n + e)
+    assert (ir + isl == d).all()                       # on the diagonal
+    assert ir[-1] == n and isl[-1] == e and ir[0] == 0 and isl[0] == 0
+    assert (isl >= rp[ir]).all()                       # the slot belongs to the row or is its end
+    inside = ir < n
+    assert (isl[inside] <= rp[ir[inside] + 1]).all()
+    # minimality: the marker of row-1 lies before the diagonal
+    prev = ir > 0
+    assert (rp[ir[prev]] + ir[prev] - 1 < d[prev]).all()
+
+
+@pytest.mark.parametrize('stage', ['tma', 'ldg'])
+@pytest.mark.parametrize('f', [68, 100, 128, 136, 256, 300, 512, 1024])
+def test_parity_random(cuda, monkeypatch, stage, f):
+    n = 997
+    ei = random_graph(f, n, 9000, loops=30, dups=40)
+    g = torch.Generator().manual_seed(f)
+    x = torch.randn(n, f, generator=g)
+    w_edge = torch.rand(ei.size(1), generator=g)
+    bias = torch.randn(f, generator=g)
+    csr = ops.layout_build(ei.to(cuda), n, 0, 0)
+    check_plan(csr)
+    w_slot = w_edge[csr.perm.cpu().long()].to(cuda)
+    for weighted in (False, True):
+        for reduce in (ops.SUM, ops.MEAN):
+            for self_scale, b in ((0.0, None), (1.25, bias)):
+                got = run(csr, x.to(cuda), w_slot if weighted else None, reduce, self_scale,
+                          b.to(cuda) if b is not None else None, 'mp', stage, monkeypatch)
+                want = oracle(ei, x, w_edge if weighted else None, reduce, self_scale, b)
+                assert rel_err(got, want) < FP32_TOL, (f, weighted, reduce, self_scale)
+
+
+@pytest.mark.parametrize('n,avg', [(20000, 16), (200000, 25)])
+def test_powerlaw_hubs_split_over_items(cuda, monkeypatch, n, avg):
+    f = 128
+    ei = powerlaw_graph(5, n, avg)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(1))
+    csr = ops.layout_build(ei.to(cuda), n, 1, 0)
+    check_plan(csr)
+    deg = ops.segment_degree(csr)
+    w = ops.gcn_norm(csr, deg)
+    assert int(torch.diff(csr.rowptr).max()) > 2000       # rows spanning >= 4 items
+    mp = run(csr, x.to(cuda), w, ops.SUM, 0.0, None, 'mp', 'tma', monkeypatch)
+    row = run(csr, x.to(cuda), w, ops.SUM, 0.0, None, 'row', 'tma', monkeypatch)
+    assert rel_err(mp, row.double()) < 2e-6
+    # rows that live inside one item are summed in the same order by both kernels: bitwise equal
+    same = (mp == row).all(dim=1).float().mean().item()
+    assert same > 0.9
+    assert torch.equal(mp, run(csr, x.to(cuda), w, ops.SUM, 0.0, None, 'mp', 'tma', monkeypatch))
+
+
+def test_empty_rows_and_marker_only_items(cuda, monkeypatch):
+    """20000 isolated nodes between two small cliques: most items hold nothing but row markers."""
+    n, f = 20000, 128
+    a = torch.combinations(torch.arange(0, 40), 2).t()
+    b = torch.combinations(torch.arange(n - 30, n), 2).t()
+    ei = torch.cat([a, a.flip(0), b, b.flip(0)], dim=1)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(2))
+    bias = torch.randn(f, generator=torch.Generator().manual_seed(3))
+    csr = ops.layout_build(ei.to(cuda), n, 0, 0)
+    check_plan(csr)
+    for reduce in (ops.SUM, ops.MEAN):
+        got = run(csr, x.to(cuda), None, reduce, 2.0, bias.to(cuda), 'mp', 'tma', monkeypatch)
+        assert rel_err(got, oracle(ei, x, None, reduce, 2.0, bias)) < FP32_TOL
+
+
+def test_no_edges_and_single_item(cuda, monkeypatch):
+    f = 128
+    for n, e in [(5, 0), (1, 0), (3, 4), (40, 10)]:
+        ei = random_graph(n, n, e) if e else torch.zeros((2, 0), dtype=torch.int64)
+        x = torch.randn(n, f, generator=torch.Generator().manual_seed(n))
+        csr = ops.layout_build(ei.to(cuda), n, 0, 0)
+        check_plan(csr)
+        got = run(csr, x.to(cuda), None, ops.SUM, 1.0, None, 'mp', 'tma', monkeypatch)
+        assert rel_err(got, oracle(ei, x, None, ops.SUM, 1.0, None)) < FP32_TOL
+
+
+def test_one_giant_row(cuda, monkeypatch):
+    """every edge points at node 7: one row of 60000 slots = 125 items chained through the fix-up."""
+    n, e, f = 300, 60000, 256
+    g = torch.Generator().manual_seed(0)
+    ei = torch.stack([torch.randint(0, n, (e,), generator=g), torch.full((e,), 7)])
+    x = torch.randn(n, f, generator=g)
+    csr = ops.layout_build(ei.to(cuda), n, 0, 0)
+    check_plan(csr)
+    for reduce in (ops.SUM, ops.MEAN):
+        got = run(csr, x.to(cuda), None, reduce, 0.0, None, 'mp', 'tma', monkeypatch)
+        assert rel_err(got, oracle(ei, x, None, reduce, 0.0, None)) < FP32_TOL

@@ -249,7 +249,7 @@ def run_ours(args, spec, rank, world, dev):
     avg_spmm_ms = float(np.mean(spmm_ms)) if spmm_ms else float('nan')
     peak, peak_src = load_peaks()
     achieved = per_launch_bytes / (avg_spmm_ms * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'spmm_vec_kernel (CSR aggregation, fwd and bwd launches)',
+    roofline = {'bound': 'hbm', 'kernel': 'spmm_mp_kernel + fixup (merge-path CSR aggregation; fwd on CSR and bwd on CSC)',
                 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
                 'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': per_launch_bytes,

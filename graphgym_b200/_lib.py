@@ -70,6 +70,16 @@ SIGNATURES = {
     "gg_gat_att_grad_workspace_bytes": (c_size, [c_i64, c_int, c_int]),
     "gg_gat_att_grad_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_int, c_int, c_ptr, c_ptr, c_size,
                                     c_ptr]),
+    "gg_cycle_diag_workspace_bytes": (c_size, [c_i64]),
+    "gg_cycle_diag_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_int, c_ptr, c_i64,
+                                  c_ptr, c_size, c_ptr]),
+    "gg_cycle_diag_i64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_int, c_ptr, c_i64, c_ptr,
+                                  c_ptr, c_size, c_ptr]),
+    "gg_egonet_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "gg_egonet_sizes": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr,
+                                c_ptr, c_size, c_ptr]),
+    "gg_egonet_fill": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr,
+                               c_i64, c_ptr, c_ptr, c_ptr]),
     "gg_gather_rows_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_scatter_add_rows_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_relu_grad_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr]),

@@ -234,6 +234,55 @@ int gg_gat_att_grad_f32(const float* h, int64_t ldh, const float* da_tgt, const 
                         int64_t n, int heads, int c, float* datt, void* workspace,
                         size_t workspace_bytes, gg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * ID-GNN Fast: cycle features diag(A^p), p = 1..k.
+ *   ref: compute_identity graphgym/contrib/transform/identity.py:25-35 (dense n x n powers, fp32).
+ * One call handles a block of `src_count` consecutive source nodes [src_begin, src_begin+src_count)
+ * inside a node range [row_begin, row_end) that is closed under adjacency (a graph, or a run of graphs
+ * of a block-diagonal batch); out[b, p-1] = diag(A^p) at node src_begin + b.
+ *   f32: A = the per-slot weights w_slot (A_hat from gg_gcn_norm on the ADD_REMAINING layout), up to
+ *        128 sources per call; fp32 propagation, fp64 dot accumulation (parity 1e-5 relative);
+ *   i64: A = the unweighted layout (duplicate edges counted), up to 64 sources per call, exact unless
+ *        a value exceeds int64: then out = INT64_MAX and *overflow_count is incremented (the caller
+ *        zeroes it).  The reference has no integer mode.
+ * symmetric != 0 uses diag(A^2t) = |A^t e_i|^2, diag(A^2t+1) = <A^t e_i, A^(t+1) e_i> (ceil(k/2) hops);
+ * symmetric == 0 propagates k hops and reads the diagonal entry.
+ * ------------------------------------------------------------------------------------------ */
+size_t gg_cycle_diag_workspace_bytes(int64_t num_rows_in_range);
+int gg_cycle_diag_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, int64_t row_begin,
+                      int64_t row_end, int k, int symmetric, int64_t src_begin, int src_count, float* out,
+                      int64_t ld_out, void* workspace, size_t workspace_bytes, gg_stream_t stream);
+int gg_cycle_diag_i64(const int32_t* rowptr, const int32_t* nbr, int64_t row_begin, int64_t row_end, int k,
+                      int symmetric, int64_t src_begin, int src_count, int64_t* out, int64_t ld_out,
+                      int32_t* overflow_count, void* workspace, size_t workspace_bytes, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ID-GNN Full: batched k-hop ego-net extraction.
+ *   ref: ego_nets graphgym/models/transform.py:11-38 (nx.ego_graph per centre + dict relabel).
+ * Input: the adjacency of a block-diagonal batch of undirected graphs as a layout grouped by source
+ * (both directions of every edge present, the DeepSNAP convention), graph_ptr[G+1] node ranges,
+ * graph_of[n] graph id per node, max_graph_nodes (bitmap size; <= ~100K).  radius > 4 => whole graph
+ * (transform.py:18-19).  Two phases:
+ *   sizes: ego_ptr[n+1] / edge_ptr[n+1] (exclusive scans of the non-centre member count and of the
+ *          directed induced-edge count per centre) and out_node_ptr[G+1]; the caller reads
+ *          out_node_ptr[G] and edge_ptr[n] to allocate;
+ *   fill:  orig_id[total_nodes], edge_index_out[2, total_edges].
+ * Numbering (per graph g, centres [lo,hi)): centre c -> out_node_ptr[g] + (c-lo) (so node_id_index of a
+ * graph is arange(n_g) + out_node_ptr[g], transform.py:38); the j-th non-centre member of ego c, in
+ * ascending original id, -> out_node_ptr[g] + n_g + (ego_ptr[c]-ego_ptr[lo]) + j.  Edges: centres in
+ * order, members ascending, adjacency slots in order.
+ * ------------------------------------------------------------------------------------------ */
+size_t gg_egonet_workspace_bytes(int64_t n, int64_t num_graphs);
+int gg_egonet_sizes(const int32_t* rowptr, const int32_t* nbr, int64_t n, int radius,
+                    const int32_t* graph_ptr, const int32_t* graph_of, int64_t num_graphs,
+                    int max_graph_nodes, uint32_t* ego_ptr, uint32_t* edge_ptr, int64_t* out_node_ptr,
+                    void* workspace, size_t workspace_bytes, gg_stream_t stream);
+int gg_egonet_fill(const int32_t* rowptr, const int32_t* nbr, int64_t n, int radius,
+                   const int32_t* graph_ptr, const int32_t* graph_of, int64_t num_graphs,
+                   int max_graph_nodes, const uint32_t* ego_ptr, const uint32_t* edge_ptr,
+                   const int64_t* out_node_ptr, int64_t total_edges, int64_t* orig_id,
+                   int64_t* edge_index_out, gg_stream_t stream);
+
 /* Row gather / scatter-add / ReLU gradient used by the GIN-ID branch (ref: idconv.py:372-375):
  *   gather:      out[r,:]      = x[id[r],:]
  *   scatter_add: out[id[r],:] += x[r,:]      (atomicAdd: exact order-independence only for unique id,

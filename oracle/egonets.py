@@ -7,15 +7,15 @@ node_id_index = arange(n).  The order of the non-centre members inside one ego i
 in the reference; the canonical form used for bit-exact parity is ASCENDING original id.
 
 Input is an undirected simple graph given as a symmetric directed edge list (both directions
-present, the DeepSNAP convention).  Output edges are directed, both directions, sorted by (src, tgt)
-within each ego, egos concatenated in centre order.
+present, the DeepSNAP convention).  Output edges are directed, both directions, ordered by (member
+ascending, adjacency slot = COO order) within each ego, egos concatenated in centre order.
 """
 import numpy as np
 
 
 def _adj_lists(edge_index, n):
     ei = np.asarray(edge_index, dtype=np.int64)
-    order = np.lexsort((ei[1], ei[0]))
+    order = np.argsort(ei[0], kind='stable')  # adjacency slots keep the COO order (the layout's order)
     src, tgt = ei[0][order], ei[1][order]
     ptr = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(np.bincount(src, minlength=n), out=ptr[1:])
@@ -68,7 +68,7 @@ def ego_nets(edge_index, n, radius):
         new_id[others] = base + np.arange(len(others))
         new_id[c] = c
         cnt = 0
-        for u in mem:  # ascending original id => sorted by (src, tgt) in the ORIGINAL ids
+        for u in mem:  # members ascending, each one's adjacency in COO order
             for v in nbr[ptr[u]:ptr[u + 1]]:
                 if new_id[v] >= 0:
                     srcs.append(new_id[u])
@@ -99,3 +99,26 @@ def canonical(num_centres, edge_index_out, orig_id, ego_ptr):
         a, b = int(orig_id[s]), int(orig_id[t])
         edges[c].add((min(a, b), max(a, b)))
     return [sorted(m) for m in members], [sorted(e) for e in edges]
+
+
+def ego_nets_batch(edge_index, graph_ptr, radius):
+    """The reference pipeline on a block-diagonal batch: ego_nets per graph (transform.py is applied per
+    graph, loader.py:175-180), then concatenation with node offsets (DeepSNAP Batch.collate)."""
+    ei = np.asarray(edge_index, dtype=np.int64)
+    gp = np.asarray(graph_ptr, dtype=np.int64)
+    edges, origs, ids = [], [], []
+    off = 0
+    out_ptr = [0]
+    for g in range(len(gp) - 1):
+        lo, hi = gp[g], gp[g + 1]
+        sel = (ei[0] >= lo) & (ei[0] < hi)
+        res = ego_nets(ei[:, sel] - lo, int(hi - lo), radius)
+        edges.append(res['edge_index'] + off)
+        origs.append(res['orig_id'] + lo)
+        ids.append(res['node_id_index'] + off)
+        off += res['num_nodes']
+        out_ptr.append(off)
+    return dict(num_nodes=off, edge_index=np.concatenate(edges, axis=1) if edges else np.zeros((2, 0), np.int64),
+                orig_id=np.concatenate(origs) if origs else np.zeros(0, np.int64),
+                node_id_index=np.concatenate(ids) if ids else np.zeros(0, np.int64),
+                out_node_ptr=np.array(out_ptr, dtype=np.int64))

@@ -1,0 +1,88 @@
+"""ID-GNN Fast cycle features: GPU sparse propagation vs (a) the golden output of the reference's own
+compute_identity, (b) the dense oracle; integer closed-walk counts bit-exact vs the int64 oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from graphgym_b200.contrib.transform.identity import closed_walk_counts, compute_identity
+from oracle import identity as oid
+from util import FP32_TOL, random_graph, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_reference_compute_identity(cuda, golden_dir):
+    d = np.load(os.path.join(golden_dir, 'identity.npz'))
+    for name in d['names']:
+        ei = torch.from_numpy(d[f'{name}/edge_index']).to(cuda)
+        n, k = int(d[f'{name}/n']), int(d[f'{name}/k'])
+        got = compute_identity(ei, n, k)
+        assert got.shape == (n, k)
+        assert rel_err(got, d[f'{name}/identity']) < FP32_TOL, name
+        got_general = compute_identity(ei, n, k, symmetric=False)   # k hops, diagonal read
+        assert rel_err(got_general, d[f'{name}/identity']) < FP32_TOL, name
+
+
+@pytest.mark.parametrize('n,k', [(300, 10), (1000, 7), (129, 1)])
+def test_symmetric_graph_vs_dense_oracle(cuda, n, k):
+    ei = random_graph(n, n, 4 * n, loops=5, symmetric=True)
+    want = oid.compute_identity(ei, n, k, torch.float64)
+    assert rel_err(compute_identity(ei.to(cuda), n, k), want) < FP32_TOL
+
+
+def test_directed_graph_needs_general_mode(cuda):
+    n, k = 200, 6
+    ei = random_graph(3, n, 1500, loops=10, dups=10)
+    want = oid.compute_identity(ei, n, k, torch.float64)
+    assert rel_err(compute_identity(ei.to(cuda), n, k, symmetric=False), want) < FP32_TOL
+
+
+def test_block_diagonal_batch(cuda):
+    """256-graph batches of 64-node graphs are how GraphGym feeds this (feature_augment.py:263-266)."""
+    sizes = [64, 64, 17, 64, 130, 1, 64]
+    ptr = np.concatenate([[0], np.cumsum(sizes)])
+    parts = []
+    for g, s in enumerate(sizes):
+        if s > 1:
+            parts.append(random_graph(g, s, 3 * s, symmetric=True) + int(ptr[g]))
+    ei = torch.cat(parts, dim=1)
+    n, k = int(ptr[-1]), 10
+    got = compute_identity(ei.to(cuda), n, k, graph_ptr=torch.from_numpy(ptr))
+    want = oid.compute_identity(ei, n, k, torch.float64)
+    assert rel_err(got, want) < FP32_TOL
+    full = compute_identity(ei.to(cuda), n, k)
+    assert rel_err(full, want) < FP32_TOL
+
+
+@pytest.mark.parametrize('symmetric', [True, False])
+def test_closed_walk_counts_bit_exact(cuda, symmetric):
+    n, k = 150, 8
+    ei = random_graph(11, n, 500, loops=6, dups=12, symmetric=symmetric)
+    got, overflow = closed_walk_counts(ei.to(cuda), n, k, symmetric=symmetric)
+    want = oid.closed_walks(ei.numpy(), n, k)
+    assert overflow == 0
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_closed_walk_known_answers_and_overflow(cuda):
+    def sym(edges):
+        e = np.array(edges, dtype=np.int64).T
+        return torch.from_numpy(np.concatenate([e, e[::-1]], axis=1))
+    k3, _ = closed_walk_counts(sym([(0, 1), (1, 2), (0, 2)]).to(cuda), 3, 5)
+    assert k3.cpu().tolist() == [[0, 2, 2, 6, 10]] * 3
+    c4, _ = closed_walk_counts(sym([(0, 1), (1, 2), (2, 3), (3, 0)]).to(cuda), 4, 5)
+    assert c4.cpu().tolist() == [[0, 2, 0, 8, 0]] * 4
+    # K64: diag(A^p) = (63^p + 63 (-1)^p) / 64 exceeds int64 from p = 11 on
+    n = 64
+    a = torch.combinations(torch.arange(n), 2).t()
+    ei = torch.cat([a, a.flip(0)], dim=1)
+    got, overflow = closed_walk_counts(ei.to(cuda), n, 12)
+    exact = [(63 ** p + 63 * (-1) ** p) // 64 for p in range(1, 13)]
+    for p in range(12):
+        if exact[p] < 2 ** 63:
+            assert got[:, p].cpu().tolist() == [exact[p]] * n
+        else:
+            assert (got[:, p] == torch.iinfo(torch.int64).max).all()
+    assert overflow == n * sum(e >= 2 ** 63 for e in exact)

@@ -183,21 +183,55 @@ def loop_policy_for(layer_name):
 def run_ours(args, spec, rank, world, dev):
     import torch.distributed as dist
 
-    from graphgym_b200 import ops
+    from graphgym_b200 import ops, parallel
     from graphgym_b200.graph import clear_cache, get_layout
     from graphgym_b200.models.layer import Batch, layer_dict
-    if world > 1:
-        raise SystemExit('multi-GPU bench: see bench_dist path (not wired in this build)')
     name, fin, fout = spec['layer'], spec['fin'], spec['fout']
+    multi = world > 1
+    if multi:
+        if name != 'gcnconv':
+            raise SystemExit(f'--gpus {world}: the row-partitioned path is wired for gcnconv workloads '
+                             f'(got {name}); run this workload with --gpus 1')
+        dist.init_process_group('nccl', device_id=dev)
     t0 = time.time()
     n, ei = gen_graph(spec, dev, seed=0)
     x = gen_features(n, fin, dev)
-    torch.manual_seed(0)
-    layer = layer_dict[name](fin, fout, bias=True).to(dev)
     gy = gen_features(n, fout, dev, seed=7)
+    if multi:  # every rank must see the same bits: rank 0's draw wins
+        for t in (ei, x, gy):
+            dist.broadcast(t, src=0)
+    torch.manual_seed(0)
+    part = parallel.RowPartition(n, world, rank)
+    if multi:
+        layer = parallel.RowPartitionedGCN(fin, fout, bias=True).to(dev)
+        x_loc, gy_loc = x[part.lo:part.hi].contiguous(), gy[part.lo:part.hi].contiguous()
+    else:
+        layer = layer_dict[name](fin, fout, bias=True).to(dev)
+        x_loc, gy_loc = x, gy
     ids = torch.arange(0, n, 64, device=dev) if 'id' in name else None
     torch.cuda.synchronize()
     gen_s = time.time() - t0
+    policy = loop_policy_for(name)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if not multi:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if not multi:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
     # ---- device-resident steps -------------------------------------------------------------
     spmm_events = []
@@ -211,45 +245,61 @@ def run_ours(args, spec, rank, world, dev):
         spmm_events.append((s, e))
         return out
 
-    def step(x_dev, ei_dev):
+    def bias_grad():
+        return layer.model.bias.grad
+
+    def step(x_dev, ei_dev, playout=None):
         layer.zero_grad(set_to_none=True)
-        b = layer(Batch(x_dev, ei_dev, ids))
-        b.node_feature.backward(gy)
-        return layer.model.bias.grad if getattr(layer.model, 'bias', None) is not None else b.node_feature
+        if multi:
+            y = layer(x_dev, playout)
+            y.backward(gy_loc)
+            parallel.allreduce_grads(layer)
+        else:
+            b = layer(Batch(x_dev, ei_dev, ids))
+            b.node_feature.backward(gy_loc)
+        return bias_grad()
 
     t0 = time.time()
-    lay = get_layout(ei, n, loop_policy_for(name))
-    slots = lay.csr.num_slots
-    _ = lay.csc
+    if multi:
+        playout = parallel.PartitionedLayout(ei, n, policy, part)
+        playout.weights('gcn_tgt')
+        slots_local, rows_local = playout.csr.num_slots, part.rows
+    else:
+        playout = None
+        lay = get_layout(ei, n, policy)
+        slots_local, rows_local = lay.csr.num_slots, n
+        _ = lay.csc
+    slots = int(sum_over_ranks(slots_local))
     torch.cuda.synchronize()
     layout_first_s = time.time() - t0
     for _ in range(args.warmup):
-        step(x, ei)
-    torch.cuda.synchronize()
-    import graphgym_b200.functional as F_
-    F_.ops.spmm = timed_spmm
+        step(x_loc, ei, playout)
+    sync_all()
+    ops.spmm = timed_spmm
     launches0 = ops.launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(dev.index or 0) as clocks:
-        torch.cuda.synchronize()
+        sync_all()
         start.record()
         for _ in range(args.steps):
-            step(x, ei)
+            step(x_loc, ei, playout)
         end.record()
-        torch.cuda.synchronize()
-    F_.ops.spmm = orig_spmm
-    launches = ops.launch_count() - launches0
-    ms = start.elapsed_time(end) / args.steps
+        sync_all()
+    ops.spmm = orig_spmm
+    launches = int(sum_over_ranks(ops.launch_count() - launches0))
+    ms = max_over_ranks(start.elapsed_time(end)) / args.steps
     ef, f_agg = edge_feat_per_step(name, n, slots, fin, fout)
     value = ef / (ms * 1e-3) / 1e9
 
     spmm_ms = [s.elapsed_time(e) for s, e in spmm_events]
     weighted = name in ('gcnconv', 'gcnidconv', 'gatconv', 'gatidconv')
-    per_launch_bytes = spmm_bytes(n, slots, f_agg, weighted)
+    per_launch_bytes = spmm_bytes(rows_local, slots_local, f_agg, weighted)
     avg_spmm_ms = float(np.mean(spmm_ms)) if spmm_ms else float('nan')
     peak, peak_src = load_peaks()
     achieved = per_launch_bytes / (avg_spmm_ms * 1e-3) / 1e9
-    roofline = {'bound': 'hbm', 'kernel': 'spmm_mp_kernel + fixup (merge-path CSR aggregation; fwd on CSR and bwd on CSC)',
+    roofline = {'bound': 'hbm',
+                'kernel': 'spmm_mp_kernel + fixup (merge-path CSR aggregation; fwd on CSR and bwd on CSC)'
+                          + (' — rank 0 of %d, rank-local rows' % world if multi else ''),
                 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
                 'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': per_launch_bytes,
@@ -258,18 +308,23 @@ def run_ours(args, spec, rank, world, dev):
 
     # ---- layout build alone (amortised over layers/epochs in training; reported, not in `value`) ---
     clear_cache()
-    torch.cuda.synchronize()
+    sync_all()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    lay = get_layout(ei, n, loop_policy_for(name))
-    _ = lay.csr, lay.csc
-    lay.weights('gcn_tgt' if name == 'gcnconv' else 'sum')
+    if multi:
+        pl2 = parallel.PartitionedLayout(ei, n, policy, part)
+        pl2.weights('gcn_tgt')
+        del pl2
+    else:
+        lay = get_layout(ei, n, policy)
+        _ = lay.csr, lay.csc
+        lay.weights('gcn_tgt' if name == 'gcnconv' else 'sum')
     e.record()
     torch.cuda.synchronize()
-    layout_ms = s.elapsed_time(e)
+    layout_ms = max_over_ranks(s.elapsed_time(e))
 
     # ---- end to end: host buffers in, result out, every step ------------------------------------
-    x_host = x.cpu().pin_memory()
+    x_host = x_loc.cpu().pin_memory()
     ei_host = ei.cpu().pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
     res_host = torch.empty(fout, dtype=torch.float32).pin_memory()
@@ -277,27 +332,28 @@ def run_ours(args, spec, rank, world, dev):
     def e2e_step():
         xd = x_host.to(dev, non_blocking=True)
         eid = ei_host.to(dev, non_blocking=True)
-        r = step(xd, eid)
+        pl = parallel.PartitionedLayout(eid, n, policy, part) if multi else None
+        r = step(xd, eid, pl)
         res_host.copy_(r.detach().reshape(-1)[:fout], non_blocking=True)
 
     for _ in range(2):
         e2e_step()
-    torch.cuda.synchronize()
+    sync_all()
     s.record()
     for _ in range(e2e_steps):
         e2e_step()
     e.record()
-    torch.cuda.synchronize()
-    e2e_ms = s.elapsed_time(e) / e2e_steps
+    sync_all()
+    e2e_ms = max_over_ranks(s.elapsed_time(e)) / e2e_steps
+    h2d = int(sum_over_ranks(x_host.numel() * 4 + ei_host.numel() * 8))
     e2e = {'value': round(ef / (e2e_ms * 1e-3) / 1e9, 3), 'unit': 'GEdge-feat/s',
            'ms_per_step': round(e2e_ms, 3), 'steps': e2e_steps,
-           'h2d_bytes_per_step': int(x_host.numel() * 4 + ei_host.numel() * 8),
-           'd2h_bytes_per_step': int(fout * 4),
-           'includes': 'H2D of node_feature+edge_index from pinned memory, CSR+CSC layout build, layer '
-                       'fwd+bwd via layer_dict API, D2H of the bias gradient'}
+           'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(fout * 4 * world),
+           'includes': 'H2D of node_feature rows + edge_index from pinned memory on every rank, CSR+CSC '
+                       'layout build, layer fwd+bwd via the layer API, D2H of the bias gradient'}
     del x_host, ei_host
 
-    cpu = cpu_baseline(spec, seconds=args.cpu_seconds) if rank == 0 and not args.no_cpu else None
+    cpu = cpu_baseline(spec, seconds=args.cpu_seconds) if rank == 0 and not args.no_cpu and not multi else None
     out = {
         'metric': 'layer fwd+bwd GEdge-feat/s', 'value': round(value, 3), 'unit': 'GEdge-feat/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms, 4),
@@ -305,6 +361,8 @@ def run_ours(args, spec, rank, world, dev):
         'data': 'synthetic (seeded power-law / BA / uniform generators in bench.py; random-init glorot weights)',
         'config': {'workload': spec['desc'], 'layer': name, 'nodes': n, 'edges_directed': int(ei.size(1)),
                    'slots_after_loop_policy': slots, 'f_in': fin, 'f_out': fout, 'f_aggregated': f_agg,
+                   'parallelism': ('row-partitioned x%d, halo all-gather (NCCL) fwd and bwd' % world) if multi
+                   else 'single GPU',
                    'l2_policy': 'inputs larger than L2 (feature matrix %.0f MB vs 126 MB L2)' % (n * f_agg * 4 / 1e6)
                    if n * f_agg * 4 > 126e6 else 'inputs fit L2: launch-bound workload, no flush',
                    'layout_cached_across_steps': True},
@@ -313,6 +371,9 @@ def run_ours(args, spec, rank, world, dev):
         'layout_build_ms': round(layout_ms, 3), 'graph_gen_s': round(gen_s, 2),
         'layout_first_call_s': round(layout_first_s, 3),
     }
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
     return out
 
 

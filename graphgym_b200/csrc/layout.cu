@@ -38,7 +38,8 @@ static inline int grid_for(int64_t n, int per_thread = 1) {
 
 __global__ void __launch_bounds__(kThreads)
     layout_prep_kernel(const int64_t* __restrict__ ei, int64_t E, int64_t N, int removes, int adds,
-                       int by_source, uint32_t* __restrict__ keys, int32_t* __restrict__ bad_count) {
+                       int by_source, int64_t range_lo, int64_t range_hi, uint32_t* __restrict__ keys,
+                       int32_t* __restrict__ bad_count) {
     int64_t total = E + (adds ? N : 0);
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
@@ -47,10 +48,13 @@ __global__ void __launch_bounds__(kThreads)
             int64_t s = ei[e], t = ei[E + e];
             bool bad = s < 0 || s >= N || t < 0 || t >= N;
             if (bad) atomicAdd(bad_count, 1);
-            bool drop = bad || (removes && s == t);
-            key = drop ? (uint32_t)N : (uint32_t)(by_source ? s : t);
+            int64_t k = by_source ? s : t;
+            // row-partitioned layouts keep only the groups this rank owns
+            bool drop = bad || (removes && s == t) || k < range_lo || k >= range_hi;
+            key = drop ? (uint32_t)N : (uint32_t)k;
         } else {
-            key = (uint32_t)(e - E);
+            int64_t i = e - E;
+            key = (i >= range_lo && i < range_hi) ? (uint32_t)i : (uint32_t)N;
         }
         keys[e] = key;
     }
@@ -207,7 +211,18 @@ size_t gg_layout_build_workspace_bytes(int64_t E, int64_t N, int policy) {
 int gg_layout_build(const int64_t* edge_index, int64_t E, int64_t N, int policy, int group_by,
                     int32_t* rowptr, int32_t* nbr, int32_t* perm, int32_t* rowid, void* workspace,
                     size_t workspace_bytes, gg_stream_t stream) {
+    return gg_layout_build_range(edge_index, E, N, policy, group_by, 0, N, rowptr, nbr, perm, rowid,
+                                 workspace, workspace_bytes, stream);
+}
+
+int gg_layout_build_range(const int64_t* edge_index, int64_t E, int64_t N, int policy, int group_by,
+                          int64_t range_begin, int64_t range_end, int32_t* rowptr, int32_t* nbr,
+                          int32_t* perm, int32_t* rowid, void* workspace, size_t workspace_bytes,
+                          gg_stream_t stream) {
     GG_REQUIRE(E >= 0 && N >= 0, "gg_layout_build: negative size");
+    GG_REQUIRE(range_begin >= 0 && range_begin <= range_end && range_end <= N,
+               "gg_layout_build_range: bad range [%lld, %lld) of %lld", (long long)range_begin,
+               (long long)range_end, (long long)N);
     GG_REQUIRE(policy >= GG_LOOPS_KEEP && policy <= GG_LOOPS_ADD, "gg_layout_build: policy=%d", policy);
     GG_REQUIRE(group_by == GG_BY_TARGET || group_by == GG_BY_SOURCE, "gg_layout_build: group_by=%d",
                group_by);
@@ -238,7 +253,8 @@ int gg_layout_build(const int64_t* edge_index, int64_t E, int64_t N, int policy,
     }
     layout_prep_kernel<<<grid_for(M, 4), kThreads, 0, st>>>(edge_index, E, N, policy_removes(policy),
                                                            policy_adds(policy),
-                                                           group_by == GG_BY_SOURCE, keys, bad);
+                                                           group_by == GG_BY_SOURCE, range_begin,
+                                                           range_end, keys, bad);
     GG_LAUNCHED();
     int rc = gg_sort_pairs_u32(keys, nullptr, sorted, reinterpret_cast<uint32_t*>(perm), M,
                                bits_for(N), sort_ws, gg_sort_pairs_workspace_bytes(M), stream);

@@ -82,9 +82,12 @@ class Csr:
         return self._plan
 
 
-def layout_build(edge_index, num_nodes, policy=LOOPS_KEEP, group_by=BY_TARGET):
+def layout_build(edge_index, num_nodes, policy=LOOPS_KEEP, group_by=BY_TARGET, row_range=None):
     """COO ``edge_index[2,E]`` (int64, row 0 = source, row 1 = target) -> Csr.  One host sync to
-    read E' (self-loop removal makes it data dependent)."""
+    read E' (self-loop removal makes it data dependent).
+
+    ``row_range=(lo, hi)``: rank-local layout of a row partition — only groups in [lo, hi) are kept,
+    the returned Csr has hi-lo rows (rowptr is the [lo, hi] slice) and GLOBAL ids in ``nbr`` / ``rowid``."""
     _need_cuda(edge_index)
     if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise ValueError(f"edge_index must be int64 [2,E], got {tuple(edge_index.shape)} {edge_index.dtype}")
@@ -99,13 +102,17 @@ def layout_build(edge_index, num_nodes, policy=LOOPS_KEEP, group_by=BY_TARGET):
     rowid = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
     ws_bytes = int(L.gg_layout_build_workspace_bytes(E, N, policy))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(L.gg_layout_build(_ptr(ei), E, N, policy, group_by, _ptr(rowptr), _ptr(nbr), _ptr(perm),
-                            _ptr(rowid), _ptr(ws), ws_bytes, _stream()), "gg_layout_build")
+    lo, hi = (0, N) if row_range is None else (int(row_range[0]), int(row_range[1]))
+    check(L.gg_layout_build_range(_ptr(ei), E, N, policy, group_by, lo, hi, _ptr(rowptr), _ptr(nbr),
+                                  _ptr(perm), _ptr(rowid), _ptr(ws), ws_bytes, _stream()),
+          "gg_layout_build_range")
     bad = int(ws[:4].view(torch.int32).item())
     if bad:
         raise ValueError(f"edge_index holds {bad} edge(s) with an endpoint outside [0, {N})")
     num_slots = int(rowptr[N].item())
-    return Csr(rowptr, nbr[:num_slots], perm[:num_slots], rowid[:num_slots], num_slots, N, E, policy,
+    if row_range is not None:
+        rowptr = rowptr[lo:hi + 1]   # rows before lo are empty, so rowptr[lo] == 0
+    return Csr(rowptr, nbr[:num_slots], perm[:num_slots], rowid[:num_slots], num_slots, hi - lo, E, policy,
                group_by)
 
 

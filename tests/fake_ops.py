@@ -1,0 +1,84 @@
+"""CPU stand-ins for the gg_* kernels, built on the oracle, used ONLY by the world_size-2 gloo test of the
+row-partitioned host logic (there is no GPU in the CPU test tier).  They mirror the signatures of
+graphgym_b200.ops; the real ops reject CPU tensors."""
+import numpy as np
+import torch
+
+from graphgym_b200 import ops
+from oracle import layout as olayout
+
+
+def layout_build(edge_index, num_nodes, policy=0, group_by=0, row_range=None):
+    n = int(num_nodes)
+    lo, hi = (0, n) if row_range is None else row_range
+    src, tgt, eid = olayout.edited_edges(edge_index.numpy(), n, policy)
+    key, other = (tgt, src) if group_by == 0 else (src, tgt)
+    keep = (key >= lo) & (key < hi)
+    key, other, eid = key[keep], other[keep], eid[keep]
+    order = np.argsort(key, kind='stable')
+    rowptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(key, minlength=n), out=rowptr[1:])
+    t = lambda a: torch.from_numpy(a.astype(np.int32))
+    return ops.Csr(t(rowptr[lo:hi + 1]), t(other[order]), t(eid[order]), t(key[order]), int(rowptr[-1]), hi - lo,
+                   edge_index.size(1), policy, group_by)
+
+
+def segment_degree(csr, w_slot=None):
+    assert w_slot is None
+    return (csr.rowptr[1:] - csr.rowptr[:-1]).float()
+
+
+def gcn_norm(csr, deg, w_slot=None):
+    dis = torch.where(deg > 0, deg.pow(-0.5), torch.zeros_like(deg))
+    return dis[csr.rowid.long()] * dis[csr.nbr.long()]
+
+
+def mean_weights(csr_t, deg):
+    inv = torch.where(deg > 0, 1.0 / deg, torch.zeros_like(deg))
+    return inv[csr_t.nbr.long()]
+
+
+def spmm(csr, x, w_slot=None, reduce=0, x_self=None, self_scale=0.0, bias=None, out=None):
+    rows = csr.num_nodes
+    seg = torch.repeat_interleave(torch.arange(rows), (csr.rowptr[1:] - csr.rowptr[:-1]).long())
+    msg = x[csr.nbr.long()]
+    if w_slot is not None:
+        msg = msg * w_slot.view(-1, 1)
+    res = torch.zeros((rows, x.size(1)), dtype=x.dtype).index_add_(0, seg, msg)
+    if reduce == 1:
+        res = res / (csr.rowptr[1:] - csr.rowptr[:-1]).clamp(min=1).view(-1, 1)
+    if x_self is not None:
+        res = res + self_scale * x_self
+    if bias is not None:
+        res = res + bias
+    return res
+
+
+def id_gemm(segments, n, f, b_trans=False, bias=None, act=0, relu_mask=None, out=None):
+    res = torch.zeros((n, f))
+    for a, b, scale in segments:
+        y = a @ (b.t() if b_trans else b)
+        res = res + (y if scale is None else y * scale.view(-1, 1))
+    if bias is not None:
+        res = res + bias
+    if act == 1:
+        res = res.relu()
+    if relu_mask is not None:
+        res = res * (relu_mask > 0)
+    return res
+
+
+def gemm_tn(a, g, row_index=None):
+    if row_index is not None:
+        a, g = a[row_index], g[row_index]
+    return a.t() @ g
+
+
+def colsum(g):
+    return g.sum(0)
+
+
+def install(monkeypatch_setattr):
+    for name in ('layout_build', 'segment_degree', 'gcn_norm', 'mean_weights', 'spmm', 'id_gemm', 'gemm_tn',
+                 'colsum'):
+        monkeypatch_setattr(ops, name, globals()[name])

@@ -1,0 +1,81 @@
+"""Row-partitioned layer on 2 ranks over gloo (CPU): partition bounds, padded all-gather of the halo,
+degree exchange, backward all-gather and gradient all-reduce must reproduce the single-process oracle.
+The kernels are replaced by oracle-backed stand-ins (tests/fake_ops.py) — this tier has no GPU; the same
+code path runs on NCCL in tests/test_parallel_gpu.py and bench.py --gpus N."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, ret):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import fake_ops
+        from graphgym_b200 import ops, parallel
+        from oracle import layers as olayers
+        from util import random_graph
+        fake_ops.install(lambda mod, name, fn: setattr(mod, name, fn))
+        torch.manual_seed(0)
+        fin, fout = 12, 8
+        ei = random_graph(3, n, 6 * n, loops=5, dups=7)
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(n, fin, generator=g)
+        gy = torch.randn(n, fout, generator=g)
+        part = parallel.RowPartition(n, world, rank)
+        layer = parallel.RowPartitionedGCN(fin, fout, bias=True)   # same seed on every rank
+        with torch.no_grad():
+            layer.model.bias.uniform_(-0.5, 0.5)
+        playout = parallel.PartitionedLayout(ei, n, ops.LOOPS_ADD_REMAINING, part)
+        xl = x[part.lo:part.hi].clone().requires_grad_(True)
+        y = layer(xl, playout)
+        y.backward(gy[part.lo:part.hi])
+        parallel.allreduce_grads(layer)
+        # single-process oracle
+        P = {k: v.detach().clone().requires_grad_(True) for k, v in layer.model.named_parameters()}
+        xo = x.clone().requires_grad_(True)
+        yo = olayers.gcnconv(xo, ei, P['weight'], P['bias'])
+        yo.backward(gy)
+        ok = torch.allclose(y.detach(), yo.detach()[part.lo:part.hi], atol=1e-5)
+        ok &= torch.allclose(xl.grad, xo.grad[part.lo:part.hi], atol=1e-5)
+        ok &= torch.allclose(layer.model.weight.grad, P['weight'].grad, atol=1e-4)
+        ok &= torch.allclose(layer.model.bias.grad, P['bias'].grad, atol=1e-4)
+        ret[rank] = bool(ok) and part.rows == (part.hi - part.lo)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('n', [40, 41])   # 41: the last rank's block is shorter -> padded all-gather
+def test_row_partitioned_gcn_world2(n):
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), n, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_partition_bounds_cover_all_rows():
+    sys.path.insert(0, os.path.dirname(HERE))
+    from graphgym_b200.parallel import RowPartition
+    for n in (0, 1, 7, 8, 9, 2449029):
+        for world in (1, 2, 4, 8):
+            spans = [RowPartition(n, world, r) for r in range(world)]
+            assert spans[0].lo == 0 and spans[-1].hi == n
+            assert all(a.hi == b.lo for a, b in zip(spans, spans[1:]))
+            assert all(s.rows <= s.per for s in spans)

@@ -1,0 +1,74 @@
+"""Row-partitioned GCN layer on 2 GPUs over NCCL == the single-GPU layer (needs >= 2 visible GPUs;
+skipped on a 1-GPU box — the host logic is covered on CPU by test_parallel_gloo.py)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dev = torch.device('cuda', rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    try:
+        from graphgym_b200 import ops, parallel
+        from graphgym_b200.models.layer import Batch, layer_dict
+        from util import powerlaw_graph, rel_err
+        n, fin, fout = 30001, 100, 128
+        ei = powerlaw_graph(2, n, 12).to(dev)
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(n, fin, generator=g).to(dev)
+        gy = torch.randn(n, fout, generator=g).to(dev)
+        torch.manual_seed(0)
+        ref = layer_dict['gcnconv'](fin, fout, bias=True).to(dev)
+        torch.manual_seed(0)
+        layer = parallel.RowPartitionedGCN(fin, fout, bias=True).to(dev)
+        with torch.no_grad():
+            ref.model.bias.uniform_(-0.5, 0.5)
+            layer.model.bias.copy_(ref.model.bias)
+        part = parallel.RowPartition(n, world, rank)
+        playout = parallel.PartitionedLayout(ei, n, ops.LOOPS_ADD_REMAINING, part)
+        xl = x[part.lo:part.hi].clone().requires_grad_(True)
+        y = layer(xl, playout)
+        y.backward(gy[part.lo:part.hi])
+        parallel.allreduce_grads(layer)
+        xr = x.clone().requires_grad_(True)
+        yr = ref(Batch(xr, ei)).node_feature
+        yr.backward(gy)
+        errs = [rel_err(y.detach(), yr.detach()[part.lo:part.hi]), rel_err(xl.grad, xr.grad[part.lo:part.hi]),
+                rel_err(layer.model.weight.grad, ref.model.weight.grad),
+                rel_err(layer.model.bias.grad, ref.model.bias.grad)]
+        # the data path is rank-local in a fixed order: owned rows are BITWISE the single-GPU rows
+        bitwise = torch.equal(y.detach(), yr.detach()[part.lo:part.hi])
+        ret[rank] = (max(errs) < 1e-5, bitwise, errs)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_row_partition_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    for r in range(2):
+        ok, bitwise, errs = ret[r]
+        assert ok, errs
+        assert bitwise

@@ -10,7 +10,8 @@ their CSR rows (global source ids) and the matching output rows.
   backward  all-gather of dOut  ->  local CSC SpMM (rows = owned SOURCE nodes, global target ids)
             gives dH_r  ->  dW_r = X_r^T dH_r, all-reduced with the other (tiny) parameter gradients.
 Both directions use the same collective, and every reduction on the data path is rank-local in a
-fixed order, so the N-GPU result equals the 1-GPU result up to fp32 re-association of dW.
+fixed order: the N-GPU result equals the 1-GPU result up to fp32 re-association (rows that the
+merge-path plan splits at different places, and the all-reduced dW).
 
 The collective is issued through ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests).
 """

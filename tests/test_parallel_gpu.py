@@ -56,9 +56,10 @@ def _worker(rank, world, port, ret):
         errs = [rel_err(y.detach(), yr.detach()[part.lo:part.hi]), rel_err(xl.grad, xr.grad[part.lo:part.hi]),
                 rel_err(layer.model.weight.grad, ref.model.weight.grad),
                 rel_err(layer.model.bias.grad, ref.model.bias.grad)]
-        # the data path is rank-local in a fixed order: owned rows are BITWISE the single-GPU rows
-        bitwise = torch.equal(y.detach(), yr.detach()[part.lo:part.hi])
-        ret[rank] = (max(errs) < 1e-5, bitwise, errs)
+        # the merge-path plan cuts rank-local rows at other places than the global plan, so rows split
+        # over items re-associate their fp32 partial sums; most rows are bitwise the single-GPU rows
+        same = (y.detach() == yr.detach()[part.lo:part.hi]).all(dim=1).float().mean().item()
+        ret[rank] = (max(errs) < 1e-5, same > 0.5, errs)
     finally:
         dist.destroy_process_group()
 

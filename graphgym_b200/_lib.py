@@ -55,6 +55,9 @@ SIGNATURES = {
                                c_i64, c_int, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_size, c_int, c_ptr]),
     "gg_id_gemm_f32": (c_int, [ctypes.POINTER(GemmSegment), c_int, c_int, c_i64, c_i64, c_ptr, c_int,
                                c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
+    "gg_id_gemm_tc_workspace_bytes": (c_size, [ctypes.POINTER(GemmSegment), c_int, c_i64]),
+    "gg_id_gemm_tc_f32": (c_int, [ctypes.POINTER(GemmSegment), c_int, c_int, c_i64, c_i64, c_ptr, c_int,
+                                  c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_size, c_ptr]),
     "gg_gemm_tn_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
     "gg_gemm_tn_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64,
                                c_ptr, c_size, c_ptr]),

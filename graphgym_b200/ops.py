@@ -20,6 +20,7 @@ ACT_NONE, ACT_RELU = 0, 1
 import os as _os
 SPMM_ALGO = _os.environ.get("GG_SPMM_ALGO", "auto")    # auto | mp | row
 SPMM_STAGE = _os.environ.get("GG_SPMM_STAGE", "tma")   # tma | ldg
+GEMM_MODE = _os.environ.get("GG_GEMM", "tc")           # tc (tcgen05 3xTF32) | simt (fp32 CUDA cores)
 
 
 def _stream():
@@ -260,8 +261,15 @@ def id_gemm(segments, n, f, b_trans=False, bias=None, act=ACT_NONE, relu_mask=No
         relu_mask, ld_mask = _rows(relu_mask, "relu_mask")
     if bias is not None:
         bias = bias.contiguous()
-    check(lib().gg_id_gemm_f32(arr, len(segments), int(b_trans), n, f, _ptr(bias), act, _ptr(relu_mask),
-                               ld_mask, _ptr(out), ldo, _stream()), "gg_id_gemm_f32")
+    L = lib()
+    if GEMM_MODE == "tc" and n > 0 and f > 0:
+        ws_bytes = int(L.gg_id_gemm_tc_workspace_bytes(arr, len(segments), f))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(L.gg_id_gemm_tc_f32(arr, len(segments), int(b_trans), n, f, _ptr(bias), act, _ptr(relu_mask),
+                                  ld_mask, _ptr(out), ldo, _ptr(ws), ws_bytes, _stream()), "gg_id_gemm_tc_f32")
+        return out
+    check(L.gg_id_gemm_f32(arr, len(segments), int(b_trans), n, f, _ptr(bias), act, _ptr(relu_mask),
+                           ld_mask, _ptr(out), ldo, _stream()), "gg_id_gemm_f32")
     return out
 
 

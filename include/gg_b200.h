@@ -192,6 +192,15 @@ int gg_id_gemm_f32(const gg_gemm_segment* segments_host, int num_segments, int b
                    int64_t f, const float* bias, int act, const float* relu_mask, int64_t ld_mask,
                    float* out, int64_t ldo, gg_stream_t stream);
 
+/* The same transform on the tensor cores: tcgen05.mma kind::tf32 with a 3xTF32 operand split
+ * (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM), fp32 in / fp32 out, <= 1e-5 relative against the
+ * fp32 reference.  Same arguments as gg_id_gemm_f32 plus a workspace for the pre-split B operand images
+ * (gg_id_gemm_tc_workspace_bytes).  See csrc/gemm_tc.cu. */
+size_t gg_id_gemm_tc_workspace_bytes(const gg_gemm_segment* segments_host, int num_segments, int64_t f);
+int gg_id_gemm_tc_f32(const gg_gemm_segment* segments_host, int num_segments, int b_trans, int64_t n,
+                      int64_t f, const float* bias, int act, const float* relu_mask, int64_t ld_mask,
+                      float* out, int64_t ldo, void* workspace, size_t workspace_bytes, gg_stream_t stream);
+
 /* Weight gradient: out[K,F] = sum_{r<n} A[row(r),:]^T * G[row(r),:], row(r) = row_index ? row_index[r] : r
  * (dW = X^T dH over all N rows; dW_id = X[id]^T dH[id] over the M centre rows, duplicates counted
  * like index_add_, ref: idconv.py:64-67).  Deterministic two-stage split over rows. */

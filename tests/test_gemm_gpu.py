@@ -8,6 +8,13 @@ from util import FP32_TOL, rel_err
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=['tc', 'simt'], autouse=True)
+def gemm_mode(request, monkeypatch):
+    """every test runs on the tcgen05 3xTF32 kernel and on the fp32 CUDA-core kernel"""
+    monkeypatch.setattr(ops, 'GEMM_MODE', request.param)
+    return request.param
+
+
 @pytest.mark.parametrize('n,k,f', [(1, 1, 1), (37, 12, 16), (300, 1433, 128), (1000, 100, 128),
                                    (513, 128, 256), (129, 7, 130), (64, 1, 128), (2000, 256, 256)])
 @pytest.mark.parametrize('b_trans', [False, True])
@@ -83,3 +90,20 @@ def test_row_helpers(cuda):
     assert torch.equal(got, base.index_add(0, ids, upd))
     y = torch.randn(50, 20, generator=g)
     assert torch.equal(ops.relu_grad(x.to(cuda), y.to(cuda)).cpu(), x * (y > 0))
+
+
+def test_tc_gemm_four_segments_sage_id_shape(cuda):
+    """[x | mean] (W, W_id on centres): 4 K-segments into one TMEM tile, centres only in the first tile."""
+    g = torch.Generator().manual_seed(5)
+    n, k, f = 900, 20, 136
+    x, m = torch.randn(n, k, generator=g), torch.randn(n, k, generator=g)
+    w, wid = torch.randn(2 * k, f, generator=g), torch.randn(2 * k, f, generator=g)
+    ids = torch.arange(0, 60, 3)
+    cnt = ops.id_count(ids.to(cuda), n)
+    d = lambda t: t.to(cuda)
+    got = ops.id_gemm([(d(x), d(w[:k]), None), (d(m), d(w[k:]), None), (d(x), d(wid[:k]), cnt),
+                       (d(m), d(wid[k:]), cnt)], n, f)
+    z = torch.cat([x, m], 1).double()
+    want = z @ w.double()
+    want[ids] += z[ids] @ wid.double()
+    assert rel_err(got, want) < FP32_TOL

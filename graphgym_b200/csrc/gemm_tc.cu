@@ -4,7 +4,7 @@
 //   out[N,F] = act( sum_g diag(scale_g) A_g[N,K_g] B_g + bias ) .* (mask > 0)       (same contract as gemm.cu)
 //
 // fp32 parity (<= 1e-5 relative) through a tensor core: 3xTF32.  Every operand is split
-//   x = hi + lo,  hi = x with the low 13 mantissa bits cleared (exactly a TF32 value), lo = x - hi (exact in fp32)
+//   x = hi + lo,  hi = rna_tf32(x), lo = rna_tf32(x - hi)   (round-to-nearest: unbiased, both exact TF32 values)
 // and the product is  hi_a*hi_b + hi_a*lo_b + lo_a*hi_b  (the dropped lo*lo term is ~2^-22 relative),
 // three kind::tf32 MMAs accumulating into the same fp32 TMEM tile.
 //
@@ -51,6 +51,8 @@ struct TcArgs {
     int64_t ld_mask;
     float* out;
     int64_t ldo;
+    int accumulate_out;  // epilogue adds the tile already in `out` (a previous K-chunk's partial)
+    int final_chunk;     // bias / act / mask are applied by the last chunk only
 };
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) {
@@ -112,9 +114,16 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// hi = x rounded to nearest TF32, lo = (x - hi) rounded to nearest TF32: both are exact TF32 values, so
+// the tensor core's own operand truncation never fires and the split error is unbiased.
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    lo = x - hi;
+    hi = rna_tf32(x);
+    lo = rna_tf32(x - hi);
 }
 
 // B operand image: for N-tile nt, k-slab ks: [hi | lo] slabs in the canonical layout,
@@ -283,9 +292,12 @@ __global__ void __launch_bounds__(TC_THREADS, 3) tc_gemm_kernel(TcArgs g) {
                 for (int e = 0; e < 4; ++e) {
                     v[e] = __uint_as_float(acc[j + e]);
                     if (c + e < g.f) {
-                        if (g.bias) v[e] += __ldg(g.bias + c + e);
-                        if (g.act == GG_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
-                        if (g.relu_mask) v[e] = __ldg(g.relu_mask + r * g.ld_mask + c + e) > 0.f ? v[e] : 0.f;
+                        if (g.accumulate_out) v[e] += g.out[r * g.ldo + c + e];  // fp32 round-to-nearest add
+                        if (g.final_chunk) {
+                            if (g.bias) v[e] += __ldg(g.bias + c + e);
+                            if (g.act == GG_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
+                            if (g.relu_mask) v[e] = __ldg(g.relu_mask + r * g.ld_mask + c + e) > 0.f ? v[e] : 0.f;
+                        }
                     }
                 }
                 if (vec_out && c + 3 < g.f) {
@@ -317,12 +329,47 @@ static inline size_t tc_image_floats(int64_t k, int64_t f) {
 
 using namespace gg;
 
+// The tensor core accumulates with truncation: the result is biased towards zero by ~6e-9 * K relative
+// (measured, scratch/tc_err_probe.py).  To stay inside 1e-5 for any K the reduction is cut into launches
+// of at most kTcMaxKPerLaunch k; each launch's partial tile is added to `out` in fp32 (round to nearest)
+// by the next launch's epilogue.  GNN hidden sizes (K <= 512) take one launch.
+constexpr int kTcMaxKPerLaunch = 512;
+
+struct TcPiece {  // a sub-range of a caller segment
+    int seg;
+    int64_t k_off, k_len;
+};
+
+static int tc_plan(const gg_gemm_segment* segs, int num_segments, TcPiece* pieces, int* launch_of, int max_pieces) {
+    int np = 0, launch = 0, in_launch = 0;
+    int64_t k_in_launch = 0;
+    for (int i = 0; i < num_segments; ++i) {
+        int64_t off = 0;
+        while (off < segs[i].k) {
+            int64_t room = kTcMaxKPerLaunch - k_in_launch;
+            if (room < TC_BK || in_launch == GG_GEMM_MAX_SEGMENTS) {
+                ++launch; in_launch = 0; k_in_launch = 0; room = kTcMaxKPerLaunch;
+            }
+            int64_t len = segs[i].k - off;
+            if (len > room) len = room / TC_BK * TC_BK;  // keep slab alignment inside a segment
+            if (np >= max_pieces) return -1;
+            pieces[np] = TcPiece{i, off, len};
+            launch_of[np] = launch;
+            ++np; ++in_launch; k_in_launch += len; off += len;
+        }
+    }
+    return np;
+}
+constexpr int kTcMaxPieces = 256;
+
 extern "C" {
 
 size_t gg_id_gemm_tc_workspace_bytes(const gg_gemm_segment* segs, int num_segments, int64_t f) {
     size_t b = 256;
-    for (int i = 0; i < num_segments; ++i)
-        if (segs[i].k > 0) b += align_up(tc_image_floats(segs[i].k, f) * 4, 256);
+    TcPiece pieces[kTcMaxPieces];
+    int launch_of[kTcMaxPieces];
+    int np = tc_plan(segs, num_segments, pieces, launch_of, kTcMaxPieces);
+    for (int i = 0; i < np; ++i) b += align_up(tc_image_floats(pieces[i].k_len, f) * 4, 256);
     return b;
 }
 
@@ -337,45 +384,64 @@ int gg_id_gemm_tc_f32(const gg_gemm_segment* segs, int num_segments, int b_trans
     GG_REQUIRE(out && ldo >= f && workspace, "gg_id_gemm_tc_f32: bad output / workspace");
     GG_REQUIRE(!relu_mask || ld_mask >= f, "gg_id_gemm_tc_f32: bad mask stride");
     GG_REQUIRE(f < (1 << 20) && tc_ntiles(f) <= 65535, "gg_id_gemm_tc_f32: f out of range");
+    for (int i = 0; i < num_segments; ++i) {
+        const gg_gemm_segment& s = segs[i];
+        GG_REQUIRE(s.k >= 0 && s.k < (1 << 24), "gg_id_gemm_tc_f32: segment %d k out of range", i);
+        if (s.k == 0) continue;
+        GG_REQUIRE(s.a && s.b && s.lda >= s.k, "gg_id_gemm_tc_f32: segment %d has a bad operand", i);
+        GG_REQUIRE(s.ldb >= (b_trans ? s.k : f), "gg_id_gemm_tc_f32: segment %d ldb too small", i);
+    }
+    TcPiece pieces[kTcMaxPieces];
+    int launch_of[kTcMaxPieces];
+    const int np = tc_plan(segs, num_segments, pieces, launch_of, kTcMaxPieces);
+    GG_REQUIRE(np >= 0, "gg_id_gemm_tc_f32: reduction too long (more than %d pieces of %d)", kTcMaxPieces,
+               kTcMaxKPerLaunch);
     if (workspace_bytes < gg_id_gemm_tc_workspace_bytes(segs, num_segments, f)) {
         set_error("gg_id_gemm_tc_f32: workspace %zu < %zu", workspace_bytes,
                   gg_id_gemm_tc_workspace_bytes(segs, num_segments, f));
         return GG_ERR_WORKSPACE;
     }
     cudaStream_t st = as_stream(stream);
-    Carver c(workspace);
-    TcArgs g{};
-    bool vec_a = true;
-    for (int i = 0; i < num_segments; ++i) {
-        const gg_gemm_segment& s = segs[i];
-        GG_REQUIRE(s.k >= 0 && s.k < (1 << 24), "gg_id_gemm_tc_f32: segment %d k out of range", i);
-        TcSegment& t = g.seg[i];
-        t.k = (int)s.k;
-        t.k_slabs = s.k > 0 ? tc_slabs(s.k) : 0;
-        if (s.k == 0) continue;
-        GG_REQUIRE(s.a && s.b && s.lda >= s.k, "gg_id_gemm_tc_f32: segment %d has a bad operand", i);
-        GG_REQUIRE(s.ldb >= (b_trans ? s.k : f), "gg_id_gemm_tc_f32: segment %d ldb too small", i);
-        vec_a = vec_a && (s.k % 4 == 0) && (s.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(s.a) & 15) == 0);
-        float* image = c.take<float>(tc_image_floats(s.k, f));
-        int64_t chunks = (int64_t)tc_ntiles(f) * t.k_slabs * (TC_BK / 4) * TC_BN;
-        int grid = (int)(ceil_div(chunks, 256) < kNumSMs * 8 ? ceil_div(chunks, 256) : kNumSMs * 8);
-        b_image_kernel<<<grid, 256, 0, st>>>(s.b, s.ldb, b_trans, (int)s.k, (int)f, t.k_slabs, tc_ntiles(f), image);
-        GG_LAUNCHED();
-        t.a = s.a; t.lda = s.lda; t.scale = s.scale; t.b_image = image;
-    }
-    g.num_segments = num_segments;
-    g.n = n; g.f = (int)f; g.bias = bias; g.act = act; g.relu_mask = relu_mask; g.ld_mask = ld_mask;
-    g.out = out; g.ldo = ldo;
     static bool attr_done = false;
     if (!attr_done) {
         GG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         GG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         attr_done = true;
     }
+    Carver c(workspace);
+    const int num_launches = np > 0 ? launch_of[np - 1] + 1 : 1;
     dim3 grid((unsigned)ceil_div(n, TC_BM), (unsigned)tc_ntiles(f));
-    if (vec_a) tc_gemm_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g);
-    else tc_gemm_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g);
-    GG_LAUNCHED();
+    int p = 0;
+    for (int l = 0; l < num_launches; ++l) {
+        TcArgs g{};
+        bool vec_a = true;
+        int ns = 0;
+        for (; p < np && launch_of[p] == l; ++p, ++ns) {
+            const gg_gemm_segment& s = segs[pieces[p].seg];
+            const int64_t k_off = pieces[p].k_off, k_len = pieces[p].k_len;
+            TcSegment& t = g.seg[ns];
+            t.k = (int)k_len;
+            t.k_slabs = tc_slabs(k_len);
+            t.a = s.a + k_off; t.lda = s.lda; t.scale = s.scale;
+            vec_a = vec_a && (k_len % 4 == 0) && (s.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(t.a) & 15) == 0);
+            float* image = c.take<float>(tc_image_floats(k_len, f));
+            const float* bsrc = b_trans ? s.b + k_off : s.b + k_off * s.ldb;
+            int64_t chunks = (int64_t)tc_ntiles(f) * t.k_slabs * (TC_BK / 4) * TC_BN;
+            int bgrid = (int)(ceil_div(chunks, 256) < kNumSMs * 8 ? ceil_div(chunks, 256) : kNumSMs * 8);
+            b_image_kernel<<<bgrid, 256, 0, st>>>(bsrc, s.ldb, b_trans, (int)k_len, (int)f, t.k_slabs, tc_ntiles(f),
+                                                  image);
+            GG_LAUNCHED();
+            t.b_image = image;
+        }
+        g.num_segments = ns;
+        g.n = n; g.f = (int)f; g.bias = bias; g.act = act; g.relu_mask = relu_mask; g.ld_mask = ld_mask;
+        g.out = out; g.ldo = ldo;
+        g.accumulate_out = l > 0;
+        g.final_chunk = l == num_launches - 1;
+        if (vec_a) tc_gemm_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g);
+        else tc_gemm_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g);
+        GG_LAUNCHED();
+    }
     return GG_OK;
 }
 

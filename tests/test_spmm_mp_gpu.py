@@ -81,7 +81,14 @@ def test_powerlaw_hubs_split_over_items(cuda, monkeypatch, n, avg):
     assert int(torch.diff(csr.rowptr).max()) > 2000       # rows spanning >= 4 items
     mp = run(csr, x.to(cuda), w, ops.SUM, 0.0, None, 'mp', 'tma', monkeypatch)
     row = run(csr, x.to(cuda), w, ops.SUM, 0.0, None, 'row', 'tma', monkeypatch)
-    assert rel_err(mp, row.double()) < FP32_TOL   # two fp32 summation orders over 10^3-term hub rows
+    # fp64 arbiter: the same weighted adjacency as a sparse matrix on the CPU
+    a = torch.sparse_coo_tensor(torch.stack([csr.rowid.cpu().long(), csr.nbr.cpu().long()]), w.cpu().double(),
+                                (n, n)).coalesce()
+    want = torch.sparse.mm(a, x.double())
+    assert rel_err(mp, want) < FP32_TOL
+    # one warp summing a 10^4-slot hub row strictly in sequence accumulates more fp32 rounding than the
+    # merge-path kernel's <= 480-slot partials (the reference's atomic scatter-add is no better)
+    assert rel_err(row, want) < 5 * FP32_TOL
     # rows that live inside one item are summed in the same order by both kernels: bitwise equal
     same = (mp == row).all(dim=1).float().mean().item()
     assert same > (0.8 if n >= 200000 else 0.05)   # small graphs use 64-unit items: most rows are split

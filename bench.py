@@ -115,7 +115,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -250,6 +250,9 @@ def run_ours(args, spec, rank, world, dev):
 
     def step(x_dev, ei_dev, playout=None):
         layer.zero_grad(set_to_none=True)
+        # the layer input needs its gradient: message-passing layers sit behind pre_mp / earlier layers
+        # (ref: gnn.py:165-168), so the backward includes dX = dH W^T as well as dW, dbias
+        x_dev = x_dev.detach().requires_grad_(True)
         if multi:
             y = layer(x_dev, playout)
             y.backward(gy_loc)
@@ -272,19 +275,22 @@ def run_ours(args, spec, rank, world, dev):
     slots = int(sum_over_ranks(slots_local))
     torch.cuda.synchronize()
     layout_first_s = time.time() - t0
+    clocks = ClockSampler(dev.index or 0)
+    clocks.__enter__()   # sampled at 20 ms from the warm-up on: short timed regions still get samples under load
     for _ in range(args.warmup):
         step(x_loc, ei, playout)
     sync_all()
     ops.spmm = timed_spmm
     launches0 = ops.launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(dev.index or 0) as clocks:
+    if True:
         sync_all()
         start.record()
         for _ in range(args.steps):
             step(x_loc, ei, playout)
         end.record()
         sync_all()
+    clocks.__exit__(None, None, None)
     ops.spmm = orig_spmm
     launches = int(sum_over_ranks(ops.launch_count() - launches0))
     ms = max_over_ranks(start.elapsed_time(end)) / args.steps
@@ -350,7 +356,7 @@ def run_ours(args, spec, rank, world, dev):
            'ms_per_step': round(e2e_ms, 3), 'steps': e2e_steps,
            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(fout * 4 * world),
            'includes': 'H2D of node_feature rows + edge_index from pinned memory on every rank, CSR+CSC '
-                       'layout build, layer fwd+bwd via the layer API, D2H of the bias gradient'}
+                       'layout build, layer fwd+bwd (dX, dW, dbias) via the layer API, D2H of the bias gradient'}
     del x_host, ei_host
 
     cpu = cpu_baseline(spec, seconds=args.cpu_seconds) if rank == 0 and not args.no_cpu and not multi else None
@@ -451,6 +457,9 @@ def run_reference(args, spec, rank, world):
 
 
 def main():
+    # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

@@ -8,17 +8,18 @@
 // and the product is  hi_a*hi_b + hi_a*lo_b + lo_a*hi_b  (the dropped lo*lo term is ~2^-22 relative),
 // three kind::tf32 MMAs accumulating into the same fp32 TMEM tile.
 //
-// Structure of one CTA (128 x 128 output tile, 256 threads, up to 3 CTAs per SM, 128 TMEM columns each):
+// Structure of one CTA (128 x 128 output tile, 256 threads, 2 CTAs per SM, 128 TMEM columns each):
 //   * the K-segments (X W, then the centre rows' X W_id with the row multiplicity as scale; tiles with
 //     no centre row skip it) are walked in slabs of 16 k;
 //   * A slab: each thread loads 2 x 16 B of its row, applies the scale, splits hi/lo in registers and
 //     stores both into shared memory in the UMMA canonical K-major no-swizzle layout
 //     (16-byte chunks, chunk-major: address = chunk * 2048 + row * 16, i.e. LBO = 2048 B, SBO = 128 B);
-//   * B slab: pre-split once per call by b_image_kernel into exactly that layout, copied linearly;
+//   * B slab: pre-split once per call by b_image_kernel into exactly that layout; one cp.async.bulk
+//     (TMA) of 16 KB per slab, one slab ahead, completing on the stage's b_full mbarrier;
 //   * fence.proxy.async + __syncthreads, then ONE thread issues the 6 tcgen05.mma of the slab and a
-//     tcgen05.commit onto the stage's mbarrier; two stages, the next slab's global loads are in flight
-//     while the tensor core works;
-//   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias / ReLU / mask -> global.
+//     tcgen05.commit onto the stage's mma_done mbarrier; three stages, A rows four slabs ahead in registers;
+//   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> shared memory -> bias / ReLU / mask ->
+//     coalesced 512-byte row stores.
 #include "common.cuh"
 
 namespace gg {
@@ -27,7 +28,8 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 16;
 constexpr int TC_THREADS = 256;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;        // 8192: one operand slab (hi or lo)
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;       // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_SMEM_BYTES = 2 * TC_STAGE_BYTES;       // two stages
+constexpr int TC_STAGES = 3;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES;  // 96 KB: two CTAs per SM
 constexpr uint32_t TC_LBO = TC_BM * 16;                 // bytes between 16-byte k-chunks
 constexpr uint32_t TC_SBO = 128;                        // bytes between 8-row groups
 constexpr int TC_TMEM_COLS = 128;
@@ -154,20 +156,34 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+__device__ __forceinline__ void tc_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     tc_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(tc_smem_u32(bar))
+                 : "memory");
+}
+
 template <bool VEC_A>
-__global__ void __launch_bounds__(TC_THREADS, 3) tc_gemm_kernel(TcArgs g) {
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t mma_done[2];
+    __shared__ __align__(8) uint64_t mma_done[TC_STAGES];  // slab consumed by the tensor core
+    __shared__ __align__(8) uint64_t b_full[TC_STAGES];    // B image slab landed (TMA bulk copy)
     __shared__ uint32_t tmem_base_smem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
     const int nt = blockIdx.y;
-    const int n_tiles = gridDim.y;
 
     if (tid == 0) {
-        tc_mbar_init(&mma_done[0], 1);
-        tc_mbar_init(&mma_done[1], 1);
+#pragma unroll
+        for (int i = 0; i < TC_STAGES; ++i) {
+            tc_mbar_init(&mma_done[i], 1);
+            tc_mbar_init(&b_full[i], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {  // TMEM: 128 fp32 accumulator columns for this CTA
@@ -182,77 +198,118 @@ __global__ void __launch_bounds__(TC_THREADS, 3) tc_gemm_kernel(TcArgs g) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
 
-    // this thread's share of a slab: A row (tid & 127), chunks 2*(tid>>7) and +1; 64 B of the B image
+    // this thread's share of an A slab: row (tid & 127), 16-byte chunks 2*(tid>>7) and +1
     const int a_row = tid & 127;
     const int a_c0 = (tid >> 7) * 2;
     const int64_t grow = row0 + a_row;
     const bool row_ok = grow < g.n;
 
-    int it = 0;  // slabs issued so far
-    for (int sg = 0; sg < g.num_segments; ++sg) {
-        const TcSegment s = g.seg[sg];
-        if (s.k_slabs <= 0) continue;
-        float sc = 1.f;
-        if (s.scale) {
-            sc = row_ok ? __ldg(s.scale + grow) : 0.f;
-            if (!__syncthreads_or(sc != 0.f)) continue;  // no centre row in this tile
-        }
-        const float* arow = s.a + grow * s.lda;
-        const float4* bimg = reinterpret_cast<const float4*>(s.b_image) +
-                             (int64_t)nt * s.k_slabs * (2 * TC_TILE_BYTES / 16);
-        float4 ra[2], rb[4];
-        auto fetch = [&](int ks) {
+    // active segments of this tile (an ID segment with no centre row in the tile is skipped)
+    int seg_slabs[GG_GEMM_MAX_SEGMENTS];
+    float seg_scale[GG_GEMM_MAX_SEGMENTS];
+    int total = 0;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int k = ks * TC_BK + (a_c0 + i) * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row_ok) {
-                    if (VEC_A) {
-                        if (k < s.k) v = __ldg(reinterpret_cast<const float4*>(arow + k));
-                    } else {
-                        if (k + 0 < s.k) v.x = __ldg(arow + k + 0);
-                        if (k + 1 < s.k) v.y = __ldg(arow + k + 1);
-                        if (k + 2 < s.k) v.z = __ldg(arow + k + 2);
-                        if (k + 3 < s.k) v.w = __ldg(arow + k + 3);
-                    }
-                }
-                ra[i] = v;
+    for (int sg = 0; sg < GG_GEMM_MAX_SEGMENTS; ++sg) {
+        seg_slabs[sg] = 0;
+        seg_scale[sg] = 1.f;
+        if (sg < g.num_segments && g.seg[sg].k_slabs > 0) {
+            bool on = true;
+            if (g.seg[sg].scale) {
+                seg_scale[sg] = row_ok ? __ldg(g.seg[sg].scale + grow) : 0.f;
+                on = __syncthreads_or(seg_scale[sg] != 0.f);
             }
-            const float4* src = bimg + (int64_t)ks * (2 * TC_TILE_BYTES / 16);
+            if (on) seg_slabs[sg] = g.seg[sg].k_slabs;
+        }
+        total += seg_slabs[sg];
+    }
+    // slab i of the flattened sequence -> (segment, slab inside the segment)
+    auto locate = [&](int i, int& sg, int& ks) {
+        sg = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) rb[j] = __ldg(src + tid + j * TC_THREADS);
-        };
-        fetch(0);
-        for (int ks = 0; ks < s.k_slabs; ++ks, ++it) {
-            const int stage = it & 1;
+        for (int t = 0; t < GG_GEMM_MAX_SEGMENTS - 1; ++t)
+            if (i >= seg_slabs[sg] && sg < GG_GEMM_MAX_SEGMENTS - 1) { i -= seg_slabs[sg]; ++sg; }
+        ks = i;
+    };
+    auto fetch_a = [&](int i, float4 (&r)[2]) {
+        int sg, ks;
+        locate(i, sg, ks);
+        const TcSegment& s = g.seg[sg];
+        const float* arow = s.a + grow * s.lda;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int k = ks * TC_BK + (a_c0 + c) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_ok) {
+                if (VEC_A) {
+                    if (k < s.k) v = __ldg(reinterpret_cast<const float4*>(arow + k));
+                } else {
+                    if (k + 0 < s.k) v.x = __ldg(arow + k + 0);
+                    if (k + 1 < s.k) v.y = __ldg(arow + k + 1);
+                    if (k + 2 < s.k) v.z = __ldg(arow + k + 2);
+                    if (k + 3 < s.k) v.w = __ldg(arow + k + 3);
+                }
+            }
+            r[c] = v;  // raw: the row scale is applied when the slab is consumed, not here (no stall on the load)
+        }
+    };
+    auto issue_b = [&](int i) {  // one elected thread: 16 KB image slab -> stage, completes on b_full
+        int sg, ks;
+        locate(i, sg, ks);
+        const TcSegment& s = g.seg[sg];
+        const float* src = s.b_image + ((int64_t)nt * s.k_slabs + ks) * (2 * TC_TILE_BYTES / 4);
+        const int stage = i % TC_STAGES;
+        tc_expect_tx(&b_full[stage], 2 * TC_TILE_BYTES);
+        tc_bulk_g2s(smem + stage * TC_STAGE_BYTES + 2 * TC_TILE_BYTES, src, 2 * TC_TILE_BYTES, &b_full[stage]);
+    };
+
+    // A rows run kPrefetch slabs ahead in registers (slot u holds the slab with i % kPrefetch == u, so the
+    // ring is indexed statically): 2 CTAs x 256 threads x 4 slabs x 32 B = 64 KB in flight per SM
+    constexpr int kPrefetch = 4;
+    float4 ring[kPrefetch][2];
+#pragma unroll
+    for (int u = 0; u < kPrefetch; ++u)
+        if (u < total) fetch_a(u, ring[u]);
+    if (total > 0 && tid == 0) issue_b(0);
+    for (int i0 = 0; i0 < total; i0 += kPrefetch) {
+#pragma unroll
+        for (int u = 0; u < kPrefetch; ++u) {
+            const int i = i0 + u;
+            if (i >= total) break;
+            const int stage = i % TC_STAGES;
             uint8_t* st = smem + stage * TC_STAGE_BYTES;
-            if (it >= 2) tc_mbar_wait(&mma_done[stage], (uint32_t)((it >> 1) - 1) & 1u);  // slab it-2 consumed
-            // A: scale, split, store hi / lo;  B: linear copy of the prepared image
+            // stage `stage` is free: slab i-3 was waited for when B(i) was requested in iteration i-1
+            int csg, cks;
+            locate(i, csg, cks);
+            const float sc = seg_scale[csg];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int c = 0; c < 2; ++c) {
                 float4 h, l;
-                split_tf32(ra[i].x * sc, h.x, l.x);
-                split_tf32(ra[i].y * sc, h.y, l.y);
-                split_tf32(ra[i].z * sc, h.z, l.z);
-                split_tf32(ra[i].w * sc, h.w, l.w);
-                const int off = (a_c0 + i) * (int)TC_LBO + a_row * 16;
+                split_tf32(ring[u][c].x * sc, h.x, l.x);
+                split_tf32(ring[u][c].y * sc, h.y, l.y);
+                split_tf32(ring[u][c].z * sc, h.z, l.z);
+                split_tf32(ring[u][c].w * sc, h.w, l.w);
+                const int off = (a_c0 + c) * (int)TC_LBO + a_row * 16;
                 *reinterpret_cast<float4*>(st + off) = h;
                 *reinterpret_cast<float4*>(st + TC_TILE_BYTES + off) = l;
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<float4*>(st + 2 * TC_TILE_BYTES + (tid + j * TC_THREADS) * 16) = rb[j];
-            if (ks + 1 < s.k_slabs) fetch(ks + 1);  // in flight while the tensor core works
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy
+            if (i + kPrefetch < total) fetch_a(i + kPrefetch, ring[u]);
+            if (i + 1 < total) {
+                const int nstage = (i + 1) % TC_STAGES;
+                if (i + 1 >= TC_STAGES)  // slab i-2 used that stage: wait until the tensor core consumed it
+                    tc_mbar_wait(&mma_done[nstage], (uint32_t)((i + 1) / TC_STAGES - 1) & 1u);
+                if (tid == 0) issue_b(i + 1);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic smem writes -> async proxy
             __syncthreads();
             if (tid == 0) {
+                tc_mbar_wait(&b_full[stage], (uint32_t)(i / TC_STAGES) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = tc_smem_u32(st), a_lo = a_hi + TC_TILE_BYTES;
                 const uint32_t b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
 #pragma unroll
                 for (int j = 0; j < TC_BK / 8; ++j) {  // one MMA consumes 8 k = two 16-byte chunks
                     const uint32_t ko = j * 2 * TC_LBO;
-                    tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_hi + ko), (it > 0 || j > 0) ? 1u : 0u);
+                    tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_hi + ko), (i > 0 || j > 0) ? 1u : 0u);
                     tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_lo + ko), 1u);
                     tc_mma(tmem_base, tc_smem_desc(a_lo + ko), tc_smem_desc(b_hi + ko), 1u);
                 }
@@ -261,53 +318,34 @@ __global__ void __launch_bounds__(TC_THREADS, 3) tc_gemm_kernel(TcArgs g) {
         }
     }
     // all MMAs were issued by one thread in order: the last commit covers them all
-    if (it > 0) {
-        const int last = it - 1;
-        tc_mbar_wait(&mma_done[last & 1], (uint32_t)(last >> 1) & 1u);
+    if (total > 0) {
+        const int last = total - 1;
+        tc_mbar_wait(&mma_done[last % TC_STAGES], (uint32_t)(last / TC_STAGES) & 1u);
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: TMEM -> registers -> bias / act / mask -> global ----
-    const int q = warp & 3;        // TMEM lane quarter this warp may read
-    const int half = warp >> 2;    // column half
-    const int64_t r = row0 + q * 32 + lane;
-    const bool vec_out = (g.f % 4 == 0) && (g.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0) &&
-                         (!g.relu_mask || (g.ld_mask % 4 == 0 && (reinterpret_cast<uintptr_t>(g.relu_mask) & 15) == 0));
+    // ---- epilogue: TMEM -> registers -> shared (row stride 132 floats) -> coalesced 512-byte rows ----
+    constexpr int kRowStride = TC_BN + 4;
+    float* tile = reinterpret_cast<float*>(smem);  // the operand stages are free now (67.6 KB of 96 KB)
+    {
+        const int q = warp & 3;      // TMEM lane quarter this warp may read
+        const int half = warp >> 2;  // column half
+        const int trow = q * 32 + lane;
 #pragma unroll
-    for (int part = 0; part < 2; ++part) {
-        const int cbase = half * 64 + part * 32;
-        uint32_t acc[32];
-        if (it > 0) {
-            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase, acc);
-        } else {
+        for (int part = 0; part < 2; ++part) {
+            const int cbase = half * 64 + part * 32;
+            uint32_t acc[32];
+            if (total > 0) {
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase, acc);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0u;
-        }
-        if (r < g.n) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const int c = nt * TC_BN + cbase + j;
-                float v[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    v[e] = __uint_as_float(acc[j + e]);
-                    if (c + e < g.f) {
-                        if (g.accumulate_out) v[e] += g.out[r * g.ldo + c + e];  // fp32 round-to-nearest add
-                        if (g.final_chunk) {
-                            if (g.bias) v[e] += __ldg(g.bias + c + e);
-                            if (g.act == GG_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
-                            if (g.relu_mask) v[e] = __ldg(g.relu_mask + r * g.ld_mask + c + e) > 0.f ? v[e] : 0.f;
-                        }
-                    }
-                }
-                if (vec_out && c + 3 < g.f) {
-                    *reinterpret_cast<float4*>(g.out + r * g.ldo + c) = make_float4(v[0], v[1], v[2], v[3]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (c + e < g.f) g.out[r * g.ldo + c + e] = v[e];
-                }
+                for (int e = 0; e < 32; ++e) acc[e] = 0u;
             }
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+                *reinterpret_cast<float4*>(tile + trow * kRowStride + cbase + e) =
+                    make_float4(__uint_as_float(acc[e]), __uint_as_float(acc[e + 1]), __uint_as_float(acc[e + 2]),
+                                __uint_as_float(acc[e + 3]));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -316,7 +354,51 @@ __global__ void __launch_bounds__(TC_THREADS, 3) tc_gemm_kernel(TcArgs g) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
                      : "memory");
     }
-    (void)n_tiles;
+    const bool vec_out = (g.f % 4 == 0) && (g.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0) &&
+                         (!g.relu_mask || (g.ld_mask % 4 == 0 && (reinterpret_cast<uintptr_t>(g.relu_mask) & 15) == 0)) &&
+                         (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
+    const int c = nt * TC_BN + lane * 4;  // this lane's 4 columns
+    for (int rr = warp; rr < TC_BM; rr += TC_THREADS / 32) {
+        const int64_t r = row0 + rr;
+        if (r >= g.n) break;
+        const float4 a4 = *reinterpret_cast<const float4*>(tile + rr * kRowStride + lane * 4);
+        float v[4] = {a4.x, a4.y, a4.z, a4.w};
+        if (vec_out && c + 3 < g.f) {
+            if (g.accumulate_out) {
+                const float4 o = *reinterpret_cast<const float4*>(g.out + r * g.ldo + c);
+                v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;  // fp32 round-to-nearest add of partials
+            }
+            if (g.final_chunk) {
+                if (g.bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + c));
+                    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                }
+                if (g.act == GG_ACT_RELU) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+                }
+                if (g.relu_mask) {
+                    const float4 m = __ldg(reinterpret_cast<const float4*>(g.relu_mask + r * g.ld_mask + c));
+                    v[0] = m.x > 0.f ? v[0] : 0.f; v[1] = m.y > 0.f ? v[1] : 0.f;
+                    v[2] = m.z > 0.f ? v[2] : 0.f; v[3] = m.w > 0.f ? v[3] : 0.f;
+                }
+            }
+            *reinterpret_cast<float4*>(g.out + r * g.ldo + c) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (c + e >= g.f) continue;
+                float x = v[e];
+                if (g.accumulate_out) x += g.out[r * g.ldo + c + e];
+                if (g.final_chunk) {
+                    if (g.bias) x += __ldg(g.bias + c + e);
+                    if (g.act == GG_ACT_RELU) x = fmaxf(x, 0.f);
+                    if (g.relu_mask) x = __ldg(g.relu_mask + r * g.ld_mask + c + e) > 0.f ? x : 0.f;
+                }
+                g.out[r * g.ldo + c + e] = x;
+            }
+        }
+    }
 }
 
 static inline int tc_slabs(int64_t k) { return (int)ceil_div(k, TC_BK); }

@@ -61,6 +61,9 @@ SIGNATURES = {
     "gg_gemm_tn_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
     "gg_gemm_tn_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64,
                                c_ptr, c_size, c_ptr]),
+    "gg_gemm_tn_tc_workspace_bytes": (c_size, [c_i64, c_i64, c_i64]),
+    "gg_gemm_tn_tc_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_i64,
+                                  c_ptr, c_size, c_ptr]),
     "gg_colsum_workspace_bytes": (c_size, [c_i64, c_i64]),
     "gg_colsum_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_size, c_ptr]),
     "gg_id_count": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_ptr]),

@@ -401,6 +401,187 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(TcArgs g) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores:  partial[split][K,F] = sum_{r in split} A[row(r),:]^T G[row(r),:]
+// (dW = X^T dH; dW_id = X[id]^T dH[id]).  M = K, N = F, the reduction runs over matrix ROWS, so both
+// operands are transposed while they are staged: thread t < 128 owns column t of the A tile, thread
+// t >= 128 column t-128 of the G tile; per slab it reads its column's 16 rows (coalesced across the warp),
+// packs 4 consecutive rows into one 16-byte k-chunk, splits hi/lo and stores the canonical K-major slabs.
+// A split covers kTnRowsPerSplit = 512 rows so that the truncating tensor-core accumulation stays
+// below 3e-6 relative; the partial tiles are summed in fp64, in split order, by split_reduce.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTnRowsPerSplit = 512;
+
+struct TnTcArgs {
+    const float* a;
+    int64_t lda;
+    const float* g;
+    int64_t ldg;
+    const int64_t* row_index;
+    int64_t n;
+    int k, f;
+    float* partial;  // [splits][k][f]
+};
+
+template <bool DUMMY>
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_tn_kernel(TnTcArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t mma_done[TC_STAGES];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = (g.f + TC_BN - 1) / TC_BN;
+    const int m0 = (blockIdx.x / n_tiles) * TC_BM;  // offset in K (rows of the output)
+    const int c0 = (blockIdx.x % n_tiles) * TC_BN;  // offset in F
+    const int64_t r_beg = (int64_t)blockIdx.y * kTnRowsPerSplit;
+    const int64_t r_end = r_beg + kTnRowsPerSplit < g.n ? r_beg + kTnRowsPerSplit : g.n;
+    const int total = (int)((r_end - r_beg + TC_BK - 1) / TC_BK);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < TC_STAGES; ++i) tc_mbar_init(&mma_done[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         tc_smem_u32(&tmem_base_smem)),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    // operand column owned by this thread
+    const bool is_a = tid < 128;
+    const int col = is_a ? m0 + tid : c0 + (tid - 128);
+    const bool col_ok = is_a ? col < g.k : col < g.f;
+    const float* base = is_a ? g.a : g.g;
+    const int64_t ld = is_a ? g.lda : g.ldg;
+    const int trow = tid & 127;  // row of the smem slab (= M or N index)
+
+    auto fetch = [&](int i, float (&v)[TC_BK]) {
+        const int64_t r0 = r_beg + (int64_t)i * TC_BK;
+#pragma unroll
+        for (int kk = 0; kk < TC_BK; ++kk) {
+            const int64_t r = r0 + kk;
+            float x = 0.f;
+            if (col_ok && r < r_end) {
+                const int64_t rr = g.row_index ? __ldg(g.row_index + r) : r;
+                x = __ldg(base + rr * ld + col);
+            }
+            v[kk] = x;
+        }
+    };
+    constexpr int kPrefetch = 2;
+    float ring[kPrefetch][TC_BK];
+#pragma unroll
+    for (int u = 0; u < kPrefetch; ++u)
+        if (u < total) fetch(u, ring[u]);
+    for (int i0 = 0; i0 < total; i0 += kPrefetch) {
+#pragma unroll
+        for (int u = 0; u < kPrefetch; ++u) {
+            const int i = i0 + u;
+            if (i >= total) break;
+            const int stage = i % TC_STAGES;
+            if (i >= TC_STAGES)  // slab i-3 used this stage
+                tc_mbar_wait(&mma_done[stage], (uint32_t)(i / TC_STAGES - 1) & 1u);
+            uint8_t* st = smem + stage * TC_STAGE_BYTES + (is_a ? 0 : 2 * TC_TILE_BYTES);
+#pragma unroll
+            for (int c = 0; c < TC_BK / 4; ++c) {
+                float4 h, l;
+                split_tf32(ring[u][c * 4 + 0], h.x, l.x);
+                split_tf32(ring[u][c * 4 + 1], h.y, l.y);
+                split_tf32(ring[u][c * 4 + 2], h.z, l.z);
+                split_tf32(ring[u][c * 4 + 3], h.w, l.w);
+                const int off = c * (int)TC_LBO + trow * 16;
+                *reinterpret_cast<float4*>(st + off) = h;
+                *reinterpret_cast<float4*>(st + TC_TILE_BYTES + off) = l;
+            }
+            if (i + kPrefetch < total) fetch(i + kPrefetch, ring[u]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = tc_smem_u32(smem + stage * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
+                const uint32_t b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
+#pragma unroll
+                for (int j = 0; j < TC_BK / 8; ++j) {
+                    const uint32_t ko = j * 2 * TC_LBO;
+                    tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_hi + ko), (i > 0 || j > 0) ? 1u : 0u);
+                    tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_lo + ko), 1u);
+                    tc_mma(tmem_base, tc_smem_desc(a_lo + ko), tc_smem_desc(b_hi + ko), 1u);
+                }
+                tc_commit(&mma_done[stage]);
+            }
+        }
+    }
+    if (total > 0) {
+        const int last = total - 1;
+        tc_mbar_wait(&mma_done[last % TC_STAGES], (uint32_t)(last / TC_STAGES) & 1u);
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    constexpr int kRowStride = TC_BN + 4;
+    float* tile = reinterpret_cast<float*>(smem);
+    {
+        const int q = warp & 3, half = warp >> 2;
+        const int tr = q * 32 + lane;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            const int cbase = half * 64 + part * 32;
+            uint32_t acc[32];
+            if (total > 0) {
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase, acc);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) acc[e] = 0u;
+            }
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+                *reinterpret_cast<float4*>(tile + tr * kRowStride + cbase + e) =
+                    make_float4(__uint_as_float(acc[e]), __uint_as_float(acc[e + 1]), __uint_as_float(acc[e + 2]),
+                                __uint_as_float(acc[e + 3]));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
+                     : "memory");
+    }
+    float* dst = g.partial + (int64_t)blockIdx.y * g.k * g.f;
+    const int c = c0 + lane * 4;
+    const bool vec = (g.f % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.partial) & 15) == 0);
+    for (int rr = warp; rr < TC_BM; rr += TC_THREADS / 32) {
+        const int m = m0 + rr;
+        if (m >= g.k) break;
+        const float4 a4 = *reinterpret_cast<const float4*>(tile + rr * kRowStride + lane * 4);
+        if (vec && c + 3 < g.f) {
+            *reinterpret_cast<float4*>(dst + (int64_t)m * g.f + c) = a4;
+        } else {
+            const float v[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (c + e < g.f) dst[(int64_t)m * g.f + c + e] = v[e];
+        }
+    }
+}
+
+// out[e] = sum_s part[s][e] in fp64, s ascending (fixed order)
+__global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict__ part, int64_t splits, int64_t rows,
+                                                        int64_t cols, float* __restrict__ out, int64_t ldo) {
+    const int64_t total = rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int64_t p = 0; p < splits; ++p) s += (double)part[p * total + e];
+        out[(e / cols) * ldo + (e % cols)] = (float)s;
+    }
+}
+
 static inline int tc_slabs(int64_t k) { return (int)ceil_div(k, TC_BK); }
 static inline int tc_ntiles(int64_t f) { return (int)ceil_div(f, TC_BN); }
 static inline size_t tc_image_floats(int64_t k, int64_t f) {
@@ -524,6 +705,50 @@ int gg_id_gemm_tc_f32(const gg_gemm_segment* segs, int num_segments, int b_trans
         else tc_gemm_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g);
         GG_LAUNCHED();
     }
+    return GG_OK;
+}
+
+size_t gg_gemm_tn_tc_workspace_bytes(int64_t n, int64_t k, int64_t f) {
+    int64_t splits = ceil_div(n > 0 ? n : 1, kTnRowsPerSplit);
+    return (size_t)splits * (size_t)k * (size_t)f * sizeof(float) + 256;
+}
+
+int gg_gemm_tn_tc_f32(const float* a, int64_t lda, const int64_t* row_index, const float* g, int64_t ldg,
+                      int64_t n, int64_t k, int64_t f, float* out, int64_t ldo, void* workspace,
+                      size_t workspace_bytes, gg_stream_t stream) {
+    GG_REQUIRE(n >= 0 && k >= 0 && f >= 0, "gg_gemm_tn_tc_f32: negative size");
+    if (k == 0 || f == 0) return GG_OK;
+    GG_REQUIRE(out && ldo >= f, "gg_gemm_tn_tc_f32: bad output");
+    cudaStream_t st = as_stream(stream);
+    if (n == 0) {
+        GG_CUDA(cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)f * 4, (size_t)k, st));
+        return GG_OK;
+    }
+    GG_REQUIRE(a && g && lda >= k && ldg >= f && workspace, "gg_gemm_tn_tc_f32: bad operands");
+    GG_REQUIRE(k < (1 << 20) && f < (1 << 20), "gg_gemm_tn_tc_f32: k / f out of range");
+    if (workspace_bytes < gg_gemm_tn_tc_workspace_bytes(n, k, f)) {
+        set_error("gg_gemm_tn_tc_f32: workspace %zu < %zu", workspace_bytes, gg_gemm_tn_tc_workspace_bytes(n, k, f));
+        return GG_ERR_WORKSPACE;
+    }
+    const int64_t splits = ceil_div(n, kTnRowsPerSplit);
+    GG_REQUIRE(splits <= 65535 * 16, "gg_gemm_tn_tc_f32: too many rows");
+    static bool attr_done = false;
+    if (!attr_done) {
+        GG_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TC_SMEM_BYTES));
+        attr_done = true;
+    }
+    TnTcArgs t{a, lda, g, ldg, row_index, n, (int)k, (int)f, static_cast<float*>(workspace)};
+    const int64_t tiles = ceil_div(k, TC_BM) * ceil_div(f, TC_BN);
+    // gridDim.y is limited to 65535: fold the splits when there are more
+    GG_REQUIRE(splits <= 65535, "gg_gemm_tn_tc_f32: more than 65535 row splits (n > 33.5M rows)");
+    dim3 grid((unsigned)tiles, (unsigned)splits);
+    tc_gemm_tn_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(t);
+    GG_LAUNCHED();
+    const int64_t total = k * f;
+    int blocks = (int)(ceil_div(total, 256) < kNumSMs * 8 ? ceil_div(total, 256) : kNumSMs * 8);
+    tn_reduce_kernel<<<blocks, 256, 0, st>>>(t.partial, splits, k, f, out, ldo);
+    GG_LAUNCHED();
     return GG_OK;
 }
 

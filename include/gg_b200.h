@@ -209,6 +209,13 @@ int gg_gemm_tn_f32(const float* a, int64_t lda, const int64_t* row_index, const 
                    int64_t n, int64_t k, int64_t f, float* out, int64_t ldo, void* workspace,
                    size_t workspace_bytes, gg_stream_t stream);
 
+/* Weight gradient on the tensor cores (tcgen05 3xTF32, 512 rows per TMEM accumulation, fp64 reduction of
+ * the per-split partial tiles); same arguments as gg_gemm_tn_f32. */
+size_t gg_gemm_tn_tc_workspace_bytes(int64_t n, int64_t k, int64_t f);
+int gg_gemm_tn_tc_f32(const float* a, int64_t lda, const int64_t* row_index, const float* g, int64_t ldg,
+                      int64_t n, int64_t k, int64_t f, float* out, int64_t ldo, void* workspace,
+                      size_t workspace_bytes, gg_stream_t stream);
+
 /* Column sums (bias gradient): out[f] = sum_r g[r,f], fixed-order two-stage reduction.
  * workspace: gg_colsum_workspace_bytes. */
 size_t gg_colsum_workspace_bytes(int64_t n, int64_t f);

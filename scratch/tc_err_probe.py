@@ -40,3 +40,17 @@ for mode in ('tc', 'simt'):
     e.record(); torch.cuda.synchronize()
     ms = s.elapsed_time(e) / 10
     print(mode, 'ba1m 256->256:', round(ms, 3), 'ms', round(2 * n * k * f / ms / 1e9, 1), 'TFLOP/s(fp32-equivalent)')
+# weight-gradient kernel
+for (n, k, f) in ((2449029, 100, 128), (1000000, 256, 256)):
+    a, gg_ = torch.randn(n, k, device=dev), torch.randn(n, f, device=dev)
+    want = (a[:200000].double().t() @ gg_[:200000].double()).cpu()
+    for mode in ('tc', 'simt'):
+        ops.GEMM_MODE = mode
+        err = rel_err(ops.gemm_tn(a[:200000], gg_[:200000]), want)
+        for _ in range(3): ops.gemm_tn(a, gg_)
+        torch.cuda.synchronize(); s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10): ops.gemm_tn(a, gg_)
+        e.record(); torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 10
+        print(mode, f'gemm_tn n={n} {k}x{f}: {ms:.3f} ms, {(n*(k+f)*4)/ms/1e6:.0f} GB/s, err(200K rows) {err:.2e}')

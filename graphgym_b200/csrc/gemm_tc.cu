@@ -25,11 +25,8 @@
 namespace gg {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 16;
-constexpr int TC_THREADS = 256;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;        // 8192: one operand slab (hi or lo)
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;       // A_hi, A_lo, B_hi, B_lo
-constexpr int TC_STAGES = 3;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES;  // 96 KB: two CTAs per SM
 constexpr uint32_t TC_LBO = TC_BM * 16;                 // bytes between 16-byte k-chunks
 constexpr uint32_t TC_SBO = 128;                        // bytes between 8-row groups
 constexpr int TC_TMEM_COLS = 128;
@@ -160,30 +157,78 @@ __device__ __forceinline__ void tc_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc_smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void tc_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tc_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      tc_smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(tc_smem_u32(bar))
                  : "memory");
 }
+// 16-byte / 4-byte asynchronous global -> shared copies (LDGSTS); src_bytes < size zero-fills the rest
+__device__ __forceinline__ void tc_cp_async16(void* dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc_smem_u32(dst)), "l"(src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_cp_async4(void* dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(tc_smem_u32(dst)), "l"(src), "r"(src_bytes)
+                 : "memory");
+}
+// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void tc_cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
+}
+// ring bookkeeping: item i lives in slot i % Z and is the (i / Z)-th use of that slot
+__device__ __forceinline__ uint32_t tc_full_parity(int i, int z) { return (uint32_t)(i / z) & 1u; }
+__device__ __forceinline__ uint32_t tc_free_parity(int i, int z) { return (uint32_t)(i / z - 1) & 1u; }
+
+// Warp roles.  A memory fence waits for the thread's outstanding loads, so the threads that fence
+// (fence.proxy.async, needed between their st.shared and the tensor core's reads) must not be the ones
+// that prefetch from global memory — otherwise every slab pays a DRAM round trip (measured: 1.45 us/slab).
+//   warps 0-3  loaders    cp.async of the raw fp32 slab into a staging ring; never wait on data
+//   warps 4-7  converters staging ring -> scale / hi-lo split -> operand stage, fence.proxy.async
+//   warp  8    issuer     TMA bulk copies of the B image, tcgen05.mma, tcgen05.commit
+constexpr int TC_ROLE_THREADS = 128;
+constexpr int TC_BLOCK = 2 * TC_ROLE_THREADS + 32;
+
+// ---- NN kernel shared-memory plan: raw ring (3 x 8 KB) | A operand stages (2 x 16 KB) | B ring (3 x 16 KB)
+constexpr int NN_RAW_SLOTS = 3, NN_A_STAGES = 2, NN_B_SLOTS = 3;
+constexpr int NN_RAW_BYTES = TC_TILE_BYTES;
+constexpr int NN_OFF_A = NN_RAW_SLOTS * NN_RAW_BYTES;
+constexpr int NN_OFF_B = NN_OFF_A + NN_A_STAGES * 2 * TC_TILE_BYTES;
+constexpr int NN_SMEM_BYTES = NN_OFF_B + NN_B_SLOTS * 2 * TC_TILE_BYTES;  // 104 KB: two CTAs per SM
+constexpr int TC_EPI_STRIDE = TC_BN + 4;
+static_assert(TC_BM * TC_EPI_STRIDE * 4 <= NN_SMEM_BYTES, "epilogue tile must fit in the operand rings");
 
 template <bool VEC_A>
-__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(TcArgs g) {
+__global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_kernel(TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t mma_done[TC_STAGES];  // slab consumed by the tensor core
-    __shared__ __align__(8) uint64_t b_full[TC_STAGES];    // B image slab landed (TMA bulk copy)
+    __shared__ __align__(8) uint64_t raw_full[NN_RAW_SLOTS], raw_empty[NN_RAW_SLOTS];
+    __shared__ __align__(8) uint64_t op_full[NN_A_STAGES], a_free[NN_A_STAGES];
+    __shared__ __align__(8) uint64_t b_full[NN_B_SLOTS], b_free[NN_B_SLOTS];
+    __shared__ __align__(8) uint64_t all_done;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ int s_slabs[GG_GEMM_MAX_SEGMENTS];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
     const int nt = blockIdx.y;
 
     if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < TC_STAGES; ++i) {
-            tc_mbar_init(&mma_done[i], 1);
-            tc_mbar_init(&b_full[i], 1);
+        for (int i = 0; i < NN_RAW_SLOTS; ++i) {
+            tc_mbar_init(&raw_full[i], TC_ROLE_THREADS);
+            tc_mbar_init(&raw_empty[i], TC_ROLE_THREADS);
         }
+        for (int i = 0; i < NN_A_STAGES; ++i) {
+            tc_mbar_init(&op_full[i], TC_ROLE_THREADS);
+            tc_mbar_init(&a_free[i], 1);
+        }
+        for (int i = 0; i < NN_B_SLOTS; ++i) {
+            tc_mbar_init(&b_full[i], 1);
+            tc_mbar_init(&b_free[i], 1);
+        }
+        tc_mbar_init(&all_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {  // TMEM: 128 fp32 accumulator columns for this CTA
@@ -193,33 +238,34 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(TcArgs g) {
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // active segments of this tile: an ID segment whose rows all have scale 0 (no centre) is skipped
+    const int my_row = tid & (TC_ROLE_THREADS - 1);
+    const int64_t grow = row0 + my_row;
+    const bool row_ok = grow < g.n;
+    float seg_scale[GG_GEMM_MAX_SEGMENTS];
+#pragma unroll
+    for (int sg = 0; sg < GG_GEMM_MAX_SEGMENTS; ++sg) {
+        seg_scale[sg] = 1.f;
+        int slabs = 0;
+        if (sg < g.num_segments && g.seg[sg].k_slabs > 0) {
+            bool on = true;
+            if (g.seg[sg].scale) {
+                seg_scale[sg] = (row_ok && tid < 2 * TC_ROLE_THREADS) ? __ldg(g.seg[sg].scale + grow) : 0.f;
+                on = __syncthreads_or(seg_scale[sg] != 0.f);
+            }
+            if (on) slabs = g.seg[sg].k_slabs;
+        }
+        if (tid == 0) s_slabs[sg] = slabs;
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
-
-    // this thread's share of an A slab: row (tid & 127), 16-byte chunks 2*(tid>>7) and +1
-    const int a_row = tid & 127;
-    const int a_c0 = (tid >> 7) * 2;
-    const int64_t grow = row0 + a_row;
-    const bool row_ok = grow < g.n;
-
-    // active segments of this tile (an ID segment with no centre row in the tile is skipped)
     int seg_slabs[GG_GEMM_MAX_SEGMENTS];
-    float seg_scale[GG_GEMM_MAX_SEGMENTS];
     int total = 0;
 #pragma unroll
     for (int sg = 0; sg < GG_GEMM_MAX_SEGMENTS; ++sg) {
-        seg_slabs[sg] = 0;
-        seg_scale[sg] = 1.f;
-        if (sg < g.num_segments && g.seg[sg].k_slabs > 0) {
-            bool on = true;
-            if (g.seg[sg].scale) {
-                seg_scale[sg] = row_ok ? __ldg(g.seg[sg].scale + grow) : 0.f;
-                on = __syncthreads_or(seg_scale[sg] != 0.f);
-            }
-            if (on) seg_slabs[sg] = g.seg[sg].k_slabs;
-        }
+        seg_slabs[sg] = s_slabs[sg];
         total += seg_slabs[sg];
     }
     // slab i of the flattened sequence -> (segment, slab inside the segment)
@@ -230,104 +276,104 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(TcArgs g) {
             if (i >= seg_slabs[sg] && sg < GG_GEMM_MAX_SEGMENTS - 1) { i -= seg_slabs[sg]; ++sg; }
         ks = i;
     };
-    auto fetch_a = [&](int i, float4 (&r)[2]) {
-        int sg, ks;
-        locate(i, sg, ks);
-        const TcSegment& s = g.seg[sg];
-        const float* arow = s.a + grow * s.lda;
+
+    if (warp < 4) {
+        // ===== loaders: this thread's row, 64 B per slab, straight into the raw ring =====
+        for (int i = 0; i < total; ++i) {
+            const int slot = i % NN_RAW_SLOTS;
+            if (i >= NN_RAW_SLOTS) tc_mbar_wait(&raw_empty[slot], tc_free_parity(i, NN_RAW_SLOTS));
+            int sg, ks;
+            locate(i, sg, ks);
+            const TcSegment& s = g.seg[sg];
+            const float* arow = s.a + (row_ok ? grow : 0) * s.lda;
+            uint8_t* dst = smem + slot * NN_RAW_BYTES + my_row * 16;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            const int k = ks * TC_BK + (a_c0 + c) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row_ok) {
+            for (int c = 0; c < TC_BK / 4; ++c) {
+                const int k = ks * TC_BK + c * 4;
                 if (VEC_A) {
-                    if (k < s.k) v = __ldg(reinterpret_cast<const float4*>(arow + k));
+                    const int left = row_ok ? (s.k - k) * 4 : 0;
+                    tc_cp_async16(dst + c * TC_LBO, arow + (k < s.k ? k : 0), left >= 16 ? 16u : (left > 0 ? (uint32_t)left : 0u));
                 } else {
-                    if (k + 0 < s.k) v.x = __ldg(arow + k + 0);
-                    if (k + 1 < s.k) v.y = __ldg(arow + k + 1);
-                    if (k + 2 < s.k) v.z = __ldg(arow + k + 2);
-                    if (k + 3 < s.k) v.w = __ldg(arow + k + 3);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const bool ok = row_ok && k + e < s.k;
+                        tc_cp_async4(dst + c * TC_LBO + e * 4, arow + (ok ? k + e : 0), ok ? 4u : 0u);
+                    }
                 }
             }
-            r[c] = v;  // raw: the row scale is applied when the slab is consumed, not here (no stall on the load)
+            tc_cp_async_arrive(&raw_full[slot]);
         }
-    };
-    auto issue_b = [&](int i) {  // one elected thread: 16 KB image slab -> stage, completes on b_full
-        int sg, ks;
-        locate(i, sg, ks);
-        const TcSegment& s = g.seg[sg];
-        const float* src = s.b_image + ((int64_t)nt * s.k_slabs + ks) * (2 * TC_TILE_BYTES / 4);
-        const int stage = i % TC_STAGES;
-        tc_expect_tx(&b_full[stage], 2 * TC_TILE_BYTES);
-        tc_bulk_g2s(smem + stage * TC_STAGE_BYTES + 2 * TC_TILE_BYTES, src, 2 * TC_TILE_BYTES, &b_full[stage]);
-    };
-
-    // A rows run kPrefetch slabs ahead in registers (slot u holds the slab with i % kPrefetch == u, so the
-    // ring is indexed statically): 2 CTAs x 256 threads x 4 slabs x 32 B = 64 KB in flight per SM
-    constexpr int kPrefetch = 4;
-    float4 ring[kPrefetch][2];
+    } else if (warp < 8) {
+        // ===== converters: raw slab -> scale, hi/lo split -> operand stage =====
+        for (int i = 0; i < total; ++i) {
+            const int slot = i % NN_RAW_SLOTS, stage = i % NN_A_STAGES;
+            int sg, ks;
+            locate(i, sg, ks);
+            const float sc = seg_scale[sg];
+            tc_mbar_wait(&raw_full[slot], tc_full_parity(i, NN_RAW_SLOTS));
+            float4 v[TC_BK / 4];
 #pragma unroll
-    for (int u = 0; u < kPrefetch; ++u)
-        if (u < total) fetch_a(u, ring[u]);
-    if (total > 0 && tid == 0) issue_b(0);
-    for (int i0 = 0; i0 < total; i0 += kPrefetch) {
+            for (int c = 0; c < TC_BK / 4; ++c)
+                v[c] = *reinterpret_cast<const float4*>(smem + slot * NN_RAW_BYTES + c * TC_LBO + my_row * 16);
+            tc_arrive(&raw_empty[slot]);
+            if (i >= NN_A_STAGES) tc_mbar_wait(&a_free[stage], tc_free_parity(i, NN_A_STAGES));
+            uint8_t* st = smem + NN_OFF_A + stage * 2 * TC_TILE_BYTES;
 #pragma unroll
-        for (int u = 0; u < kPrefetch; ++u) {
-            const int i = i0 + u;
-            if (i >= total) break;
-            const int stage = i % TC_STAGES;
-            uint8_t* st = smem + stage * TC_STAGE_BYTES;
-            // stage `stage` is free: slab i-3 was waited for when B(i) was requested in iteration i-1
-            int csg, cks;
-            locate(i, csg, cks);
-            const float sc = seg_scale[csg];
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < TC_BK / 4; ++c) {
                 float4 h, l;
-                split_tf32(ring[u][c].x * sc, h.x, l.x);
-                split_tf32(ring[u][c].y * sc, h.y, l.y);
-                split_tf32(ring[u][c].z * sc, h.z, l.z);
-                split_tf32(ring[u][c].w * sc, h.w, l.w);
-                const int off = (a_c0 + c) * (int)TC_LBO + a_row * 16;
+                split_tf32(v[c].x * sc, h.x, l.x);
+                split_tf32(v[c].y * sc, h.y, l.y);
+                split_tf32(v[c].z * sc, h.z, l.z);
+                split_tf32(v[c].w * sc, h.w, l.w);
+                const int off = c * (int)TC_LBO + my_row * 16;
                 *reinterpret_cast<float4*>(st + off) = h;
                 *reinterpret_cast<float4*>(st + TC_TILE_BYTES + off) = l;
             }
-            if (i + kPrefetch < total) fetch_a(i + kPrefetch, ring[u]);
-            if (i + 1 < total) {
-                const int nstage = (i + 1) % TC_STAGES;
-                if (i + 1 >= TC_STAGES)  // slab i-2 used that stage: wait until the tensor core consumed it
-                    tc_mbar_wait(&mma_done[nstage], (uint32_t)((i + 1) / TC_STAGES - 1) & 1u);
-                if (tid == 0) issue_b(i + 1);
-            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic smem writes -> async proxy
-            __syncthreads();
-            if (tid == 0) {
-                tc_mbar_wait(&b_full[stage], (uint32_t)(i / TC_STAGES) & 1u);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = tc_smem_u32(st), a_lo = a_hi + TC_TILE_BYTES;
-                const uint32_t b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
-#pragma unroll
-                for (int j = 0; j < TC_BK / 8; ++j) {  // one MMA consumes 8 k = two 16-byte chunks
-                    const uint32_t ko = j * 2 * TC_LBO;
-                    tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_hi + ko), (i > 0 || j > 0) ? 1u : 0u);
-                    tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_lo + ko), 1u);
-                    tc_mma(tmem_base, tc_smem_desc(a_lo + ko), tc_smem_desc(b_hi + ko), 1u);
-                }
-                tc_commit(&mma_done[stage]);
-            }
+            tc_arrive(&op_full[stage]);
         }
+    } else if (lane == 0) {
+        // ===== issuer: B image slabs by TMA (two ahead), then the six MMAs of every slab =====
+        auto issue_b = [&](int i) {
+            int sg, ks;
+            locate(i, sg, ks);
+            const TcSegment& s = g.seg[sg];
+            const float* src = s.b_image + ((int64_t)nt * s.k_slabs + ks) * (2 * TC_TILE_BYTES / 4);
+            const int slot = i % NN_B_SLOTS;
+            tc_expect_tx(&b_full[slot], 2 * TC_TILE_BYTES);
+            tc_bulk_g2s(smem + NN_OFF_B + slot * 2 * TC_TILE_BYTES, src, 2 * TC_TILE_BYTES, &b_full[slot]);
+        };
+        if (total > 0) issue_b(0);
+        if (total > 1) issue_b(1);
+        for (int i = 0; i < total; ++i) {
+            const int stage = i % NN_A_STAGES, slot = i % NN_B_SLOTS;
+            if (i + 2 < total) {  // slot (i+2)%3 was last read by slab i-1
+                if (i + 2 >= NN_B_SLOTS) tc_mbar_wait(&b_free[(i + 2) % NN_B_SLOTS], tc_free_parity(i + 2, NN_B_SLOTS));
+                issue_b(i + 2);
+            }
+            tc_mbar_wait(&op_full[stage], tc_full_parity(i, NN_A_STAGES));
+            tc_mbar_wait(&b_full[slot], tc_full_parity(i, NN_B_SLOTS));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = tc_smem_u32(smem + NN_OFF_A + stage * 2 * TC_TILE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
+            const uint32_t b_hi = tc_smem_u32(smem + NN_OFF_B + slot * 2 * TC_TILE_BYTES), b_lo = b_hi + TC_TILE_BYTES;
+#pragma unroll
+            for (int j = 0; j < TC_BK / 8; ++j) {  // one MMA consumes 8 k = two 16-byte chunks
+                const uint32_t ko = j * 2 * TC_LBO;
+                tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_hi + ko), (i > 0 || j > 0) ? 1u : 0u);
+                tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_lo + ko), 1u);
+                tc_mma(tmem_base, tc_smem_desc(a_lo + ko), tc_smem_desc(b_hi + ko), 1u);
+            }
+            tc_commit(&a_free[stage]);
+            tc_commit(&b_free[slot]);
+        }
+        tc_commit(&all_done);  // completes when every MMA issued above has completed
     }
-    // all MMAs were issued by one thread in order: the last commit covers them all
-    if (total > 0) {
-        const int last = total - 1;
-        tc_mbar_wait(&mma_done[last % TC_STAGES], (uint32_t)(last / TC_STAGES) & 1u);
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
     // ---- epilogue: TMEM -> registers -> shared (row stride 132 floats) -> coalesced 512-byte rows ----
-    constexpr int kRowStride = TC_BN + 4;
-    float* tile = reinterpret_cast<float*>(smem);  // the operand stages are free now (67.6 KB of 96 KB)
-    {
+    tc_mbar_wait(&all_done, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();  // every role is done with the rings
+    float* tile = reinterpret_cast<float*>(smem);
+    if (warp < 8) {
         const int q = warp & 3;      // TMEM lane quarter this warp may read
         const int half = warp >> 2;  // column half
         const int trow = q * 32 + lane;
@@ -343,7 +389,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(TcArgs g) {
             }
 #pragma unroll
             for (int e = 0; e < 32; e += 4)
-                *reinterpret_cast<float4*>(tile + trow * kRowStride + cbase + e) =
+                *reinterpret_cast<float4*>(tile + trow * TC_EPI_STRIDE + cbase + e) =
                     make_float4(__uint_as_float(acc[e]), __uint_as_float(acc[e + 1]), __uint_as_float(acc[e + 2]),
                                 __uint_as_float(acc[e + 3]));
         }
@@ -354,14 +400,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(TcArgs g) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
                      : "memory");
     }
+    if (warp >= 8) return;
     const bool vec_out = (g.f % 4 == 0) && (g.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.out) & 15) == 0) &&
                          (!g.relu_mask || (g.ld_mask % 4 == 0 && (reinterpret_cast<uintptr_t>(g.relu_mask) & 15) == 0)) &&
                          (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
     const int c = nt * TC_BN + lane * 4;  // this lane's 4 columns
-    for (int rr = warp; rr < TC_BM; rr += TC_THREADS / 32) {
+    for (int rr = warp; rr < TC_BM; rr += 8) {
         const int64_t r = row0 + rr;
         if (r >= g.n) break;
-        const float4 a4 = *reinterpret_cast<const float4*>(tile + rr * kRowStride + lane * 4);
+        const float4 a4 = *reinterpret_cast<const float4*>(tile + rr * TC_EPI_STRIDE + lane * 4);
         float v[4] = {a4.x, a4.y, a4.z, a4.w};
         if (vec_out && c + 3 < g.f) {
             if (g.accumulate_out) {
@@ -404,13 +451,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(TcArgs g) {
 // ---------------------------------------------------------------------------------------------
 // Weight gradient on the tensor cores:  partial[split][K,F] = sum_{r in split} A[row(r),:]^T G[row(r),:]
 // (dW = X^T dH; dW_id = X[id]^T dH[id]).  M = K, N = F, the reduction runs over matrix ROWS, so both
-// operands are transposed while they are staged: thread t < 128 owns column t of the A tile, thread
-// t >= 128 column t-128 of the G tile; per slab it reads its column's 16 rows (coalesced across the warp),
-// packs 4 consecutive rows into one 16-byte k-chunk, splits hi/lo and stores the canonical K-major slabs.
+// operands are transposed on their way to the operand stage:
+//   loaders     cp.async 16 rows x 512 B of A and of G (row segments, coalesced) into the raw ring
+//   converters  thread c reads COLUMN c of the raw A slab (16 values, conflict-free), packs 4 consecutive
+//               rows per 16-byte k-chunk, splits hi/lo, stores the K-major operand slab; same for G
+//   issuer      six tcgen05.mma per slab
 // A split covers kTnRowsPerSplit = 512 rows so that the truncating tensor-core accumulation stays
-// below 3e-6 relative; the partial tiles are summed in fp64, in split order, by split_reduce.
+// below 3e-6 relative; several splits run back to back in one CTA, their tiles are added in fp32
+// (round to nearest) in the CTA's shared accumulator, and the per-CTA partials are reduced in fp64.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTnRowsPerSplit = 512;
+constexpr int TN_RAW_SLOTS = 2, TN_STAGES = 2;
+constexpr int TN_RAW_BYTES = 2 * TC_BK * TC_BM * 4;                   // raw A (16 x 128) + raw G (16 x 128)
+constexpr int TN_OFF_OP = TN_RAW_SLOTS * TN_RAW_BYTES;                // 32 KB
+constexpr int TN_SMEM_BYTES = TN_OFF_OP + TN_STAGES * TC_STAGE_BYTES;  // 96 KB
+static_assert(TC_BM * TC_EPI_STRIDE * 4 <= TN_SMEM_BYTES, "epilogue tile must fit");
 
 struct TnTcArgs {
     const float* a;
@@ -420,26 +475,38 @@ struct TnTcArgs {
     const int64_t* row_index;
     int64_t n;
     int k, f;
-    float* partial;  // [splits][k][f]
+    int64_t rows_per_cta;  // multiple of kTnRowsPerSplit
+    float* partial;        // [gridDim.y][k][f]
 };
 
-template <bool DUMMY>
-__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_tn_kernel(TnTcArgs g) {
+template <bool VEC>
+__global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_tn_kernel(TnTcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t mma_done[TC_STAGES];
+    __shared__ __align__(8) uint64_t raw_full[TN_RAW_SLOTS], raw_empty[TN_RAW_SLOTS];
+    __shared__ __align__(8) uint64_t op_full[TN_STAGES], op_free[TN_STAGES];
+    __shared__ __align__(8) uint64_t seg_done, tmem_free;
     __shared__ uint32_t tmem_base_smem;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_tiles = (g.f + TC_BN - 1) / TC_BN;
     const int m0 = (blockIdx.x / n_tiles) * TC_BM;  // offset in K (rows of the output)
     const int c0 = (blockIdx.x % n_tiles) * TC_BN;  // offset in F
-    const int64_t r_beg = (int64_t)blockIdx.y * kTnRowsPerSplit;
-    const int64_t r_end = r_beg + kTnRowsPerSplit < g.n ? r_beg + kTnRowsPerSplit : g.n;
-    const int total = (int)((r_end - r_beg + TC_BK - 1) / TC_BK);
+    const int64_t r_beg = (int64_t)blockIdx.y * g.rows_per_cta;
+    const int64_t r_end = r_beg + g.rows_per_cta < g.n ? r_beg + g.rows_per_cta : g.n;
+    const int total = r_end > r_beg ? (int)((r_end - r_beg + TC_BK - 1) / TC_BK) : 0;
+    constexpr int kSlabsPerSeg = kTnRowsPerSplit / TC_BK;  // 32 slabs, then the accumulator is drained
 
     if (tid == 0) {
-#pragma unroll
-        for (int i = 0; i < TC_STAGES; ++i) tc_mbar_init(&mma_done[i], 1);
+        for (int i = 0; i < TN_RAW_SLOTS; ++i) {
+            tc_mbar_init(&raw_full[i], TC_ROLE_THREADS);
+            tc_mbar_init(&raw_empty[i], TC_ROLE_THREADS);
+        }
+        for (int i = 0; i < TN_STAGES; ++i) {
+            tc_mbar_init(&op_full[i], TC_ROLE_THREADS);
+            tc_mbar_init(&op_free[i], 1);
+        }
+        tc_mbar_init(&seg_done, 1);
+        tc_mbar_init(&tmem_free, 2 * TC_ROLE_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -453,98 +520,133 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_tn_kernel(TnTcArgs g) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
+    const int rt = tid & (TC_ROLE_THREADS - 1);
 
-    // operand column owned by this thread
-    const bool is_a = tid < 128;
-    const int col = is_a ? m0 + tid : c0 + (tid - 128);
-    const bool col_ok = is_a ? col < g.k : col < g.f;
-    const float* base = is_a ? g.a : g.g;
-    const int64_t ld = is_a ? g.lda : g.ldg;
-    const int trow = tid & 127;  // row of the smem slab (= M or N index)
-
-    auto fetch = [&](int i, float (&v)[TC_BK]) {
-        const int64_t r0 = r_beg + (int64_t)i * TC_BK;
+    // fp32 accumulator of the CTA across its 512-row segments: this thread's share of the 128x128 tile
+    // in the epilogue mapping (row = warp-quarter*32 + lane, 64 columns) -- kept in registers
+    float racc[64];
 #pragma unroll
-        for (int kk = 0; kk < TC_BK; ++kk) {
-            const int64_t r = r0 + kk;
-            float x = 0.f;
-            if (col_ok && r < r_end) {
-                const int64_t rr = g.row_index ? __ldg(g.row_index + r) : r;
-                x = __ldg(base + rr * ld + col);
-            }
-            v[kk] = x;
+    for (int e = 0; e < 64; ++e) racc[e] = 0.f;
+
+    // At the end of every 512-row segment warps 0-7 drain the TMEM tile into racc (each warp its lane
+    // quarter, loaders the low / converters the high 64 columns) and release the accumulator.  Both
+    // roles have finished their part of the segment when they get here, so nothing can deadlock.
+    auto drain = [&](int sgi) {
+        const int q = warp & 3, half = warp >> 2;
+        tc_mbar_wait(&seg_done, (uint32_t)sgi & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            uint32_t acc[32];
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64 + part * 32), acc);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) racc[part * 32 + e] += __uint_as_float(acc[e]);
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        tc_arrive(&tmem_free);  // the issuer may overwrite the accumulator
     };
-    constexpr int kPrefetch = 2;
-    float ring[kPrefetch][TC_BK];
+
+    if (warp < 4) {
+        // ===== loaders =====
+        for (int i = 0; i < total; ++i) {
+            const int slot = i % TN_RAW_SLOTS;
+            if (i >= TN_RAW_SLOTS) tc_mbar_wait(&raw_empty[slot], tc_free_parity(i, TN_RAW_SLOTS));
+            const int64_t r0 = r_beg + (int64_t)i * TC_BK;
+            uint8_t* raw_a = smem + slot * TN_RAW_BYTES;
+            uint8_t* raw_g = raw_a + TC_BK * TC_BM * 4;
 #pragma unroll
-    for (int u = 0; u < kPrefetch; ++u)
-        if (u < total) fetch(u, ring[u]);
-    for (int i0 = 0; i0 < total; i0 += kPrefetch) {
+            for (int j = 0; j < (TC_BK * TC_BM / 4) / TC_ROLE_THREADS; ++j) {  // 4 x 16 B per operand per thread
+                const int q = rt + j * TC_ROLE_THREADS;
+                const int kk = q >> 5, cq = q & 31;  // slab row, 16-byte chunk inside the 512-byte row segment
+                const int64_t r = r0 + kk;
+                const bool rok = r < r_end;
+                const int64_t rr = rok ? (g.row_index ? __ldg(g.row_index + r) : r) : 0;
+                const int ca = m0 + cq * 4, cg = c0 + cq * 4;
+                if (VEC) {
+                    const int la = rok ? (g.k - ca) * 4 : 0, lg = rok ? (g.f - cg) * 4 : 0;
+                    tc_cp_async16(raw_a + q * 16, g.a + rr * g.lda + (ca < g.k ? ca : 0),
+                                  la >= 16 ? 16u : (la > 0 ? (uint32_t)la : 0u));
+                    tc_cp_async16(raw_g + q * 16, g.g + rr * g.ldg + (cg < g.f ? cg : 0),
+                                  lg >= 16 ? 16u : (lg > 0 ? (uint32_t)lg : 0u));
+                } else {
 #pragma unroll
-        for (int u = 0; u < kPrefetch; ++u) {
-            const int i = i0 + u;
-            if (i >= total) break;
-            const int stage = i % TC_STAGES;
-            if (i >= TC_STAGES)  // slab i-3 used this stage
-                tc_mbar_wait(&mma_done[stage], (uint32_t)(i / TC_STAGES - 1) & 1u);
-            uint8_t* st = smem + stage * TC_STAGE_BYTES + (is_a ? 0 : 2 * TC_TILE_BYTES);
+                    for (int e = 0; e < 4; ++e) {
+                        const bool oka = rok && ca + e < g.k, okg = rok && cg + e < g.f;
+                        tc_cp_async4(raw_a + q * 16 + e * 4, g.a + rr * g.lda + (oka ? ca + e : 0), oka ? 4u : 0u);
+                        tc_cp_async4(raw_g + q * 16 + e * 4, g.g + rr * g.ldg + (okg ? cg + e : 0), okg ? 4u : 0u);
+                    }
+                }
+            }
+            tc_cp_async_arrive(&raw_full[slot]);
+            if (i % kSlabsPerSeg == kSlabsPerSeg - 1 || i == total - 1) drain(i / kSlabsPerSeg);
+        }
+    } else if (warp < 8) {
+        // ===== converters: column rt of raw A and raw G -> K-major hi/lo slabs =====
+        for (int i = 0; i < total; ++i) {
+            const int slot = i % TN_RAW_SLOTS, stage = i % TN_STAGES;
+            tc_mbar_wait(&raw_full[slot], tc_full_parity(i, TN_RAW_SLOTS));
+            const float* raw_a = reinterpret_cast<const float*>(smem + slot * TN_RAW_BYTES);
+            const float* raw_g = raw_a + TC_BK * TC_BM;
+            float va[TC_BK], vg[TC_BK];
+#pragma unroll
+            for (int kk = 0; kk < TC_BK; ++kk) {
+                va[kk] = raw_a[kk * TC_BM + rt];
+                vg[kk] = raw_g[kk * TC_BM + rt];
+            }
+            tc_arrive(&raw_empty[slot]);
+            if (i >= TN_STAGES) tc_mbar_wait(&op_free[stage], tc_free_parity(i, TN_STAGES));
+            uint8_t* st = smem + TN_OFF_OP + stage * TC_STAGE_BYTES;
 #pragma unroll
             for (int c = 0; c < TC_BK / 4; ++c) {
                 float4 h, l;
-                split_tf32(ring[u][c * 4 + 0], h.x, l.x);
-                split_tf32(ring[u][c * 4 + 1], h.y, l.y);
-                split_tf32(ring[u][c * 4 + 2], h.z, l.z);
-                split_tf32(ring[u][c * 4 + 3], h.w, l.w);
-                const int off = c * (int)TC_LBO + trow * 16;
+                const int off = c * (int)TC_LBO + rt * 16;
+                split_tf32(va[c * 4 + 0], h.x, l.x);
+                split_tf32(va[c * 4 + 1], h.y, l.y);
+                split_tf32(va[c * 4 + 2], h.z, l.z);
+                split_tf32(va[c * 4 + 3], h.w, l.w);
                 *reinterpret_cast<float4*>(st + off) = h;
                 *reinterpret_cast<float4*>(st + TC_TILE_BYTES + off) = l;
+                split_tf32(vg[c * 4 + 0], h.x, l.x);
+                split_tf32(vg[c * 4 + 1], h.y, l.y);
+                split_tf32(vg[c * 4 + 2], h.z, l.z);
+                split_tf32(vg[c * 4 + 3], h.w, l.w);
+                *reinterpret_cast<float4*>(st + 2 * TC_TILE_BYTES + off) = h;
+                *reinterpret_cast<float4*>(st + 3 * TC_TILE_BYTES + off) = l;
             }
-            if (i + kPrefetch < total) fetch(i + kPrefetch, ring[u]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            if (tid == 0) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = tc_smem_u32(smem + stage * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
-                const uint32_t b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
+            tc_arrive(&op_full[stage]);
+            if (i % kSlabsPerSeg == kSlabsPerSeg - 1 || i == total - 1) drain(i / kSlabsPerSeg);
+        }
+    } else if (lane == 0) {
+        // ===== issuer =====
+        for (int i = 0; i < total; ++i) {
+            const int stage = i % TN_STAGES;
+            const int in_seg = i % kSlabsPerSeg;
+            if (in_seg == 0 && i > 0) tc_mbar_wait(&tmem_free, (uint32_t)(i / kSlabsPerSeg - 1) & 1u);  // drained
+            tc_mbar_wait(&op_full[stage], tc_full_parity(i, TN_STAGES));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = tc_smem_u32(smem + TN_OFF_OP + stage * TC_STAGE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
+            const uint32_t b_hi = a_hi + 2 * TC_TILE_BYTES, b_lo = a_hi + 3 * TC_TILE_BYTES;
 #pragma unroll
-                for (int j = 0; j < TC_BK / 8; ++j) {
-                    const uint32_t ko = j * 2 * TC_LBO;
-                    tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_hi + ko), (i > 0 || j > 0) ? 1u : 0u);
-                    tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_lo + ko), 1u);
-                    tc_mma(tmem_base, tc_smem_desc(a_lo + ko), tc_smem_desc(b_hi + ko), 1u);
-                }
-                tc_commit(&mma_done[stage]);
+            for (int j = 0; j < TC_BK / 8; ++j) {
+                const uint32_t ko = j * 2 * TC_LBO;
+                tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_hi + ko), (in_seg > 0 || j > 0) ? 1u : 0u);
+                tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_lo + ko), 1u);
+                tc_mma(tmem_base, tc_smem_desc(a_lo + ko), tc_smem_desc(b_hi + ko), 1u);
             }
+            tc_commit(&op_free[stage]);
+            if (in_seg == kSlabsPerSeg - 1 || i == total - 1) tc_commit(&seg_done);  // this 512-row segment is in TMEM
         }
     }
-    if (total > 0) {
-        const int last = total - 1;
-        tc_mbar_wait(&mma_done[last % TC_STAGES], (uint32_t)(last / TC_STAGES) & 1u);
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    constexpr int kRowStride = TC_BN + 4;
+    __syncthreads();  // all roles done with the rings
     float* tile = reinterpret_cast<float*>(smem);
-    {
+    if (warp < 8) {
         const int q = warp & 3, half = warp >> 2;
         const int tr = q * 32 + lane;
 #pragma unroll
-        for (int part = 0; part < 2; ++part) {
-            const int cbase = half * 64 + part * 32;
-            uint32_t acc[32];
-            if (total > 0) {
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbase, acc);
-            } else {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) acc[e] = 0u;
-            }
-#pragma unroll
-            for (int e = 0; e < 32; e += 4)
-                *reinterpret_cast<float4*>(tile + tr * kRowStride + cbase + e) =
-                    make_float4(__uint_as_float(acc[e]), __uint_as_float(acc[e + 1]), __uint_as_float(acc[e + 2]),
-                                __uint_as_float(acc[e + 3]));
-        }
+        for (int e = 0; e < 64; e += 4)
+            *reinterpret_cast<float4*>(tile + tr * TC_EPI_STRIDE + half * 64 + e) =
+                make_float4(racc[e], racc[e + 1], racc[e + 2], racc[e + 3]);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -552,13 +654,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_tn_kernel(TnTcArgs g) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS)
                      : "memory");
     }
+    if (warp >= 8) return;
     float* dst = g.partial + (int64_t)blockIdx.y * g.k * g.f;
     const int c = c0 + lane * 4;
     const bool vec = (g.f % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.partial) & 15) == 0);
-    for (int rr = warp; rr < TC_BM; rr += TC_THREADS / 32) {
+    for (int rr = warp; rr < TC_BM; rr += 8) {
         const int m = m0 + rr;
         if (m >= g.k) break;
-        const float4 a4 = *reinterpret_cast<const float4*>(tile + rr * kRowStride + lane * 4);
+        const float4 a4 = *reinterpret_cast<const float4*>(tile + rr * TC_EPI_STRIDE + lane * 4);
         if (vec && c + 3 < g.f) {
             *reinterpret_cast<float4*>(dst + (int64_t)m * g.f + c) = a4;
         } else {
@@ -576,9 +679,16 @@ __global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict_
     const int64_t total = rows * cols;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
-        double s = 0.0;
-        for (int64_t p = 0; p < splits; ++p) s += (double)part[p * total + e];
-        out[(e / cols) * ldo + (e % cols)] = (float)s;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int64_t p = 0;
+        for (; p + 3 < splits; p += 4) {
+            s0 += (double)part[p * total + e];
+            s1 += (double)part[(p + 1) * total + e];
+            s2 += (double)part[(p + 2) * total + e];
+            s3 += (double)part[(p + 3) * total + e];
+        }
+        for (; p < splits; ++p) s0 += (double)part[p * total + e];
+        out[(e / cols) * ldo + (e % cols)] = (float)((s0 + s1) + (s2 + s3));
     }
 }
 
@@ -667,8 +777,8 @@ int gg_id_gemm_tc_f32(const gg_gemm_segment* segs, int num_segments, int b_trans
     cudaStream_t st = as_stream(stream);
     static bool attr_done = false;
     if (!attr_done) {
-        GG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-        GG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        GG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM_BYTES));
+        GG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM_BYTES));
         attr_done = true;
     }
     Carver c(workspace);
@@ -701,16 +811,29 @@ int gg_id_gemm_tc_f32(const gg_gemm_segment* segs, int num_segments, int b_trans
         g.out = out; g.ldo = ldo;
         g.accumulate_out = l > 0;
         g.final_chunk = l == num_launches - 1;
-        if (vec_a) tc_gemm_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g);
-        else tc_gemm_kernel<false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(g);
+        if (vec_a) tc_gemm_kernel<true><<<grid, TC_BLOCK, NN_SMEM_BYTES, st>>>(g);
+        else tc_gemm_kernel<false><<<grid, TC_BLOCK, NN_SMEM_BYTES, st>>>(g);
         GG_LAUNCHED();
     }
     return GG_OK;
 }
 
+static void tn_tc_plan(int64_t n, int64_t k, int64_t f, int64_t* ctas, int64_t* rows_per_cta) {
+    // about two waves of CTAs over the 148 SMs x 2; every CTA runs whole 512-row segments back to back
+    int64_t tiles = ceil_div(k, TC_BM) * ceil_div(f, TC_BN);
+    int64_t segs = ceil_div(n > 0 ? n : 1, kTnRowsPerSplit);
+    int64_t want = ceil_div((int64_t)kNumSMs * 4, tiles);
+    int64_t c = segs < want ? segs : want;
+    if (c < 1) c = 1;
+    int64_t rpc = ceil_div(segs, c) * kTnRowsPerSplit;
+    *rows_per_cta = rpc;
+    *ctas = ceil_div(n > 0 ? n : 1, rpc);
+}
+
 size_t gg_gemm_tn_tc_workspace_bytes(int64_t n, int64_t k, int64_t f) {
-    int64_t splits = ceil_div(n > 0 ? n : 1, kTnRowsPerSplit);
-    return (size_t)splits * (size_t)k * (size_t)f * sizeof(float) + 256;
+    int64_t ctas, rpc;
+    tn_tc_plan(n, k, f, &ctas, &rpc);
+    return (size_t)ctas * (size_t)k * (size_t)f * sizeof(float) + 256;
 }
 
 int gg_gemm_tn_tc_f32(const float* a, int64_t lda, const int64_t* row_index, const float* g, int64_t ldg,
@@ -730,24 +853,25 @@ int gg_gemm_tn_tc_f32(const float* a, int64_t lda, const int64_t* row_index, con
         set_error("gg_gemm_tn_tc_f32: workspace %zu < %zu", workspace_bytes, gg_gemm_tn_tc_workspace_bytes(n, k, f));
         return GG_ERR_WORKSPACE;
     }
-    const int64_t splits = ceil_div(n, kTnRowsPerSplit);
-    GG_REQUIRE(splits <= 65535 * 16, "gg_gemm_tn_tc_f32: too many rows");
+    int64_t ctas, rpc;
+    tn_tc_plan(n, k, f, &ctas, &rpc);
     static bool attr_done = false;
     if (!attr_done) {
-        GG_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     TC_SMEM_BYTES));
+        GG_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
+        GG_CUDA(cudaFuncSetAttribute(tc_gemm_tn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TN_SMEM_BYTES));
         attr_done = true;
     }
-    TnTcArgs t{a, lda, g, ldg, row_index, n, (int)k, (int)f, static_cast<float*>(workspace)};
+    TnTcArgs t{a, lda, g, ldg, row_index, n, (int)k, (int)f, rpc, static_cast<float*>(workspace)};
     const int64_t tiles = ceil_div(k, TC_BM) * ceil_div(f, TC_BN);
-    // gridDim.y is limited to 65535: fold the splits when there are more
-    GG_REQUIRE(splits <= 65535, "gg_gemm_tn_tc_f32: more than 65535 row splits (n > 33.5M rows)");
-    dim3 grid((unsigned)tiles, (unsigned)splits);
-    tc_gemm_tn_kernel<true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(t);
+    const bool vec = (k % 4 == 0) && (f % 4 == 0) && (lda % 4 == 0) && (ldg % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(a) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+    dim3 grid((unsigned)tiles, (unsigned)ctas);
+    if (vec) tc_gemm_tn_kernel<true><<<grid, TC_BLOCK, TN_SMEM_BYTES, st>>>(t);
+    else tc_gemm_tn_kernel<false><<<grid, TC_BLOCK, TN_SMEM_BYTES, st>>>(t);
     GG_LAUNCHED();
     const int64_t total = k * f;
     int blocks = (int)(ceil_div(total, 256) < kNumSMs * 8 ? ceil_div(total, 256) : kNumSMs * 8);
-    tn_reduce_kernel<<<blocks, 256, 0, st>>>(t.partial, splits, k, f, out, ldo);
+    tn_reduce_kernel<<<blocks, 256, 0, st>>>(t.partial, ctas, k, f, out, ldo);
     GG_LAUNCHED();
     return GG_OK;
 }

@@ -52,7 +52,8 @@ SIGNATURES = {
     "gg_spmm_plan_build": (c_int, [c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr]),
     "gg_spmm_mp_workspace_bytes": (c_size, [c_i64, c_i64]),
     "gg_spmm_mp_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64,
-                               c_i64, c_int, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_size, c_int, c_ptr]),
+                               c_i64, c_int, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                               c_size, c_int, c_ptr]),
     "gg_id_gemm_f32": (c_int, [ctypes.POINTER(GemmSegment), c_int, c_int, c_i64, c_i64, c_ptr, c_int,
                                c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_id_gemm_tc_workspace_bytes": (c_size, [ctypes.POINTER(GemmSegment), c_int, c_i64]),
@@ -88,6 +89,11 @@ SIGNATURES = {
                                 c_ptr, c_size, c_ptr]),
     "gg_egonet_fill": (c_int, [c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_ptr, c_ptr,
                                c_i64, c_ptr, c_ptr, c_ptr]),
+    "gg_gat_alpha_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_ptr, c_ptr]),
+    "gg_gat_sddmm_mp_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64,
+                                    c_ptr, c_ptr, c_ptr]),
+    "gg_gat_dz_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_ptr]),
+    "gg_gat_csc_gather_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "gg_gather_rows_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_scatter_add_rows_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_relu_grad_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr]),

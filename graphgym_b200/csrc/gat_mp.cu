@@ -1,0 +1,305 @@
+// GAT at scale (heads = 1): the three gather passes of a GAT layer on the merge-path machinery.
+//
+// gat.cu fuses softmax and aggregation in one warp-per-row kernel; on power-law graphs that inherits the
+// imbalance measured for SpMM v1 (hub rows of 10^4 slots serialise one warp).  Here the layer is split
+// into light per-slot passes (4-12 B per edge) and heavy feature-row passes that run on the balanced
+// merge-path kernels:
+//   forward   gat_alpha        alpha[s] = softmax_i(leaky_relu(a_tgt[i] + a_src[j_s]))    light, warp per row
+//             gg_spmm_mp_f32   out = sum_s alpha[s] H[j_s] + bias                           heavy (spmm_mp.cu)
+//   backward  gat_sddmm_mp     dalpha[s] = <g_i, H[j_s]>  (merge-path stream over the slots, g_i of the
+//                              current row in registers, 8 gathers in flight, 9-shuffle reduction)      heavy
+//             gat_dz           D_i = sum alpha dalpha;  dz = alpha (dalpha - D_i) lrelu'(z);  da_tgt      light
+//             gat_csc_gather   alpha_T[t] = alpha[map[t]],  da_src[j] = sum_t dz[map[t]]                  light
+//             gg_spmm_mp_f32   dH = sum_t alpha_T[t] g[i_t] + da_src att_src + da_tgt att_tgt (rank-1)   heavy
+// ref: GATIDConvLayer.message/update graphgym/contrib/layer/idconv.py:317-342, PyG softmax.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace gg {
+
+constexpr int kGmWarps = 8;
+constexpr int kGmThreads = kGmWarps * 32;
+
+__device__ __forceinline__ float gm_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float gm_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float gm_leaky(float z, float slope) { return z > 0.f ? z : slope * z; }
+
+// one warp per target row: max, sum of exp, alpha (PyG softmax: exp(z - max) / (sum + 1e-16))
+__global__ void __launch_bounds__(kGmThreads)
+    gat_alpha_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
+                     const float* __restrict__ a_tgt, const float* __restrict__ a_src, int64_t n, float slope,
+                     float* __restrict__ alpha) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kGmWarps + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    const float at = __ldg(a_tgt + row);
+    if (end - beg <= 32) {  // the common case: the whole row in registers, one pass
+        const int s = beg + lane;
+        const bool in = s < end;
+        const float z = in ? gm_leaky(at + __ldg(a_src + __ldg(nbr + s)), slope) : -CUDART_INF_F;
+        const float m = gm_warp_max(z);
+        const float e = in ? expf(z - m) : 0.f;
+        const float inv = 1.0f / (gm_warp_sum(e) + 1e-16f);
+        if (in) alpha[s] = e * inv;
+        return;
+    }
+    float m = -CUDART_INF_F;
+    for (int s = beg + lane; s < end; s += 32) m = fmaxf(m, gm_leaky(at + __ldg(a_src + __ldg(nbr + s)), slope));
+    m = gm_warp_max(m);
+    float sum = 0.f;
+    for (int s = beg + lane; s < end; s += 32) sum += expf(gm_leaky(at + __ldg(a_src + __ldg(nbr + s)), slope) - m);
+    const float inv = 1.0f / (gm_warp_sum(sum) + 1e-16f);
+    for (int s = beg + lane; s < end; s += 32)
+        alpha[s] = expf(gm_leaky(at + __ldg(a_src + __ldg(nbr + s)), slope) - m) * inv;
+}
+
+// one warp per target row: D_i = sum_s alpha dalpha (fixed order), dz, da_tgt
+__global__ void __launch_bounds__(kGmThreads)
+    gat_dz_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
+                  const float* __restrict__ a_tgt, const float* __restrict__ a_src,
+                  const float* __restrict__ alpha, const float* __restrict__ dalpha, int64_t n, float slope,
+                  float* __restrict__ dz, float* __restrict__ da_tgt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kGmWarps + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    const float at = __ldg(a_tgt + row);
+    float d = 0.f;
+    for (int s = beg + lane; s < end; s += 32) d = fmaf(__ldg(alpha + s), __ldg(dalpha + s), d);
+    d = gm_warp_sum(d);
+    float acc = 0.f;
+    for (int s = beg + lane; s < end; s += 32) {
+        const float z = at + __ldg(a_src + __ldg(nbr + s));
+        const float v = __ldg(alpha + s) * (__ldg(dalpha + s) - d) * (z > 0.f ? 1.f : slope);
+        dz[s] = v;
+        acc += v;
+    }
+    acc = gm_warp_sum(acc);
+    if (lane == 0) da_tgt[row] = acc;
+}
+
+// one warp per source row of the CSC layout: alpha in CSC order, da_src
+__global__ void __launch_bounds__(kGmThreads)
+    gat_csc_gather_kernel(const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ map,
+                          const float* __restrict__ alpha, const float* __restrict__ dz, int64_t n,
+                          float* __restrict__ alpha_t, float* __restrict__ da_src) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kGmWarps + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int beg = __ldg(rowptr_t + row), end = __ldg(rowptr_t + row + 1);
+    float acc = 0.f;
+    for (int t = beg + lane; t < end; t += 32) {
+        const int m = __ldg(map + t);
+        alpha_t[t] = __ldg(alpha + m);
+        acc += __ldg(dz + m);
+    }
+    acc = gm_warp_sum(acc);
+    if (lane == 0) da_src[row] = acc;
+}
+
+// ---- merge-path SDDMM: dalpha[s] = <g[row(s),:], h[nbr[s],:]> ---------------------------------------
+constexpr int kSdMaxUnits = 480;
+constexpr int kSdTile = kSdMaxUnits + 8;
+
+struct SddmmArgs {
+    const int32_t* rowptr;
+    const int32_t* nbr;
+    const int32_t* item_row;
+    const int32_t* item_slot;
+    int items;
+    const float* h;
+    int64_t ldh;
+    const float* g;
+    int64_t ldg;
+    int64_t n;
+    int f;
+    int* counter;
+    float* dalpha;
+};
+
+template <int VPL>
+__global__ void __launch_bounds__(kGmThreads, VPL == 1 ? 4 : 2) gat_sddmm_mp_kernel(SddmmArgs a) {
+    constexpr int U = 8;
+    __shared__ int32_t s_nbr_all[kGmWarps][kSdTile];
+    __shared__ int32_t s_rp_all[kGmWarps][kSdTile];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int32_t* s_nbr = s_nbr_all[wid];
+    int32_t* s_rp = s_rp_all[wid];
+    const int nvec = a.f >> 2;
+    const float4* __restrict__ h4 = reinterpret_cast<const float4*>(a.h);
+    const float4* __restrict__ g4 = reinterpret_cast<const float4*>(a.g);
+    const int64_t ldh4 = a.ldh >> 2, ldg4 = a.ldg >> 2;
+    bool act[VPL];
+#pragma unroll
+    for (int q = 0; q < VPL; ++q) act[q] = lane + q * 32 < nvec;
+
+    int item = 0;
+    if (lane == 0) item = atomicAdd(a.counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    while (item < a.items) {
+        int next = 0;
+        if (lane == 0) next = atomicAdd(a.counter, 1);
+        const int r0 = __ldg(a.item_row + item), s0 = __ldg(a.item_slot + item);
+        const int r1 = __ldg(a.item_row + item + 1), s1 = __ldg(a.item_slot + item + 1);
+        __syncwarp();
+        for (int q = s0 + lane; q < s1; q += 32) s_nbr[q - s0] = __ldg(a.nbr + q);
+        const int nrp = (r1 < a.n ? r1 + 1 : (int)a.n) - r0 + 1;
+        for (int i = lane; i < nrp; i += 32) s_rp[i] = __ldg(a.rowptr + r0 + i);
+        __syncwarp();
+
+        int cur = r0;
+        int re = r0 < a.n ? s_rp[1] : 0x7fffffff;
+        // g of the current row, and of the next one so that a row switch never waits on global memory
+        float4 gc[VPL], gn[VPL];
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) {
+            gc[q] = (act[q] && cur < a.n) ? __ldg(g4 + (int64_t)cur * ldg4 + lane + q * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gn[q] = (act[q] && cur + 1 < a.n) ? __ldg(g4 + (int64_t)(cur + 1) * ldg4 + lane + q * 32)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int s = s0; s < s1; s += U) {
+            float4 v[U][VPL];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool ok = s + u < s1;
+                const int j = ok ? s_nbr[s + u - s0] : 0;
+                const float4* p = h4 + (int64_t)j * ldh4 + lane;
+#pragma unroll
+                for (int q = 0; q < VPL; ++q)
+                    v[u][q] = (ok && act[q]) ? ldg_nc_f4(p + q * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float p8[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                p8[u] = 0.f;
+                if (s + u < s1) {  // warp-uniform
+                    while (s + u >= re) {  // this slot belongs to a later row: switch g
+                        ++cur;
+                        re = s_rp[cur - r0 + 1];
+#pragma unroll
+                        for (int q = 0; q < VPL; ++q) {
+                            gc[q] = gn[q];
+                            gn[q] = (act[q] && cur + 1 < a.n) ? __ldg(g4 + (int64_t)(cur + 1) * ldg4 + lane + q * 32)
+                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < VPL; ++q)
+                        p8[u] += gc[q].x * v[u][q].x + gc[q].y * v[u][q].y + gc[q].z * v[u][q].z + gc[q].w * v[u][q].w;
+                }
+            }
+            // reduce 8 per-lane partials over the warp with 9 shuffles: halve the value set while folding
+            // lane bits 4, 3, 2; the sum of slot k ends up in the 4 lanes with (lane >> 2) == k
+            float w4[4], w2[2], w1;
+            {
+                const bool hi = lane & 16;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float send = hi ? p8[k] : p8[k + 4];
+                    const float keep = hi ? p8[k + 4] : p8[k];
+                    w4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+            }
+            {
+                const bool hi = lane & 8;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float send = hi ? w4[k] : w4[k + 2];
+                    const float keep = hi ? w4[k + 2] : w4[k];
+                    w2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+            }
+            {
+                const bool hi = lane & 4;
+                const float send = hi ? w2[0] : w2[1];
+                const float keep = hi ? w2[1] : w2[0];
+                w1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            w1 += __shfl_xor_sync(0xffffffffu, w1, 2);
+            w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+            // lane bits (4,3,2) select the slot: bit4 -> +4, bit3 -> +2, bit2 -> +1
+            const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+            if ((lane & 3) == 0 && s + k < s1) a.dalpha[s + k] = w1;
+        }
+        item = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+static inline bool gm_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+int gg_gat_alpha_f32(const int32_t* rowptr, const int32_t* nbr, const float* a_tgt, const float* a_src,
+                     int64_t n, float slope, float* alpha, gg_stream_t stream) {
+    GG_REQUIRE(n >= 0, "gg_gat_alpha_f32: negative size");
+    if (n == 0) return GG_OK;
+    GG_REQUIRE(rowptr && a_tgt && a_src && alpha, "gg_gat_alpha_f32: null pointer");
+    gat_alpha_kernel<<<(int)ceil_div(n, kGmWarps), kGmThreads, 0, as_stream(stream)>>>(rowptr, nbr, a_tgt, a_src, n,
+                                                                                       slope, alpha);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
+int gg_gat_dz_f32(const int32_t* rowptr, const int32_t* nbr, const float* a_tgt, const float* a_src,
+                  const float* alpha, const float* dalpha, int64_t n, float slope, float* dz, float* da_tgt,
+                  gg_stream_t stream) {
+    GG_REQUIRE(n >= 0, "gg_gat_dz_f32: negative size");
+    if (n == 0) return GG_OK;
+    GG_REQUIRE(rowptr && a_tgt && a_src && alpha && dalpha && dz && da_tgt, "gg_gat_dz_f32: null pointer");
+    gat_dz_kernel<<<(int)ceil_div(n, kGmWarps), kGmThreads, 0, as_stream(stream)>>>(rowptr, nbr, a_tgt, a_src, alpha,
+                                                                                    dalpha, n, slope, dz, da_tgt);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
+int gg_gat_csc_gather_f32(const int32_t* rowptr_t, const int32_t* slot_map, const float* alpha, const float* dz,
+                          int64_t n, float* alpha_t, float* da_src, gg_stream_t stream) {
+    GG_REQUIRE(n >= 0, "gg_gat_csc_gather_f32: negative size");
+    if (n == 0) return GG_OK;
+    GG_REQUIRE(rowptr_t && alpha && dz && alpha_t && da_src, "gg_gat_csc_gather_f32: null pointer");
+    gat_csc_gather_kernel<<<(int)ceil_div(n, kGmWarps), kGmThreads, 0, as_stream(stream)>>>(rowptr_t, slot_map, alpha,
+                                                                                            dz, n, alpha_t, da_src);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
+int gg_gat_sddmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const int32_t* item_row,
+                        const int32_t* item_slot, int64_t items, const float* h, int64_t ldh, const float* g,
+                        int64_t ldg, int64_t n, int64_t f, float* dalpha, int32_t* counter, gg_stream_t stream) {
+    GG_REQUIRE(n >= 0 && f >= 0 && items >= 0, "gg_gat_sddmm_mp_f32: negative size");
+    if (n == 0 || f == 0 || items == 0) return GG_OK;
+    GG_REQUIRE(rowptr && item_row && item_slot && h && g && dalpha && counter, "gg_gat_sddmm_mp_f32: null pointer");
+    if (!((f % 4 == 0) && f <= 1024 && ldh % 4 == 0 && ldg % 4 == 0 && gm_al16(h) && gm_al16(g))) {
+        set_error("gg_gat_sddmm_mp_f32: needs f %% 4 == 0, f <= 1024 and 16-byte aligned rows");
+        return GG_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = as_stream(stream);
+    GG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    SddmmArgs a{rowptr, nbr, item_row, item_slot, (int)items, h, ldh, g, ldg, n, (int)f, counter, dalpha};
+    const int nvec = (int)(f / 4);
+    int per_sm = nvec <= 32 ? 4 : 2;
+    int grid = (int)ceil_div(items, kGmWarps);
+    if (grid > kNumSMs * per_sm) grid = kNumSMs * per_sm;
+    if (nvec <= 32) gat_sddmm_mp_kernel<1><<<grid, kGmThreads, 0, st>>>(a);
+    else if (nvec <= 64) gat_sddmm_mp_kernel<2><<<grid, kGmThreads, 0, st>>>(a);
+    else if (nvec <= 128) gat_sddmm_mp_kernel<4><<<grid, kGmThreads, 0, st>>>(a);
+    else gat_sddmm_mp_kernel<8><<<grid, kGmThreads, 0, st>>>(a);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
+}  // extern "C"

@@ -47,6 +47,12 @@ struct MpArgs {
     int* counter;
     float* carry;  // [items, f]
     float* head;   // [items, f]
+    // optional rank-1 epilogue terms: out[row,:] += r1_s[row] * r1_v[:] + r2_s[row] * r2_v[:]
+    // (GAT backward: da_src[j] * att_src + da_tgt[j] * att_tgt, ref: idconv.py:324)
+    const float* r1_s;
+    const float* r1_v;
+    const float* r2_s;
+    const float* r2_v;
 };
 
 // ---- mbarrier / bulk-copy PTX -----------------------------------------------------------------
@@ -189,6 +195,8 @@ __global__ void __launch_bounds__(kMpThreads, VPL == 1 ? 4 : 2) spmm_mp_kernel(M
                         fma4(r, a.self_scale,
                              __ldg(reinterpret_cast<const float4*>(a.x_self + (int64_t)row * a.ld_self) + vi));
                     if (a.bias) add4(r, __ldg(reinterpret_cast<const float4*>(a.bias) + vi));
+                    if (a.r1_s) fma4(r, __ldg(a.r1_s + row), __ldg(reinterpret_cast<const float4*>(a.r1_v) + vi));
+                    if (a.r2_s) fma4(r, __ldg(a.r2_s + row), __ldg(reinterpret_cast<const float4*>(a.r2_v) + vi));
                     reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[vi] = r;
                 }
             }
@@ -265,6 +273,8 @@ __global__ void __launch_bounds__(kMpThreads) spmm_mp_fixup_kernel(MpArgs a) {
         if (a.x_self)
             fma4(r, a.self_scale, __ldg(reinterpret_cast<const float4*>(a.x_self + (int64_t)r0 * a.ld_self) + vi));
         if (a.bias) add4(r, __ldg(reinterpret_cast<const float4*>(a.bias) + vi));
+        if (a.r1_s) fma4(r, __ldg(a.r1_s + r0), __ldg(reinterpret_cast<const float4*>(a.r1_v) + vi));
+        if (a.r2_s) fma4(r, __ldg(a.r2_s + r0), __ldg(reinterpret_cast<const float4*>(a.r2_v) + vi));
         reinterpret_cast<float4*>(a.out + (int64_t)r0 * a.ldo)[vi] = r;
     }
 }
@@ -364,15 +374,17 @@ int gg_spmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slo
                    const int32_t* item_row, const int32_t* item_slot, int64_t items, const float* x,
                    int64_t ldx, float* out, int64_t ldo, int64_t num_rows, int64_t f, int reduce,
                    const float* x_self, int64_t ld_self, float self_scale, const float* bias,
+                   const float* r1_s, const float* r1_v, const float* r2_s, const float* r2_v,
                    void* workspace, size_t workspace_bytes, int stage_mode, gg_stream_t stream) {
     GG_REQUIRE(num_rows >= 0 && f >= 0 && items >= 0, "gg_spmm_mp_f32: negative size");
+    GG_REQUIRE((!r1_s || r1_v) && (!r2_s || r2_v), "gg_spmm_mp_f32: rank-1 term without its vector");
     GG_REQUIRE(reduce == GG_SUM || reduce == GG_MEAN, "gg_spmm_mp_f32: reduce=%d", reduce);
     if (num_rows == 0 || f == 0) return GG_OK;
     GG_REQUIRE(rowptr && item_row && item_slot && x && out && workspace, "gg_spmm_mp_f32: null pointer");
     GG_REQUIRE(items >= 1 && items < ((int64_t)1 << 31) - 1, "gg_spmm_mp_f32: items out of range");
     bool vec = (f % 4 == 0) && f <= 1024 && (ldx % 4 == 0) && (ldo % 4 == 0) && mp_aligned16(x) &&
                mp_aligned16(out) && (!x_self || (ld_self % 4 == 0 && mp_aligned16(x_self))) &&
-               (!bias || mp_aligned16(bias));
+               (!bias || mp_aligned16(bias)) && (!r1_v || mp_aligned16(r1_v)) && (!r2_v || mp_aligned16(r2_v));
     if (!vec) {
         set_error("gg_spmm_mp_f32: needs f %% 4 == 0, f <= 1024 and 16-byte aligned rows (use gg_spmm_f32)");
         return GG_ERR_UNSUPPORTED;
@@ -388,7 +400,7 @@ int gg_spmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slo
     float* head = c.take<float>((size_t)items * f);
     GG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
     MpArgs a{rowptr, nbr, w_slot, item_row, item_slot, (int)items, x, ldx, out, ldo, num_rows, (int)f,
-             reduce, x_self, ld_self, self_scale, bias, counter, carry, head};
+             reduce, x_self, ld_self, self_scale, bias, counter, carry, head, r1_s, r1_v, r2_s, r2_v};
     // TMA staging needs 16-byte aligned index / weight arrays; otherwise plain loads
     bool tma = stage_mode != 1 && mp_aligned16(nbr) && (!w_slot || mp_aligned16(w_slot));
     const int nvec = (int)(f / 4);

@@ -189,8 +189,11 @@ def id_count(ids, num_nodes):
 # --------------------------------------------------------------------------------------------
 # aggregation
 # --------------------------------------------------------------------------------------------
-def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None, out=None):
-    """out[i,:] = reduce_{s in segment i} w[s]*x[nbr[s],:] + self_scale*x_self[i,:] + bias."""
+def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None, out=None, rank1=None):
+    """out[i,:] = reduce_{s in segment i} w[s]*x[nbr[s],:] + self_scale*x_self[i,:] + bias.
+
+    ``rank1`` = (s1 [n], v1 [f], s2 [n], v2 [f]) adds s1[i]*v1 + s2[i]*v2 in the epilogue (merge-path
+    kernel only; used by the GAT backward)."""
     _need_cuda(x, w_slot, x_self, bias, csr.rowptr)
     x, ldx = _rows(x, "x")
     n, f = csr.num_nodes, x.size(1)
@@ -208,6 +211,9 @@ def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None
         # merge-path kernel for wide rows on graphs big enough to need balancing; one-warp-per-row
         # (with sub-warp groups for narrow features) otherwise
         algo = "mp" if (f % 4 == 0 and 64 < f <= 1024 and n + csr.num_slots >= 1 << 14) else "row"
+    if rank1 is not None:
+        algo = "mp"
+    r1 = [t.contiguous() if t is not None else None for t in (rank1 or (None, None, None, None))]
     if algo == "mp" and f % 4 == 0 and f <= 1024 and n > 0:
         item_row, item_slot, items = csr.plan
         L = lib()
@@ -215,9 +221,12 @@ def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         check(L.gg_spmm_mp_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(item_row), _ptr(item_slot),
                                items, _ptr(x), ldx, _ptr(out), ldo, n, f, reduce, _ptr(x_self), ld_self,
-                               float(self_scale), _ptr(bias), _ptr(ws), ws_bytes,
-                               1 if SPMM_STAGE == "ldg" else 0, _stream()), "gg_spmm_mp_f32")
+                               float(self_scale), _ptr(bias), _ptr(r1[0]), _ptr(r1[1]), _ptr(r1[2]), _ptr(r1[3]),
+                               _ptr(ws), ws_bytes, 1 if SPMM_STAGE == "ldg" else 0, _stream()),
+              "gg_spmm_mp_f32")
         return out
+    if rank1 is not None:
+        raise ValueError("rank-1 epilogue terms need the merge-path kernel (f % 4 == 0, f <= 1024)")
     check(lib().gg_spmm_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(x), ldx, _ptr(out), ldo,
                             n, f, reduce, _ptr(x_self), ld_self, float(self_scale), _ptr(bias),
                             _stream()), "gg_spmm_f32")
@@ -356,6 +365,15 @@ def _f32(shape, dev):
     return torch.empty(max(n, 1), dtype=torch.float32, device=dev)[:n].view(*shape)
 
 
+GAT_ALGO = _os.environ.get("GG_GAT_ALGO", "auto")   # auto | mp (split passes on merge-path kernels) | row
+
+
+def _gat_use_mp(csr, f, heads):
+    if heads != 1 or f % 4 != 0 or f > 1024 or GAT_ALGO == "row":
+        return False
+    return GAT_ALGO == "mp" or csr.num_nodes + csr.num_slots >= 1 << 14
+
+
 def gat_forward(csr, h, att, heads, slope, bias):
     """-> out [n, heads*c], alpha [E', heads], a_tgt, a_src [n, heads]."""
     _need_cuda(h, att, bias)
@@ -368,6 +386,11 @@ def gat_forward(csr, h, att, heads, slope, bias):
     check(L.gg_gat_scores_f32(_ptr(h), ldh, _ptr(att), n, heads, c, _ptr(a_tgt), _ptr(a_src), _stream()),
           "gg_gat_scores_f32")
     alpha = _f32((csr.num_slots, heads), h.device)
+    if _gat_use_mp(csr, f, heads):
+        check(L.gg_gat_alpha_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(a_tgt), _ptr(a_src), n, float(slope),
+                                 _ptr(alpha), _stream()), "gg_gat_alpha_f32")
+        out = spmm(csr, h, alpha.view(-1), SUM, None, 0.0, bias)
+        return out, alpha, a_tgt, a_src
     out = torch.empty((n, f), dtype=torch.float32, device=h.device)
     if bias is not None:
         bias = bias.contiguous()
@@ -389,6 +412,27 @@ def gat_backward(csr, csc, csc2csr, h, att, heads, slope, bias, alpha, a_tgt, a_
     dz = _f32((csr.num_slots, heads), dev)
     da_tgt, da_src = _f32((n, heads), dev), _f32((n, heads), dev)
     L = lib()
+    if _gat_use_mp(csr, f, heads):
+        item_row, item_slot, items = csr.plan
+        dalpha = _f32((csr.num_slots,), dev)
+        counter = torch.empty(64, dtype=torch.int32, device=dev)
+        check(L.gg_gat_sddmm_mp_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(item_row), _ptr(item_slot), items,
+                                    _ptr(h), ldh, _ptr(g), ldg, n, f, _ptr(dalpha), _ptr(counter), _stream()),
+              "gg_gat_sddmm_mp_f32")
+        check(L.gg_gat_dz_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(a_tgt), _ptr(a_src), _ptr(alpha), _ptr(dalpha),
+                              n, float(slope), _ptr(dz), _ptr(da_tgt), _stream()), "gg_gat_dz_f32")
+        alpha_t = _f32((csc.num_slots,), dev)
+        check(L.gg_gat_csc_gather_f32(_ptr(csc.rowptr), _ptr(csc2csr), _ptr(alpha), _ptr(dz), n, _ptr(alpha_t),
+                                      _ptr(da_src), _stream()), "gg_gat_csc_gather_f32")
+        # dH = A_alpha^T g + da_src att_src + da_tgt att_tgt  (att = [a_tgt half | a_src half])
+        dh = spmm(csc, g, alpha_t, SUM, None, 0.0, None,
+                  rank1=(da_src.view(-1), att[0, c:], da_tgt.view(-1), att[0, :c]))
+        datt = torch.empty((heads, 2 * c), dtype=torch.float32, device=dev)
+        ws_bytes = int(L.gg_gat_att_grad_workspace_bytes(n, heads, c))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(L.gg_gat_att_grad_f32(_ptr(h), ldh, _ptr(da_tgt), _ptr(da_src), n, heads, c, _ptr(datt), _ptr(ws),
+                                    ws_bytes, _stream()), "gg_gat_att_grad_f32")
+        return dh, datt
     check(L.gg_gat_bwd_edge_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(h), ldh, _ptr(a_tgt), _ptr(a_src),
                                 _ptr(alpha), _ptr(g), ldg, _ptr(out), ldo, _ptr(bias), n, heads, c,
                                 float(slope), _ptr(dz), _ptr(da_tgt), _stream()), "gg_gat_bwd_edge_f32")

@@ -157,7 +157,8 @@ int gg_spmm_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, 
  *   gg_spmm_plan_build -> item_row[items+1], item_slot[items+1]
  * gg_spmm_mp_f32 has the semantics of gg_spmm_f32; it needs f % 4 == 0, f <= 1024, 16-byte aligned rows
  * (GG_ERR_UNSUPPORTED otherwise) and a workspace of gg_spmm_mp_workspace_bytes(items, f).
- * stage_mode: 0 = cp.async.bulk staging, 1 = plain loads.  Same fixed summation order per row. */
+ * stage_mode: 0 = cp.async.bulk staging, 1 = plain loads.  Same fixed summation order per row.
+ * Optional rank-1 epilogue terms (nullable): out[row,:] += r1_s[row]*r1_v[:] + r2_s[row]*r2_v[:]. */
 int gg_spmm_plan_units(int64_t num_rows, int64_t num_slots);
 int64_t gg_spmm_plan_items(int64_t num_rows, int64_t num_slots, int units);
 int gg_spmm_plan_build(const int32_t* rowptr, int64_t num_rows, int64_t num_slots, int units,
@@ -167,6 +168,7 @@ int gg_spmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slo
                    const int32_t* item_row, const int32_t* item_slot, int64_t items, const float* x,
                    int64_t ldx, float* out, int64_t ldo, int64_t num_rows, int64_t f, int reduce,
                    const float* x_self, int64_t ld_self, float self_scale, const float* bias,
+                   const float* r1_s, const float* r1_v, const float* r2_s, const float* r2_v,
                    void* workspace, size_t workspace_bytes, int stage_mode, gg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -306,6 +308,24 @@ int gg_egonet_fill(const int32_t* rowptr, const int32_t* nbr, int64_t n, int rad
                    int max_graph_nodes, const uint32_t* ego_ptr, const uint32_t* edge_ptr,
                    const int64_t* out_node_ptr, int64_t total_edges, int64_t* orig_id,
                    int64_t* edge_index_out, gg_stream_t stream);
+
+/* GAT at scale (heads = 1): the same layer split into light per-slot passes and heavy feature-row passes
+ * that run on the merge-path kernels (csrc/gat_mp.cu):
+ *   forward   gg_gat_alpha_f32 (alpha per slot)  ->  gg_spmm_mp_f32 with w_slot = alpha (+ bias)
+ *   backward  gg_gat_sddmm_mp_f32 (dalpha[s] = <g_i, h_j>, merge-path plan of the CSR layout; `counter` is
+ *             one int32 of scratch)  ->  gg_gat_dz_f32 (dz, da_tgt)  ->  gg_gat_csc_gather_f32 (alpha in CSC
+ *             order, da_src)  ->  gg_spmm_mp_f32 on the CSC layout with the rank-1 terms
+ *             da_src*att_src + da_tgt*att_tgt  ->  gg_gat_att_grad_f32. */
+int gg_gat_alpha_f32(const int32_t* rowptr, const int32_t* nbr, const float* a_tgt, const float* a_src,
+                     int64_t n, float slope, float* alpha, gg_stream_t stream);
+int gg_gat_sddmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const int32_t* item_row,
+                        const int32_t* item_slot, int64_t items, const float* h, int64_t ldh, const float* g,
+                        int64_t ldg, int64_t n, int64_t f, float* dalpha, int32_t* counter, gg_stream_t stream);
+int gg_gat_dz_f32(const int32_t* rowptr, const int32_t* nbr, const float* a_tgt, const float* a_src,
+                  const float* alpha, const float* dalpha, int64_t n, float slope, float* dz, float* da_tgt,
+                  gg_stream_t stream);
+int gg_gat_csc_gather_f32(const int32_t* rowptr_t, const int32_t* slot_map, const float* alpha, const float* dz,
+                          int64_t n, float* alpha_t, float* da_src, gg_stream_t stream);
 
 /* Row gather / scatter-add / ReLU gradient used by the GIN-ID branch (ref: idconv.py:372-375):
  *   gather:      out[r,:]      = x[id[r],:]

@@ -456,11 +456,11 @@ __global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_kernel(TcArgs g) {
 //   converters  thread c reads COLUMN c of the raw A slab (16 values, conflict-free), packs 4 consecutive
 //               rows per 16-byte k-chunk, splits hi/lo, stores the K-major operand slab; same for G
 //   issuer      six tcgen05.mma per slab
-// A split covers kTnRowsPerSplit = 512 rows so that the truncating tensor-core accumulation stays
-// below 3e-6 relative; several splits run back to back in one CTA, their tiles are added in fp32
+// A split covers kTnRowsPerSplit = 256 rows so that the truncating tensor-core accumulation stays
+// below 1.6e-6 relative; several splits run back to back in one CTA, their tiles are added in fp32
 // (round to nearest) in the CTA's shared accumulator, and the per-CTA partials are reduced in fp64.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTnRowsPerSplit = 512;
+constexpr int kTnRowsPerSplit = 256;
 constexpr int TN_RAW_SLOTS = 2, TN_STAGES = 2;
 constexpr int TN_RAW_BYTES = 2 * TC_BK * TC_BM * 4;                   // raw A (16 x 128) + raw G (16 x 128)
 constexpr int TN_OFF_OP = TN_RAW_SLOTS * TN_RAW_BYTES;                // 32 KB
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_tn_kernel(TnTcArgs g) {
 #pragma unroll
     for (int e = 0; e < 64; ++e) racc[e] = 0.f;
 
-    // At the end of every 512-row segment warps 0-7 drain the TMEM tile into racc (each warp its lane
+    // At the end of every 256-row segment warps 0-7 drain the TMEM tile into racc (each warp its lane
     // quarter, loaders the low / converters the high 64 columns) and release the accumulator.  Both
     // roles have finished their part of the segment when they get here, so nothing can deadlock.
     auto drain = [&](int sgi) {
@@ -704,9 +704,9 @@ using namespace gg;
 
 // The tensor core accumulates with truncation: the result is biased towards zero by ~6e-9 * K relative
 // (measured, scratch/tc_err_probe.py).  To stay inside 1e-5 for any K the reduction is cut into launches
-// of at most kTcMaxKPerLaunch k; each launch's partial tile is added to `out` in fp32 (round to nearest)
-// by the next launch's epilogue.  GNN hidden sizes (K <= 512) take one launch.
-constexpr int kTcMaxKPerLaunch = 512;
+// of at most kTcMaxKPerLaunch = 256 k (bias <= 1.6e-6); each launch's partial tile is added to `out` in
+// fp32 (round to nearest) by the next launch's epilogue.  GNN hidden sizes (K <= 256) take one launch.
+constexpr int kTcMaxKPerLaunch = 256;
 
 struct TcPiece {  // a sub-range of a caller segment
     int seg;

@@ -296,7 +296,7 @@ def gemm_tn(a, g, row_index=None):
         assert g.size(0) == n
     L = lib()
     out = torch.empty((k, f), dtype=torch.float32, device=a.device)
-    if GEMM_MODE == "tc" and n >= 512:   # below one 512-row split the CUDA-core kernel is as fast
+    if GEMM_MODE == "tc" and n >= 512:   # below a couple of 256-row segments the CUDA-core kernel is as fast
         ws_bytes = int(L.gg_gemm_tn_tc_workspace_bytes(n, k, f))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
         check(L.gg_gemm_tn_tc_f32(_ptr(a), lda, _ptr(row_index), _ptr(g), ldg, n, k, f, _ptr(out), max(f, 1),

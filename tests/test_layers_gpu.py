@@ -97,7 +97,8 @@ def test_layers_against_oracle(cuda, name, shape):
         pytest.skip(f'{name} not built yet')
     reset_cfg()
     n, fin, fout = shape
-    torch.manual_seed(hash((name, shape)) % 1000)
+    import zlib
+    torch.manual_seed(zlib.crc32(repr((name, shape)).encode()) % 1000)   # stable across processes
     ei = powerlaw_graph(n, n, 8) if n >= 2708 else random_graph(n, n, 6 * n, loops=n // 20, dups=n // 10)
     g = torch.Generator().manual_seed(n + fin)
     x = torch.randn(n, fin, generator=g)

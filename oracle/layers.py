@@ -64,9 +64,21 @@ def sageconv(x, edge_index, w_l, b_l, w_r):
     return out + F.linear(x, w_r)
 
 
-def ginconv(x, edge_index, w1, b1, w2, b2, eps=0.0):
+def _gin_mlp(z, p, gate=None, tap=None, key='pre'):
+    """Linear -> ReLU -> Linear (ref: layer.py:168-169, idconv.py:432-435).  ``gate`` (a 0/1 tensor)
+    replaces the ReLU's own gate so that gradients can be compared under the gates the implementation
+    under test actually took (a pre-activation within rounding of zero may gate either way); ``tap``
+    collects the pre-activation for the caller's tolerance check."""
+    pre = F.linear(z, p[0], p[1])
+    if tap is not None:
+        tap[key] = pre.detach()
+    h = F.relu(pre) if gate is None else pre * gate.to(pre.dtype)
+    return F.linear(h, p[2], p[3])
+
+
+def ginconv(x, edge_index, w1, b1, w2, b2, eps=0.0, gate=None, tap=None):
     z = (1 + eps) * x + _prop(edge_index, x, x.size(0), 'add')
-    return F.linear(F.relu(F.linear(z, w1, b1)), w2, b2)
+    return _gin_mlp(z, (w1, b1, w2, b2), gate, tap)
 
 
 def _gat_core(h, edge_index, att, heads, out_channels, negative_slope, bias, concat=True):
@@ -131,11 +143,11 @@ def gat_idconv(x, edge_index, ids, weight, weight_id, att, bias=None, heads=1, n
                      negative_slope, bias)
 
 
-def gin_idconv(x, edge_index, ids, p, p_id, eps=0.0):
+def gin_idconv(x, edge_index, ids, p, p_id, eps=0.0, gate=None, gate_id=None, tap=None):
     """ref: idconv.py:367-376; p / p_id = (w1, b1, w2, b2) of nn / nn_id."""
     ei, _ = U.remove_self_loops(edge_index)
     z = (1 + eps) * x + _prop(ei, x, x.size(0), 'add')
-    out = F.linear(F.relu(F.linear(z, p[0], p[1])), p[2], p[3])
+    out = _gin_mlp(z, p, gate, tap, 'pre')
     z_id = z.index_select(0, ids)
-    out_id = F.linear(F.relu(F.linear(z_id, p_id[0], p_id[1])), p_id[2], p_id[3])
+    out_id = _gin_mlp(z_id, p_id, gate_id, tap, 'pre_id')
     return out.index_add(0, ids, out_id)

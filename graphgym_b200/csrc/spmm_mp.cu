@@ -110,11 +110,15 @@ __device__ __forceinline__ uint32_t stage_begin(T* tile, const T* __restrict__ g
     return bytes;
 }
 
-template <int VPL> struct MpUnroll { static constexpr int value = VPL == 1 ? 8 : (VPL == 2 ? 4 : 2); };
+// U = independent feature-row gathers per lane and batch.  DEEP doubles it for the 128-wide case: 16 x 512 B
+// in flight per warp at 3 CTAs/SM (24 warps) instead of 8 x 512 B at 4 CTAs/SM (32 warps).
+template <int VPL, bool DEEP> struct MpUnroll {
+    static constexpr int value = VPL == 1 ? (DEEP ? 16 : 8) : (VPL == 2 ? (DEEP ? 8 : 4) : 2);
+};
 
-template <int VPL, bool WEIGHTED, bool TMA>
-__global__ void __launch_bounds__(kMpThreads, VPL == 1 ? 4 : 2) spmm_mp_kernel(MpArgs a) {
-    constexpr int U = MpUnroll<VPL>::value;
+template <int VPL, bool WEIGHTED, bool TMA, bool DEEP, bool RANK1>
+__global__ void __launch_bounds__(kMpThreads, VPL == 1 ? (DEEP ? 3 : 4) : 2) spmm_mp_kernel(MpArgs a) {
+    constexpr int U = MpUnroll<VPL, DEEP>::value;
     __shared__ __align__(16) int32_t s_nbr_all[kMpWarps][kMpTile];
     __shared__ __align__(16) float s_w_all[WEIGHTED ? kMpWarps : 1][WEIGHTED ? kMpTile : 4];
     __shared__ __align__(16) int32_t s_rp_all[kMpWarps][kMpTile];
@@ -195,8 +199,10 @@ __global__ void __launch_bounds__(kMpThreads, VPL == 1 ? 4 : 2) spmm_mp_kernel(M
                         fma4(r, a.self_scale,
                              __ldg(reinterpret_cast<const float4*>(a.x_self + (int64_t)row * a.ld_self) + vi));
                     if (a.bias) add4(r, __ldg(reinterpret_cast<const float4*>(a.bias) + vi));
-                    if (a.r1_s) fma4(r, __ldg(a.r1_s + row), __ldg(reinterpret_cast<const float4*>(a.r1_v) + vi));
-                    if (a.r2_s) fma4(r, __ldg(a.r2_s + row), __ldg(reinterpret_cast<const float4*>(a.r2_v) + vi));
+                    if (RANK1) {
+                        if (a.r1_s) fma4(r, __ldg(a.r1_s + row), __ldg(reinterpret_cast<const float4*>(a.r1_v) + vi));
+                        if (a.r2_s) fma4(r, __ldg(a.r2_s + row), __ldg(reinterpret_cast<const float4*>(a.r2_v) + vi));
+                    }
                     reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[vi] = r;
                 }
             }
@@ -301,28 +307,36 @@ __global__ void __launch_bounds__(256) spmm_plan_kernel(const int32_t* __restric
 
 static inline bool mp_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-template <int VPL, bool WEIGHTED, bool TMA>
-static void prefer_smem() {
-    static bool done = false;  // 4 CTAs x 47 KB of tiles per SM: ask for the large carve-out once
+template <int VPL, bool WEIGHTED, bool TMA, bool DEEP, bool RANK1 = false>
+static void launch_one(const MpArgs& a, int grid, cudaStream_t st) {
+    static bool done = false;  // up to 4 CTAs x 47 KB of tiles per SM: ask for the large carve-out once
     if (!done) {
-        cudaFuncSetAttribute(spmm_mp_kernel<VPL, WEIGHTED, TMA>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(spmm_mp_kernel<VPL, WEIGHTED, TMA, DEEP, RANK1>,
+                             cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         done = true;
     }
+    spmm_mp_kernel<VPL, WEIGHTED, TMA, DEEP, RANK1><<<grid, kMpThreads, 0, st>>>(a);
 }
 
 template <int VPL>
-static void launch_mp(const MpArgs& a, bool tma, int grid, cudaStream_t st) {
-    prefer_smem<VPL, true, true>();
-    prefer_smem<VPL, true, false>();
-    prefer_smem<VPL, false, true>();
-    prefer_smem<VPL, false, false>();
-    if (a.w) {
-        if (tma) spmm_mp_kernel<VPL, true, true><<<grid, kMpThreads, 0, st>>>(a);
-        else spmm_mp_kernel<VPL, true, false><<<grid, kMpThreads, 0, st>>>(a);
+static void launch_mp(const MpArgs& a, bool tma, bool deep, int grid, cudaStream_t st) {
+    if (a.r1_s || a.r2_s) {  // rank-1 epilogue terms: a separate instantiation keeps the common kernel lean
+        if (a.w) launch_one<VPL, true, false, false, true>(a, grid, st);
+        else launch_one<VPL, false, false, false, true>(a, grid, st);
+    } else if (deep && VPL <= 2) {
+        if (a.w) {
+            if (tma) launch_one<VPL, true, true, true>(a, grid, st);
+            else launch_one<VPL, true, false, true>(a, grid, st);
+        } else {
+            if (tma) launch_one<VPL, false, true, true>(a, grid, st);
+            else launch_one<VPL, false, false, true>(a, grid, st);
+        }
+    } else if (a.w) {
+        if (tma) launch_one<VPL, true, true, false>(a, grid, st);
+        else launch_one<VPL, true, false, false>(a, grid, st);
     } else {
-        if (tma) spmm_mp_kernel<VPL, false, true><<<grid, kMpThreads, 0, st>>>(a);
-        else spmm_mp_kernel<VPL, false, false><<<grid, kMpThreads, 0, st>>>(a);
+        if (tma) launch_one<VPL, false, true, false>(a, grid, st);
+        else launch_one<VPL, false, false, false>(a, grid, st);
     }
     count_launch();
     spmm_mp_fixup_kernel<VPL><<<(int)ceil_div(a.items, kMpWarps), kMpThreads, 0, st>>>(a);
@@ -402,15 +416,17 @@ int gg_spmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slo
     MpArgs a{rowptr, nbr, w_slot, item_row, item_slot, (int)items, x, ldx, out, ldo, num_rows, (int)f,
              reduce, x_self, ld_self, self_scale, bias, counter, carry, head, r1_s, r1_v, r2_s, r2_v};
     // TMA staging needs 16-byte aligned index / weight arrays; otherwise plain loads
-    bool tma = stage_mode != 1 && mp_aligned16(nbr) && (!w_slot || mp_aligned16(w_slot));
+    // stage_mode bit 0: 0 = cp.async.bulk staging, 1 = plain loads; bit 1: deep gather batches
+    bool tma = (stage_mode & 1) == 0 && mp_aligned16(nbr) && (!w_slot || mp_aligned16(w_slot));
+    bool deep = (stage_mode & 2) != 0;
     const int nvec = (int)(f / 4);
-    int per_sm = nvec <= 32 ? 4 : 2;
+    int per_sm = nvec <= 32 ? (deep ? 3 : 4) : 2;
     int grid = (int)ceil_div(items, kMpWarps);
     if (grid > kNumSMs * per_sm) grid = kNumSMs * per_sm;
-    if (nvec <= 32) launch_mp<1>(a, tma, grid, st);
-    else if (nvec <= 64) launch_mp<2>(a, tma, grid, st);
-    else if (nvec <= 128) launch_mp<4>(a, tma, grid, st);
-    else launch_mp<8>(a, tma, grid, st);
+    if (nvec <= 32) launch_mp<1>(a, tma, deep, grid, st);
+    else if (nvec <= 64) launch_mp<2>(a, tma, deep, grid, st);
+    else if (nvec <= 128) launch_mp<4>(a, tma, deep, grid, st);
+    else launch_mp<8>(a, tma, deep, grid, st);
     GG_CUDA(cudaPeekAtLastError());
     return GG_OK;
 }

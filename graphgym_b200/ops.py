@@ -20,6 +20,7 @@ ACT_NONE, ACT_RELU = 0, 1
 import os as _os
 SPMM_ALGO = _os.environ.get("GG_SPMM_ALGO", "auto")    # auto | mp | row
 SPMM_STAGE = _os.environ.get("GG_SPMM_STAGE", "tma")   # tma | ldg
+SPMM_DEEP = _os.environ.get("GG_SPMM_DEEP", "0") == "1"  # 16 instead of 8 gathers per lane and batch
 GEMM_MODE = _os.environ.get("GG_GEMM", "tc")           # tc (tcgen05 3xTF32) | simt (fp32 CUDA cores)
 
 
@@ -222,7 +223,7 @@ def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None
         check(L.gg_spmm_mp_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(item_row), _ptr(item_slot),
                                items, _ptr(x), ldx, _ptr(out), ldo, n, f, reduce, _ptr(x_self), ld_self,
                                float(self_scale), _ptr(bias), _ptr(r1[0]), _ptr(r1[1]), _ptr(r1[2]), _ptr(r1[3]),
-                               _ptr(ws), ws_bytes, 1 if SPMM_STAGE == "ldg" else 0, _stream()),
+                               _ptr(ws), ws_bytes, (1 if SPMM_STAGE == "ldg" else 0) | (2 if SPMM_DEEP else 0), _stream()),
               "gg_spmm_mp_f32")
         return out
     if rank1 is not None:

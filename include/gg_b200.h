@@ -157,7 +157,8 @@ int gg_spmm_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, 
  *   gg_spmm_plan_build -> item_row[items+1], item_slot[items+1]
  * gg_spmm_mp_f32 has the semantics of gg_spmm_f32; it needs f % 4 == 0, f <= 1024, 16-byte aligned rows
  * (GG_ERR_UNSUPPORTED otherwise) and a workspace of gg_spmm_mp_workspace_bytes(items, f).
- * stage_mode: 0 = cp.async.bulk staging, 1 = plain loads.  Same fixed summation order per row.
+ * stage_mode: bit 0 = plain loads instead of cp.async.bulk staging, bit 1 = deep (16-wide) gather batches.
+ * Same fixed summation order per row in every mode.
  * Optional rank-1 epilogue terms (nullable): out[row,:] += r1_s[row]*r1_v[:] + r2_s[row]*r2_v[:]. */
 int gg_spmm_plan_units(int64_t num_rows, int64_t num_slots);
 int64_t gg_spmm_plan_items(int64_t num_rows, int64_t num_slots, int units);

@@ -36,8 +36,8 @@ SIGNATURES = {
     "gg_layout_build_workspace_bytes": (c_size, [c_i64, c_i64, c_int]),
     "gg_layout_build": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                 c_size, c_ptr]),
-    "gg_layout_build_range": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_i64, c_ptr, c_ptr, c_ptr,
-                                      c_ptr, c_ptr, c_size, c_ptr]),
+    "gg_layout_build_range": (c_int, [c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_i64, c_i64, c_i64, c_ptr,
+                                      c_ptr, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "gg_sort_pairs_workspace_bytes": (c_size, [c_i64]),
     "gg_sort_pairs_u32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_int, c_ptr, c_size, c_ptr]),
     "gg_layout_slot_map": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr]),

@@ -38,8 +38,8 @@ static inline int grid_for(int64_t n, int per_thread = 1) {
 
 __global__ void __launch_bounds__(kThreads)
     layout_prep_kernel(const int64_t* __restrict__ ei, int64_t E, int64_t N, int removes, int adds,
-                       int by_source, int64_t range_lo, int64_t range_hi, uint32_t* __restrict__ keys,
-                       int32_t* __restrict__ bad_count) {
+                       int by_source, int64_t range_lo, int64_t range_hi, int64_t nbr_lo, int64_t nbr_hi,
+                       uint32_t* __restrict__ keys, int32_t* __restrict__ bad_count) {
     int64_t total = E + (adds ? N : 0);
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (int64_t)gridDim.x * blockDim.x) {
@@ -49,12 +49,15 @@ __global__ void __launch_bounds__(kThreads)
             bool bad = s < 0 || s >= N || t < 0 || t >= N;
             if (bad) atomicAdd(bad_count, 1);
             int64_t k = by_source ? s : t;
-            // row-partitioned layouts keep only the groups this rank owns
-            bool drop = bad || (removes && s == t) || k < range_lo || k >= range_hi;
+            int64_t o = by_source ? t : s;  // the other endpoint (what nbr[] will hold)
+            // row-partitioned layouts keep only the groups this rank owns, halo-pipelined ones additionally
+            // only the neighbours that live in one peer's block
+            bool drop = bad || (removes && s == t) || k < range_lo || k >= range_hi || o < nbr_lo || o >= nbr_hi;
             key = drop ? (uint32_t)N : (uint32_t)k;
         } else {
             int64_t i = e - E;
-            key = (i >= range_lo && i < range_hi) ? (uint32_t)i : (uint32_t)N;
+            bool keep = i >= range_lo && i < range_hi && i >= nbr_lo && i < nbr_hi;
+            key = keep ? (uint32_t)i : (uint32_t)N;
         }
         keys[e] = key;
     }
@@ -211,15 +214,18 @@ size_t gg_layout_build_workspace_bytes(int64_t E, int64_t N, int policy) {
 int gg_layout_build(const int64_t* edge_index, int64_t E, int64_t N, int policy, int group_by,
                     int32_t* rowptr, int32_t* nbr, int32_t* perm, int32_t* rowid, void* workspace,
                     size_t workspace_bytes, gg_stream_t stream) {
-    return gg_layout_build_range(edge_index, E, N, policy, group_by, 0, N, rowptr, nbr, perm, rowid,
+    return gg_layout_build_range(edge_index, E, N, policy, group_by, 0, N, 0, N, rowptr, nbr, perm, rowid,
                                  workspace, workspace_bytes, stream);
 }
 
 int gg_layout_build_range(const int64_t* edge_index, int64_t E, int64_t N, int policy, int group_by,
-                          int64_t range_begin, int64_t range_end, int32_t* rowptr, int32_t* nbr,
-                          int32_t* perm, int32_t* rowid, void* workspace, size_t workspace_bytes,
-                          gg_stream_t stream) {
+                          int64_t range_begin, int64_t range_end, int64_t nbr_begin, int64_t nbr_end,
+                          int32_t* rowptr, int32_t* nbr, int32_t* perm, int32_t* rowid, void* workspace,
+                          size_t workspace_bytes, gg_stream_t stream) {
     GG_REQUIRE(E >= 0 && N >= 0, "gg_layout_build: negative size");
+    GG_REQUIRE(nbr_begin >= 0 && nbr_begin <= nbr_end && nbr_end <= N,
+               "gg_layout_build_range: bad neighbour range [%lld, %lld) of %lld", (long long)nbr_begin,
+               (long long)nbr_end, (long long)N);
     GG_REQUIRE(range_begin >= 0 && range_begin <= range_end && range_end <= N,
                "gg_layout_build_range: bad range [%lld, %lld) of %lld", (long long)range_begin,
                (long long)range_end, (long long)N);
@@ -254,7 +260,7 @@ int gg_layout_build_range(const int64_t* edge_index, int64_t E, int64_t N, int p
     layout_prep_kernel<<<grid_for(M, 4), kThreads, 0, st>>>(edge_index, E, N, policy_removes(policy),
                                                            policy_adds(policy),
                                                            group_by == GG_BY_SOURCE, range_begin,
-                                                           range_end, keys, bad);
+                                                           range_end, nbr_begin, nbr_end, keys, bad);
     GG_LAUNCHED();
     int rc = gg_sort_pairs_u32(keys, nullptr, sorted, reinterpret_cast<uint32_t*>(perm), M,
                                bits_for(N), sort_ws, gg_sort_pairs_workspace_bytes(M), stream);

@@ -84,12 +84,13 @@ class Csr:
         return self._plan
 
 
-def layout_build(edge_index, num_nodes, policy=LOOPS_KEEP, group_by=BY_TARGET, row_range=None):
+def layout_build(edge_index, num_nodes, policy=LOOPS_KEEP, group_by=BY_TARGET, row_range=None, nbr_range=None):
     """COO ``edge_index[2,E]`` (int64, row 0 = source, row 1 = target) -> Csr.  One host sync to
     read E' (self-loop removal makes it data dependent).
 
     ``row_range=(lo, hi)``: rank-local layout of a row partition — only groups in [lo, hi) are kept,
-    the returned Csr has hi-lo rows (rowptr is the [lo, hi] slice) and GLOBAL ids in ``nbr`` / ``rowid``."""
+    the returned Csr has hi-lo rows (rowptr is the [lo, hi] slice) and GLOBAL ids in ``nbr`` / ``rowid``.
+    ``nbr_range=(lo, hi)`` additionally keeps only slots whose neighbour lies in that block."""
     _need_cuda(edge_index)
     if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise ValueError(f"edge_index must be int64 [2,E], got {tuple(edge_index.shape)} {edge_index.dtype}")
@@ -105,7 +106,8 @@ def layout_build(edge_index, num_nodes, policy=LOOPS_KEEP, group_by=BY_TARGET, r
     ws_bytes = int(L.gg_layout_build_workspace_bytes(E, N, policy))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     lo, hi = (0, N) if row_range is None else (int(row_range[0]), int(row_range[1]))
-    check(L.gg_layout_build_range(_ptr(ei), E, N, policy, group_by, lo, hi, _ptr(rowptr), _ptr(nbr),
+    nlo, nhi = (0, N) if nbr_range is None else (int(nbr_range[0]), int(nbr_range[1]))
+    check(L.gg_layout_build_range(_ptr(ei), E, N, policy, group_by, lo, hi, nlo, nhi, _ptr(rowptr), _ptr(nbr),
                                   _ptr(perm), _ptr(rowid), _ptr(ws), ws_bytes, _stream()),
           "gg_layout_build_range")
     bad = int(ws[:4].view(torch.int32).item())
@@ -190,14 +192,17 @@ def id_count(ids, num_nodes):
 # --------------------------------------------------------------------------------------------
 # aggregation
 # --------------------------------------------------------------------------------------------
-def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None, out=None, rank1=None):
+def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None, out=None, rank1=None,
+         x_row_base=0):
     """out[i,:] = reduce_{s in segment i} w[s]*x[nbr[s],:] + self_scale*x_self[i,:] + bias.
 
     ``rank1`` = (s1 [n], v1 [f], s2 [n], v2 [f]) adds s1[i]*v1 + s2[i]*v2 in the epilogue (merge-path
-    kernel only; used by the GAT backward)."""
+    kernel only; used by the GAT backward).  ``x_row_base``: ``x`` holds rows [x_row_base, x_row_base +
+    x.size(0)) of the matrix the neighbour ids index (a peer's block in the halo pipeline)."""
     _need_cuda(x, w_slot, x_self, bias, csr.rowptr)
     x, ldx = _rows(x, "x")
     n, f = csr.num_nodes, x.size(1)
+    x_ptr = ctypes.c_void_p(x.data_ptr() - int(x_row_base) * ldx * 4)
     if out is None:
         out = torch.empty((n, f), dtype=torch.float32, device=x.device)
     out_t, ldo = _rows(out, "out")
@@ -221,14 +226,14 @@ def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None
         ws_bytes = int(L.gg_spmm_mp_workspace_bytes(items, f))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         check(L.gg_spmm_mp_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(item_row), _ptr(item_slot),
-                               items, _ptr(x), ldx, _ptr(out), ldo, n, f, reduce, _ptr(x_self), ld_self,
+                               items, x_ptr, ldx, _ptr(out), ldo, n, f, reduce, _ptr(x_self), ld_self,
                                float(self_scale), _ptr(bias), _ptr(r1[0]), _ptr(r1[1]), _ptr(r1[2]), _ptr(r1[3]),
                                _ptr(ws), ws_bytes, (1 if SPMM_STAGE == "ldg" else 0) | (2 if SPMM_DEEP else 0), _stream()),
               "gg_spmm_mp_f32")
         return out
     if rank1 is not None:
         raise ValueError("rank-1 epilogue terms need the merge-path kernel (f % 4 == 0, f <= 1024)")
-    check(lib().gg_spmm_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(x), ldx, _ptr(out), ldo,
+    check(lib().gg_spmm_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), x_ptr, ldx, _ptr(out), ldo,
                             n, f, reduce, _ptr(x_self), ld_self, float(self_scale), _ptr(bias),
                             _stream()), "gg_spmm_f32")
     return out

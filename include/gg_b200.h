@@ -87,11 +87,13 @@ int gg_layout_build(const int64_t* edge_index, int64_t num_edges, int64_t num_no
 
 /* Row-partitioned variant: only the groups in [range_begin, range_end) are kept (edges of
  * other groups and appended loops of other nodes are dropped); rowptr still has N+1 entries, so
- * rowptr + range_begin is the rank-local row pointer and nbr holds GLOBAL node ids. */
+ * rowptr + range_begin is the rank-local row pointer and nbr holds GLOBAL node ids.
+ * [nbr_begin, nbr_end) additionally keeps only the slots whose neighbour lies in that block (one peer's
+ * rows): the per-peer sub-layouts of the pipelined halo exchange.  Pass 0, num_nodes for no filter. */
 int gg_layout_build_range(const int64_t* edge_index, int64_t num_edges, int64_t num_nodes, int policy,
-                          int group_by, int64_t range_begin, int64_t range_end, int32_t* rowptr,
-                          int32_t* nbr, int32_t* perm, int32_t* rowid, void* workspace,
-                          size_t workspace_bytes, gg_stream_t stream);
+                          int group_by, int64_t range_begin, int64_t range_end, int64_t nbr_begin,
+                          int64_t nbr_end, int32_t* rowptr, int32_t* nbr, int32_t* perm, int32_t* rowid,
+                          void* workspace, size_t workspace_bytes, gg_stream_t stream);
 
 /* Stable LSD radix sort of (key,value) u32 pairs on keys < 2^key_bits (the engine under
  * gg_layout_build, exported for the ego-net and halo code). */

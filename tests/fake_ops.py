@@ -8,12 +8,13 @@ from graphgym_b200 import ops
 from oracle import layout as olayout
 
 
-def layout_build(edge_index, num_nodes, policy=0, group_by=0, row_range=None):
+def layout_build(edge_index, num_nodes, policy=0, group_by=0, row_range=None, nbr_range=None):
     n = int(num_nodes)
     lo, hi = (0, n) if row_range is None else row_range
+    nlo, nhi = (0, n) if nbr_range is None else nbr_range
     src, tgt, eid = olayout.edited_edges(edge_index.numpy(), n, policy)
     key, other = (tgt, src) if group_by == 0 else (src, tgt)
-    keep = (key >= lo) & (key < hi)
+    keep = (key >= lo) & (key < hi) & (other >= nlo) & (other < nhi)
     key, other, eid = key[keep], other[keep], eid[keep]
     order = np.argsort(key, kind='stable')
     rowptr = np.zeros(n + 1, dtype=np.int64)
@@ -38,10 +39,11 @@ def mean_weights(csr_t, deg):
     return inv[csr_t.nbr.long()]
 
 
-def spmm(csr, x, w_slot=None, reduce=0, x_self=None, self_scale=0.0, bias=None, out=None):
+def spmm(csr, x, w_slot=None, reduce=0, x_self=None, self_scale=0.0, bias=None, out=None, rank1=None,
+         x_row_base=0):
     rows = csr.num_nodes
     seg = torch.repeat_interleave(torch.arange(rows), (csr.rowptr[1:] - csr.rowptr[:-1]).long())
-    msg = x[csr.nbr.long()]
+    msg = x[csr.nbr.long() - int(x_row_base)]
     if w_slot is not None:
         msg = msg * w_slot.view(-1, 1)
     res = torch.zeros((rows, x.size(1)), dtype=x.dtype).index_add_(0, seg, msg)
@@ -51,6 +53,9 @@ def spmm(csr, x, w_slot=None, reduce=0, x_self=None, self_scale=0.0, bias=None, 
         res = res + self_scale * x_self
     if bias is not None:
         res = res + bias
+    if out is not None:
+        out.copy_(res)
+        return out
     return res
 
 

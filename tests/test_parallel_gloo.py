@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, ret):
+def _worker(rank, world, port, n, pipelined, ret):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -43,7 +43,7 @@ def _worker(rank, world, port, n, ret):
         layer = parallel.RowPartitionedGCN(fin, fout, bias=True)   # same seed on every rank
         with torch.no_grad():
             layer.model.bias.uniform_(-0.5, 0.5)
-        playout = parallel.PartitionedLayout(ei, n, ops.LOOPS_ADD_REMAINING, part)
+        playout = parallel.PartitionedLayout(ei, n, ops.LOOPS_ADD_REMAINING, part, pipelined=pipelined)
         xl = x[part.lo:part.hi].clone().requires_grad_(True)
         y = layer(xl, playout)
         y.backward(gy[part.lo:part.hi])
@@ -62,11 +62,12 @@ def _worker(rank, world, port, n, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('n', [40, 41])   # 41: the last rank's block is shorter -> padded all-gather
-def test_row_partitioned_gcn_world2(n):
+@pytest.mark.parametrize('pipelined', [False, True])   # one all-gather vs per-peer send/recv rounds
+@pytest.mark.parametrize('n', [40, 41])   # 41: the last rank's block is shorter -> padded exchange
+def test_row_partitioned_gcn_world2(n, pipelined):
     world = 2
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), n, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, pipelined, ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
 
 
@@ -79,3 +80,11 @@ def test_partition_bounds_cover_all_rows():
             assert spans[0].lo == 0 and spans[-1].hi == n
             assert all(a.hi == b.lo for a, b in zip(spans, spans[1:]))
             assert all(s.rows <= s.per for s in spans)
+
+
+def test_row_partitioned_gcn_world3_pipelined():
+    """three ranks: two exchange rounds with different peers per round"""
+    world = 3
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), 50, True, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, pipelined, ret):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -45,7 +45,7 @@ def _worker(rank, world, port, ret):
             ref.model.bias.uniform_(-0.5, 0.5)
             layer.model.bias.copy_(ref.model.bias)
         part = parallel.RowPartition(n, world, rank)
-        playout = parallel.PartitionedLayout(ei, n, ops.LOOPS_ADD_REMAINING, part)
+        playout = parallel.PartitionedLayout(ei, n, ops.LOOPS_ADD_REMAINING, part, pipelined=pipelined)
         xl = x[part.lo:part.hi].clone().requires_grad_(True)
         y = layer(xl, playout)
         y.backward(gy[part.lo:part.hi])
@@ -64,11 +64,12 @@ def _worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-def test_two_gpu_row_partition_matches_single_gpu():
+@pytest.mark.parametrize('pipelined', [False, True])
+def test_two_gpu_row_partition_matches_single_gpu(pipelined):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), pipelined, ret), nprocs=2, join=True)
     for r in range(2):
         ok, bitwise, errs = ret[r]
         assert ok, errs

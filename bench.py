@@ -266,7 +266,7 @@ def run_ours(args, spec, rank, world, dev):
         return bias_grad()
 
     t0 = time.time()
-    halo = os.environ.get('GG_HALO', 'pipelined')   # pipelined (per-peer send/recv rounds) | allgather
+    halo = os.environ.get('GG_HALO', 'allgather')   # allgather | pipelined (per-peer send/recv rounds, +10% at N<=4)
     mk_layout = lambda e: parallel.PartitionedLayout(e, n, policy, part, pipelined=(halo == 'pipelined'))
     warm_weights = lambda pl: pl.sub_weights('gcn_tgt') if pl.pipelined else pl.weights('gcn_tgt')
     if multi:

@@ -3,42 +3,42 @@
 // This is the integer engine under the COO -> CSR/CSC build (layout.cu).  "Bit-exact" for the
 // layout means the STABLE counting sort of the edited edge list, so no atomics decide
 // an output position anywhere in this file:
-//   * every warp owns a contiguous chunk of the input;
-//   * pass p: (1) per-warp digit histogram, (2) exclusive scan of the digit-major table
-//     counts[digit][warp] -> the first output slot of every (digit, warp) pair, (3) each warp
-//     replays its chunk in order, ranks equal digits inside a 32-key round with
-//     __match_any_sync (lower lane = earlier key) and bumps its private per-digit cursor.
+//   * every CTA owns a contiguous chunk of the input and walks it in tiles of 4096 pairs;
+//   * pass p: (1) per-CTA digit histogram, (2) exclusive scan of the digit-major table
+//     counts[digit][cta] -> the first output slot of every (digit, CTA) pair, (3) per tile the CTA ranks
+//     its keys stably — __match_any_sync inside a 32-key round (lower lane = earlier key), per-warp
+//     running counts, a cross-warp prefix per digit — sorts the tile by digit in SHARED memory and only
+//     then writes it out, so that every digit's run leaves as consecutive addresses (coalesced) instead
+//     of 4-byte scattered stores (the first version: 4.2 ms per pass at 64 M pairs, 3 % of HBM).
 // Traffic per pass: 4 B (hist) + 8 B read + 8 B written per pair; HBM-bound integer work.
 #include "common.cuh"
 
 namespace gg {
 
 constexpr int kRadixBits = 8;
-constexpr int kRadix = 1 << kRadixBits;
+constexpr int kRadix = 1 << kRadixBits;   // == kSortThreads: one thread per digit in the prefix phases
 constexpr int kSortWarps = 8;  // warps per CTA
 constexpr int kSortThreads = kSortWarps * 32;
-constexpr int kSortUnroll = 4;  // rounds of 32 keys loaded ahead per warp
+constexpr int kSortItems = 16;  // keys per thread and tile
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 pairs: 32 KB of shared memory
+static_assert(kRadix == kSortThreads, "prefix phases map one thread to one digit");
 
 struct SortPlan {
     int64_t n;
-    int grid;           // CTAs
-    int64_t warps;      // grid * kSortWarps
-    int64_t chunk;      // keys per warp (multiple of 32)
-    int64_t table;      // kRadix * warps
+    int grid;        // CTAs
+    int64_t chunk;   // keys per CTA (multiple of kSortTile)
+    int64_t table;   // kRadix * grid
 };
 
 static SortPlan make_plan(int64_t n) {
     SortPlan p;
     p.n = n;
-    // at least 32*kSortUnroll*4 keys per warp so tiny inputs do not fan out into empty warps
-    int64_t min_chunk = 32 * kSortUnroll * 4;
-    int64_t want_warps = ceil_div(n > 0 ? n : 1, min_chunk);
-    int64_t max_warps = (int64_t)kNumSMs * 4 * kSortWarps;  // 4 CTAs of 8 warps per SM
-    int64_t warps = want_warps < max_warps ? want_warps : max_warps;
-    p.grid = (int)ceil_div(warps, kSortWarps);
-    p.warps = (int64_t)p.grid * kSortWarps;
-    p.chunk = ceil_div(ceil_div(n > 0 ? n : 1, p.warps), 32) * 32;
-    p.table = (int64_t)kRadix * p.warps;
+    int64_t tiles = ceil_div(n > 0 ? n : 1, kSortTile);
+    int64_t max_ctas = (int64_t)kNumSMs * 4;  // 4 CTAs of 8 warps per SM
+    int64_t ctas = tiles < max_ctas ? tiles : max_ctas;
+    p.chunk = ceil_div(tiles, ctas) * kSortTile;
+    p.grid = (int)ceil_div(n > 0 ? n : 1, p.chunk);
+    p.table = (int64_t)kRadix * p.grid;
     return p;
 }
 
@@ -157,64 +157,113 @@ int exclusive_scan_u32(const uint32_t* in, uint32_t* out, int64_t n, void* ws, c
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const uint32_t* __restrict__ keys,
                                                                   int64_t n, int shift,
-                                                                  uint32_t mask, int64_t chunk,
-                                                                  int64_t warps,
+                                                                  uint32_t mask, int64_t chunk, int ctas,
                                                                   uint32_t* __restrict__ counts) {
-    __shared__ uint32_t hist[kSortWarps][kRadix];
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int64_t gw = (int64_t)blockIdx.x * kSortWarps + w;
-    for (int d = lane; d < kRadix; d += 32) hist[w][d] = 0;
-    __syncwarp();
-    int64_t beg = gw * chunk;
-    int64_t end = beg + chunk < n ? beg + chunk : n;
-    for (int64_t i = beg + lane; i < end; i += 32) {
-        uint32_t d = (keys[i] >> shift) & mask;
-        atomicAdd(&hist[w][d], 1u);  // counts only: the total is order-independent
-    }
-    __syncwarp();
-    for (int d = lane; d < kRadix; d += 32) counts[(int64_t)d * warps + gw] = hist[w][d];
+    __shared__ uint32_t hist[kRadix];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t beg = (int64_t)blockIdx.x * chunk;
+    const int64_t end = beg + chunk < n ? beg + chunk : n;
+    for (int64_t i = beg + threadIdx.x; i < end; i += kSortThreads)
+        atomicAdd(&hist[(keys[i] >> shift) & mask], 1u);  // counts only: the total is order-independent
+    __syncthreads();
+    counts[(int64_t)threadIdx.x * ctas + blockIdx.x] = hist[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(kSortThreads)
+__global__ void __launch_bounds__(kSortThreads, 2)
     radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                          uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n,
-                         int shift, uint32_t mask, int64_t chunk, int64_t warps,
+                         int shift, uint32_t mask, int64_t chunk, int ctas,
                          const uint32_t* __restrict__ offsets) {
-    __shared__ uint32_t cursor[kSortWarps][kRadix];
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int64_t gw = (int64_t)blockIdx.x * kSortWarps + w;
-    for (int d = lane; d < kRadix; d += 32) cursor[w][d] = offsets[(int64_t)d * warps + gw];
-    __syncwarp();
-    int64_t beg = gw * chunk;
-    int64_t end = beg + chunk < n ? beg + chunk : n;
+    __shared__ uint32_t s_key[kSortTile];
+    __shared__ uint32_t s_val[kSortTile];
+    __shared__ uint32_t whist[kSortWarps][kRadix];  // per-warp running digit counts, then warp prefixes
+    __shared__ uint32_t dig_start[kRadix];          // first position of every digit inside the sorted tile
+    __shared__ uint32_t dig_total[kRadix];
+    __shared__ uint32_t cursor[kRadix];             // next global output slot of every digit for this CTA
+    __shared__ uint32_t scan_tmp[kSortWarps + 1];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    for (int64_t i = beg; i < end; i += 32 * kSortUnroll) {
-        uint32_t k[kSortUnroll], v[kSortUnroll];
+    cursor[tid] = offsets[(int64_t)tid * ctas + blockIdx.x];
+    const int64_t beg = (int64_t)blockIdx.x * chunk;
+    const int64_t end = beg + chunk < n ? beg + chunk : n;
+
+    for (int64_t t0 = beg; t0 < end; t0 += kSortTile) {
+        // ---- load: warp w owns the contiguous sub-tile [w*512, (w+1)*512) as 16 rounds of 32 keys ----
+        uint32_t k[kSortItems], v[kSortItems], rk[kSortItems];
+        const int64_t wbase = t0 + (int64_t)w * (kSortItems * 32);
 #pragma unroll
-        for (int u = 0; u < kSortUnroll; ++u) {
-            int64_t idx = i + u * 32 + lane;
-            bool ok = idx < end;
-            k[u] = ok ? keys_in[idx] : 0u;
-            // vals_in == nullptr: the value is the input position (first pass of an argsort)
-            v[u] = ok ? (vals_in ? vals_in[idx] : (uint32_t)idx) : 0u;
+        for (int r = 0; r < kSortItems; ++r) {
+            const int64_t idx = wbase + r * 32 + lane;
+            const bool ok = idx < end;
+            k[r] = ok ? keys_in[idx] : 0u;
+            v[r] = ok ? (vals_in ? vals_in[idx] : (uint32_t)idx) : 0u;
         }
 #pragma unroll
-        for (int u = 0; u < kSortUnroll; ++u) {
-            int64_t idx = i + u * 32 + lane;
-            bool ok = idx < end;
-            uint32_t d = (k[u] >> shift) & mask;
-            // lanes past the end get a digit nobody else has, so they never join a peer group
-            uint32_t peers = __match_any_sync(0xffffffffu, ok ? d : (uint32_t)(kRadix + lane));
-            uint32_t rank = __popc(peers & lt_mask);
-            uint32_t pos = ok ? cursor[w][d] + rank : 0u;
-            __syncwarp();
-            if (ok) {
-                keys_out[pos] = k[u];
-                vals_out[pos] = v[u];
-                if (rank == 0) cursor[w][d] += __popc(peers);
+        for (int i = 0; i < kSortWarps; ++i) whist[i][tid] = 0;
+        __syncthreads();
+        // ---- rank inside the warp's sub-tile (stable: earlier round, then lower lane) ----
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) {
+            const bool ok = wbase + r * 32 + lane < end;
+            const uint32_t d = (k[r] >> shift) & mask;
+            const uint32_t peers = __match_any_sync(0xffffffffu, ok ? d : (uint32_t)(kRadix + lane));
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (ok && lane == leader) {
+                base = whist[w][d];
+                whist[w][d] = base + __popc(peers);
             }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            rk[r] = base + __popc(peers & lt_mask);
             __syncwarp();
         }
+        __syncthreads();
+        // ---- cross-warp prefix per digit (thread = digit), then the digits' start positions ----
+        {
+            uint32_t run = 0;
+#pragma unroll
+            for (int i = 0; i < kSortWarps; ++i) {
+                const uint32_t c = whist[i][tid];
+                whist[i][tid] = run;
+                run += c;
+            }
+            dig_total[tid] = run;
+            uint32_t incl = warp_incl_scan(run, lane);
+            if (lane == 31) scan_tmp[w] = incl;
+            __syncthreads();
+            if (w == 0) {
+                uint32_t x = lane < kSortWarps ? scan_tmp[lane] : 0;
+                uint32_t xi = warp_incl_scan(x, lane);
+                if (lane < kSortWarps) scan_tmp[lane] = xi - x;
+            }
+            __syncthreads();
+            dig_start[tid] = scan_tmp[w] + incl - run;
+        }
+        __syncthreads();
+        // ---- sort the tile by digit in shared memory ----
+#pragma unroll
+        for (int r = 0; r < kSortItems; ++r) {
+            if (wbase + r * 32 + lane < end) {
+                const uint32_t d = (k[r] >> shift) & mask;
+                const uint32_t pos = dig_start[d] + whist[w][d] + rk[r];
+                s_key[pos] = k[r];
+                s_val[pos] = v[r];
+            }
+        }
+        __syncthreads();
+        // ---- write out: consecutive threads -> consecutive slots of a digit's run (coalesced) ----
+        const int cnt = (int)((end - t0) < kSortTile ? (end - t0) : kSortTile);
+        for (int i = tid; i < cnt; i += kSortThreads) {
+            const uint32_t kk = s_key[i];
+            const uint32_t d = (kk >> shift) & mask;
+            const uint32_t g = cursor[d] + ((uint32_t)i - dig_start[d]);
+            keys_out[g] = kk;
+            vals_out[g] = s_val[i];
+        }
+        __syncthreads();
+        cursor[tid] += dig_total[tid];
+        __syncthreads();
     }
 }
 
@@ -266,13 +315,12 @@ int gg_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t
         uint32_t* dst_k = to_out ? keys_out : tmp_k;
         uint32_t* dst_v = to_out ? vals_out : tmp_v;
         int shift = pass * bits;
-        radix_hist_kernel<<<p.grid, kSortThreads, 0, st>>>(src_k, n, shift, mask, p.chunk, p.warps,
-                                                          counts);
+        radix_hist_kernel<<<p.grid, kSortThreads, 0, st>>>(src_k, n, shift, mask, p.chunk, p.grid, counts);
         GG_LAUNCHED();
         int rc = exclusive_scan_u32(counts, counts, p.table, scan_ws, st);
         if (rc != GG_OK) return rc;
-        radix_scatter_kernel<<<p.grid, kSortThreads, 0, st>>>(src_k, src_v, dst_k, dst_v, n, shift,
-                                                             mask, p.chunk, p.warps, counts);
+        radix_scatter_kernel<<<p.grid, kSortThreads, 0, st>>>(src_k, src_v, dst_k, dst_v, n, shift, mask,
+                                                             p.chunk, p.grid, counts);
         GG_LAUNCHED();
         src_k = dst_k;
         src_v = dst_v;

@@ -46,6 +46,14 @@ WORKLOADS = {
                      desc='gcnconv 1433->128 on Cora-shaped graph (2708 nodes, 10556 directed edges)'),
 }
 DEFAULT_WORKLOAD = 'products_gcn'
+DEFAULT_HALO = 'sliced'
+HALO_DESC = {
+    'allgather': 'halo all-gather of the feature rows over NCCL, rank-local SpMM',
+    'pipelined': 'P-1 NCCL send/recv rounds overlapped with the per-peer SpMMs',
+    'sliced': 'feature-sliced transposition over NVLink peer memory (column-scatter kernel out, SpMM epilogue '
+              'stores finished rows to their owners, flag barrier; no NCCL on the data path)',
+    'sliced_nccl': 'feature-sliced transposition over two NCCL all-to-alls around a full-graph SpMM of F/P columns',
+}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -266,19 +274,25 @@ def run_ours(args, spec, rank, world, dev):
         return bias_grad()
 
     t0 = time.time()
-    halo = os.environ.get('GG_HALO', 'allgather')   # allgather | pipelined (per-peer send/recv rounds, +10% at N<=4)
-    mk_layout = lambda e: parallel.PartitionedLayout(e, n, policy, part, pipelined=(halo == 'pipelined'))
+    # allgather | pipelined (per-peer send/recv rounds) | sliced (feature-sliced transposition over peer memory,
+    # SpMM epilogue stores to the owners) | sliced_nccl (same over all_to_all)
+    halo = os.environ.get('GG_HALO', DEFAULT_HALO)
+    if multi and halo.startswith('sliced') and not parallel.sliced_width(fout, world):
+        halo = 'allgather'
+    mk_layout = lambda e: parallel.PartitionedLayout(e, n, policy, part, exchange=halo)
     warm_weights = lambda pl: pl.sub_weights('gcn_tgt') if pl.pipelined else pl.weights('gcn_tgt')
     if multi:
         playout = mk_layout(ei)
         warm_weights(playout)
         slots_local, rows_local = playout.csr.num_slots, part.rows
+        if playout.sliced:   # every rank aggregates F/P columns of ALL rows
+            rows_local = n
     else:
         playout = None
         lay = get_layout(ei, n, policy)
         slots_local, rows_local = lay.csr.num_slots, n
         _ = lay.csc
-    slots = int(sum_over_ranks(slots_local))
+    slots = slots_local if (multi and playout.sliced) else int(sum_over_ranks(slots_local))
     torch.cuda.synchronize()
     layout_first_s = time.time() - t0
     clocks = ClockSampler(dev.index or 0)
@@ -305,13 +319,15 @@ def run_ours(args, spec, rank, world, dev):
 
     spmm_ms = [s.elapsed_time(e) for s, e in spmm_events]
     weighted = name in ('gcnconv', 'gcnidconv', 'gatconv', 'gatidconv')
-    per_launch_bytes = spmm_bytes(rows_local, slots_local, f_agg, weighted)
+    f_launch = f_agg // world if (multi and playout.sliced) else f_agg
+    per_launch_bytes = spmm_bytes(rows_local, slots_local, f_launch, weighted)
     avg_spmm_ms = float(np.mean(spmm_ms)) if spmm_ms else float('nan')
     peak, peak_src = load_peaks()
     achieved = per_launch_bytes / (avg_spmm_ms * 1e-3) / 1e9
     roofline = {'bound': 'hbm',
                 'kernel': 'spmm_mp_kernel + fixup (merge-path CSR aggregation; fwd on CSR and bwd on CSC)'
-                          + (' — rank 0 of %d, rank-local rows' % world if multi else ''),
+                          + ((' — rank 0 of %d, ' % world) + ('all rows x F/%d columns (sub-warp-group kernel, rows stored '
+                             'to their owners over NVLink)' % world if playout.sliced else 'rank-local rows') if multi else ''),
                 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
                 'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': per_launch_bytes,
@@ -389,9 +405,7 @@ def run_ours(args, spec, rank, world, dev):
         'data': 'synthetic (seeded power-law / BA / uniform generators in bench.py; random-init glorot weights)',
         'config': {'workload': spec['desc'], 'layer': name, 'nodes': n, 'edges_directed': int(ei.size(1)),
                    'slots_after_loop_policy': slots, 'f_in': fin, 'f_out': fout, 'f_aggregated': f_agg,
-                   'parallelism': ('row-partitioned x%d, halo exchange fwd and bwd over NCCL: %s' % (
-                       world, 'P-1 send/recv rounds overlapped with the per-peer SpMMs' if halo == 'pipelined'
-                       else 'one all-gather')) if multi
+                   'parallelism': ('row-partitioned x%d, exchange fwd and bwd: %s' % (world, HALO_DESC[halo])) if multi
                    else 'single GPU',
                    'l2_policy': 'inputs larger than L2 (feature matrix %.0f MB vs 126 MB L2)' % (n * f_agg * 4 / 1e6)
                    if n * f_agg * 4 > 126e6 else 'inputs fit L2: launch-bound workload, no flush',
@@ -402,6 +416,8 @@ def run_ours(args, spec, rank, world, dev):
         'layout_first_call_s': round(layout_first_s, 3),
     }
     if multi:
+        if playout.pool is not None:
+            playout.pool.close()
         dist.barrier()
         dist.destroy_process_group()
     return out
@@ -482,8 +498,8 @@ def run_reference(args, spec, rank, world):
 
 def main():
     # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
-    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-        os.environ['NCCL_DEBUG'] = 'WARN'
+    # (the banner appears at every level >= VERSION, so the level stays and the NCCL log moves to stderr)
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)

@@ -54,6 +54,17 @@ SIGNATURES = {
     "gg_spmm_mp_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64,
                                c_i64, c_int, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                c_size, c_int, c_ptr]),
+    "gg_spmm_group_lanes": (c_int, [c_i64]),
+    "gg_spmm_mpg_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64,
+                                c_ptr, c_int, c_i64, c_i64, c_i64, c_int, c_ptr, c_i64, c_f32, c_ptr, c_ptr,
+                                c_size, c_int, c_ptr]),
+    "gg_peer_handle_bytes": (c_int, []),
+    "gg_peer_alloc": (c_int, [c_size, ctypes.POINTER(c_ptr), ctypes.c_char_p]),
+    "gg_peer_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_ptr)]),
+    "gg_peer_close": (c_int, [c_ptr]),
+    "gg_peer_free": (c_int, [c_ptr]),
+    "gg_peer_barrier": (c_int, [ctypes.POINTER(c_ptr), c_int, c_int, ctypes.c_uint32, c_ptr]),
+    "gg_peer_scatter_cols_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, ctypes.POINTER(c_ptr), c_int, c_i64, c_ptr]),
     "gg_id_gemm_f32": (c_int, [ctypes.POINTER(GemmSegment), c_int, c_int, c_i64, c_i64, c_ptr, c_int,
                                c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_id_gemm_tc_workspace_bytes": (c_size, [ctypes.POINTER(GemmSegment), c_int, c_i64]),

@@ -69,6 +69,39 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
                  : "l"(p));
     return r;
 }
+// ---- L2 residency control ------------------------------------------------------------------------
+// The aggregation gathers feature rows at random (reused across rows, worth keeping in the 126 MB L2) while
+// it streams neighbour ids, weights and output rows through once.  Without hints the streams evict the
+// rows; with them the gathers are tagged evict_last and the streams evict_first.
+__device__ __forceinline__ uint64_t l2_policy(int kind) {  // 0 normal, 1 evict_last, 2 evict_first
+    uint64_t p;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg_nc_f4_hint(const float4* p, uint64_t pol) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ int32_t ldg_nc_s32_hint(const int32_t* p, uint64_t pol) {
+    int32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ldg_nc_f32_hint(const float* p, uint64_t pol) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void stg_f4_hint(float4* p, const float4& v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
     acc.x = fmaf(w, v.x, acc.x);
     acc.y = fmaf(w, v.y, acc.y);

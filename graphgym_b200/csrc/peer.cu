@@ -1,0 +1,149 @@
+// Peer memory over NVLink / NVSwitch for the row-partitioned path: buffers that the other
+// GPUs of the box can read and write directly, a stream-ordered barrier between the ranks, and the
+// column-slice scatter that turns a rank's rows [rows_r, F] into every peer's feature slice [N, F/P].
+//
+// One process per GPU: a buffer is cudaMalloc'ed by its owner, exported as a CUDA IPC handle (64 opaque
+// bytes the host side passes around with torch.distributed) and opened by the peers; the peers' stores
+// then travel over NVLink as ordinary global stores.  Nothing here calls NCCL.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace gg {
+
+struct PeerPtrs {
+    void* p[GG_PEER_MAX];
+};
+
+// ---- barrier --------------------------------------------------------------------------------------
+// flags[r] lives on rank r: GG_PEER_MAX u32 epochs, slot s written by rank s only.  Thread t signals peer t
+// (release, system scope: every store this stream issued before the barrier is visible to whoever
+// acquires the flag) and then waits until peer t's signal for the same epoch has landed here.
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerPtrs flags, int world, int rank, uint32_t epoch,
+                                                          long long timeout_cycles) {
+    const int t = threadIdx.x;
+    if (t >= world || t == rank) return;
+    __threadfence_system();
+    st_release_sys(static_cast<uint32_t*>(flags.p[t]) + rank, epoch);
+    const uint32_t* mine = static_cast<const uint32_t*>(flags.p[rank]) + t;
+    const long long t0 = clock64();
+    // epochs only grow; the signed difference keeps the comparison right across a u32 wrap
+    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+        if (clock64() - t0 > timeout_cycles) __trap();  // a lost peer fails the launch instead of hanging the GPU
+        __nanosleep(64);
+    }
+}
+
+// ---- column-slice scatter -------------------------------------------------------------------------
+// dst[c][(row_base + i) * fs + k] = src[i * ld + c * fs + k],  c = 0..world-1, fs = f / world.
+// One 16-byte vector per thread and iteration; consecutive threads walk a source row, so the reads are
+// coalesced 512-byte rows and the stores leave as fs*4-byte segments per peer.
+__global__ void __launch_bounds__(256) peer_scatter_cols_kernel(const float* __restrict__ src, int64_t ld,
+                                                                int64_t rows, int f, int fs,
+                                                                const __grid_constant__ PeerPtrs dst,
+                                                                int64_t row_base) {
+    const int nvec = f >> 2, svec = fs >> 2;
+    const int64_t total = rows * nvec;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / nvec;
+        const int v = (int)(e - i * nvec);
+        const int c = v / svec, k = v - c * svec;
+        const float4 val = __ldg(reinterpret_cast<const float4*>(src + i * ld) + v);
+        reinterpret_cast<float4*>(static_cast<float*>(dst.p[c]) + (row_base + i) * fs)[k] = val;
+    }
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+int gg_peer_handle_bytes(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int gg_peer_alloc(size_t bytes, void** ptr_host, unsigned char* handle_host) {
+    GG_REQUIRE(ptr_host && handle_host && bytes > 0, "gg_peer_alloc: bad arguments");
+    void* p = nullptr;
+    GG_CUDA(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("gg_peer_alloc: %s", cudaGetErrorString(e));
+        return GG_ERR_CUDA;
+    }
+    memcpy(handle_host, &h, sizeof(h));
+    *ptr_host = p;
+    return GG_OK;
+}
+
+int gg_peer_open(const unsigned char* handle_host, void** ptr_host) {
+    GG_REQUIRE(handle_host && ptr_host, "gg_peer_open: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_host, sizeof(h));
+    GG_CUDA(cudaIpcOpenMemHandle(ptr_host, h, cudaIpcMemLazyEnablePeerAccess));
+    return GG_OK;
+}
+
+int gg_peer_close(void* ptr) {
+    if (ptr) GG_CUDA(cudaIpcCloseMemHandle(ptr));
+    return GG_OK;
+}
+
+int gg_peer_free(void* ptr) {
+    if (ptr) GG_CUDA(cudaFree(ptr));
+    return GG_OK;
+}
+
+int gg_peer_barrier(void* const* flags_host, int world, int rank, uint32_t epoch, gg_stream_t stream) {
+    GG_REQUIRE(flags_host && world >= 1 && world <= GG_PEER_MAX && rank >= 0 && rank < world,
+               "gg_peer_barrier: world=%d rank=%d (at most %d peers)", world, rank, GG_PEER_MAX);
+    if (world == 1) return GG_OK;
+    PeerPtrs f{};
+    for (int i = 0; i < world; ++i) {
+        GG_REQUIRE(flags_host[i], "gg_peer_barrier: null flag block for rank %d", i);
+        f.p[i] = flags_host[i];
+    }
+    // ~20 s at 2 GHz: far beyond any healthy skew between ranks, short enough to fail before a box-level timeout
+    peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(f, world, rank, epoch, 40000000000LL);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
+int gg_peer_scatter_cols_f32(const float* src, int64_t ld, int64_t rows, int64_t f, float* const* dst_host,
+                             int world, int64_t row_base, gg_stream_t stream) {
+    GG_REQUIRE(rows >= 0 && f >= 0 && row_base >= 0, "gg_peer_scatter_cols_f32: negative size");
+    GG_REQUIRE(dst_host && world >= 1 && world <= GG_PEER_MAX, "gg_peer_scatter_cols_f32: world=%d", world);
+    if (rows == 0 || f == 0) return GG_OK;
+    GG_REQUIRE(f % (4 * world) == 0, "gg_peer_scatter_cols_f32: f=%lld must be a multiple of 4*world=%d",
+               (long long)f, 4 * world);
+    GG_REQUIRE(src && ld >= f && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0,
+               "gg_peer_scatter_cols_f32: source rows must be 16-byte aligned");
+    PeerPtrs d{};
+    for (int i = 0; i < world; ++i) {
+        GG_REQUIRE(dst_host[i] && (reinterpret_cast<uintptr_t>(dst_host[i]) & 15) == 0,
+                   "gg_peer_scatter_cols_f32: destination %d null or misaligned", i);
+        d.p[i] = dst_host[i];
+    }
+    int64_t total = rows * (f / 4);
+    int64_t grid = ceil_div(total, 256 * 4);
+    if (grid > (int64_t)kNumSMs * 8) grid = (int64_t)kNumSMs * 8;
+    if (grid < 1) grid = 1;
+    peer_scatter_cols_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(src, ld, rows, (int)f, (int)(f / world), d,
+                                                                      row_base);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
+}  // extern "C"

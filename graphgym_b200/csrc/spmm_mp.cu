@@ -53,6 +53,7 @@ struct MpArgs {
     const float* r1_v;
     const float* r2_s;
     const float* r2_v;
+    int l2_hint;  // 1: gathers evict_last, index / weight / output streams evict_first
 };
 
 // ---- mbarrier / bulk-copy PTX -----------------------------------------------------------------
@@ -69,11 +70,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
             smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
         : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -93,14 +94,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Stage global[s0, s1) into tile so that tile[s - sa] holds element s, sa = s0 & ~3.
 template <typename T, bool TMA>
 __device__ __forceinline__ uint32_t stage_begin(T* tile, const T* __restrict__ g, int s0, int s1, int lane,
-                                                uint64_t* bar) {
+                                                uint64_t* bar, uint64_t pol) {
     const int sa = s0 & ~3;
     const int ea = s1 & ~3;  // interior [sa, ea) is 16-byte aligned on both sides
     uint32_t bytes = 0;
     if (TMA) {
         if (ea > sa) {
             bytes = (uint32_t)(ea - sa) * 4u;
-            if (lane == 0) bulk_g2s(tile, g + sa, bytes, bar);
+            if (lane == 0) bulk_g2s(tile, g + sa, bytes, bar, pol);
         }
         const int t = ea + lane;  // <= 3 tail elements past the aligned interior (ea >= sa always)
         if (lane < 4 && t < s1) tile[t - sa] = g[t];
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(kMpThreads, VPL == 1 ? (DEEP ? 3 : 4) : 2) spm
         __syncwarp();
     }
     uint32_t phase = 0;
+    const uint64_t pol_keep = l2_policy(a.l2_hint ? 1 : 0), pol_stream = l2_policy(a.l2_hint ? 2 : 0);
 
     const int nvec = a.f >> 2;
     const float4* __restrict__ x4 = reinterpret_cast<const float4*>(a.x);
@@ -163,8 +165,8 @@ __global__ void __launch_bounds__(kMpThreads, VPL == 1 ? (DEEP ? 3 : 4) : 2) spm
             const int ea = s1 & ~3;
             if (ea > sa) mbar_expect_tx(bar, (uint32_t)(ea - sa) * 4u * (WEIGHTED ? 2u : 1u));
         }
-        bytes += stage_begin<int32_t, TMA>(s_nbr, a.nbr, s0, s1, lane, bar);
-        if (WEIGHTED) bytes += stage_begin<float, TMA>(s_w, a.w, s0, s1, lane, bar);
+        bytes += stage_begin<int32_t, TMA>(s_nbr, a.nbr, s0, s1, lane, bar, pol_stream);
+        if (WEIGHTED) bytes += stage_begin<float, TMA>(s_w, a.w, s0, s1, lane, bar, pol_stream);
         const int nrp = (r1 < a.n ? r1 + 1 : (int)a.n) - r0 + 1;  // rowptr[r0 .. min(r1+1, n)]
         for (int i = lane; i < nrp; i += 32) s_rp[i] = __ldg(a.rowptr + r0 + i);
         __syncwarp();
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(kMpThreads, VPL == 1 ? (DEEP ? 3 : 4) : 2) spm
                         if (a.r1_s) fma4(r, __ldg(a.r1_s + row), __ldg(reinterpret_cast<const float4*>(a.r1_v) + vi));
                         if (a.r2_s) fma4(r, __ldg(a.r2_s + row), __ldg(reinterpret_cast<const float4*>(a.r2_v) + vi));
                     }
-                    reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[vi] = r;
+                    stg_f4_hint(reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo) + vi, r, pol_stream);
                 }
             }
 #pragma unroll
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(kMpThreads, VPL == 1 ? (DEEP ? 3 : 4) : 2) spm
                 const float4* p = x4 + (int64_t)j * ldx4 + lane;
 #pragma unroll
                 for (int q = 0; q < VPL; ++q)
-                    v[u][q] = (ok && act[q]) ? ldg_nc_f4(p + q * 32) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[u][q] = (ok && act[q]) ? ldg_nc_f4_hint(p + q * 32, pol_keep) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -303,6 +305,249 @@ __global__ void __launch_bounds__(256) spmm_plan_kernel(const int32_t* __restric
         item_row[k] = (int32_t)lo;
         item_slot[k] = (int32_t)(d - lo);
     }
+}
+
+// =====================================================================================================
+// Narrow rows (f <= 128) and peer-memory output.
+//
+// With f/4 < 32 vectors per row the kernel above would leave most lanes idle.  Here the 32 lanes are cut
+// into S = 32/G groups of G lanes (G = 4, 8, 16 or 32 >= f/4) and one warp instruction gathers S DIFFERENT
+// slots of the warp's item: a batch is S x 8 consecutive slots, group g owns slots [8g, 8g+8) of it (two
+// 128-bit shared loads fetch its 8 neighbour ids), every group accumulates privately, and when a row ends
+// the partial sums are combined with a fixed xor-butterfly across the groups.  Everything is warp-uniform:
+// a row end costs one predicated sweep + log2(S) shuffle stages, never a divergent branch.
+// (The first design made every group an independent item consumer; the union of 8 groups' row-end
+// branches serialised the warp at 65 instructions per slot and 33 G slots/s whatever the row width —
+// profiles/r01_mpg16_v0_ncu_raw.csv.)
+//
+// PEER: the row-partitioned path's feature-sliced exchange (parallel.py).  This rank aggregates its
+// F/P-wide column slice for ALL rows; a finished row is stored straight into the memory of the rank that
+// owns the row (peer pointer table, plain 16-byte stores that travel over NVLink), so the aggregation
+// and the return leg of the exchange are one kernel.
+// =====================================================================================================
+struct PeerOut {
+    float* out[GG_PEER_MAX];  // out[o] = rank o's [rows_per_rank, ldo] block, already offset to this rank's columns
+    int per;                  // rows per rank
+};
+
+template <bool PEER>
+__device__ __forceinline__ float4* mpg_out_row(const MpArgs& a, const PeerOut& po, int row) {
+    if (PEER) {
+        const int o = row / po.per;
+        return reinterpret_cast<float4*>(po.out[o] + (int64_t)(row - o * po.per) * a.ldo);
+    }
+    return reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo);
+}
+
+template <int G>
+__device__ __forceinline__ void mpg_reduce_groups(float4& r) {
+#pragma unroll
+    for (int m = G; m < 32; m <<= 1) {
+        r.x += __shfl_xor_sync(0xffffffffu, r.x, m);
+        r.y += __shfl_xor_sync(0xffffffffu, r.y, m);
+        r.z += __shfl_xor_sync(0xffffffffu, r.z, m);
+        r.w += __shfl_xor_sync(0xffffffffu, r.w, m);
+    }
+}
+
+template <int G, bool WEIGHTED, bool PEER>
+__global__ void __launch_bounds__(kMpThreads, 4)
+    spmm_mpg_kernel(const __grid_constant__ MpArgs a, const __grid_constant__ PeerOut po) {
+    constexpr int S = 32 / G;  // slots per warp instruction
+    constexpr int U = 8;       // slots per group and batch
+    constexpr int B = S * U;   // slots per batch
+    __shared__ __align__(16) int32_t s_nbr_all[kMpWarps][kMpTile];
+    __shared__ __align__(16) float s_w_all[WEIGHTED ? kMpWarps : 1][WEIGHTED ? kMpTile : 4];
+    __shared__ __align__(16) int32_t s_rp_all[kMpWarps][kMpTile];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int grp = lane / G, gl = lane % G;
+    int32_t* s_nbr = s_nbr_all[wid];
+    float* s_w = s_w_all[WEIGHTED ? wid : 0];
+    int32_t* s_rp = s_rp_all[wid];
+
+    const int nvec = a.f >> 2;
+    const bool act = gl < nvec;
+    const bool writer = act && grp == 0;
+    // gather address = xg + j * row_bytes: one IMAD.WIDE.U32 per slot (the host checks ldx * 4 < 2^32);
+    // lanes past the row's last vector (f/4 < G) gather a duplicate of it and never store: no predicates
+    const char* __restrict__ xg = reinterpret_cast<const char*>(a.x) + (act ? gl : nvec - 1) * 16;
+    const uint32_t row_bytes = (uint32_t)a.ldx * 4u;
+    const uint64_t pol_keep = l2_policy(a.l2_hint ? 1 : 0), pol_stream = l2_policy(a.l2_hint ? 2 : 0);
+    auto gather = [&](int j) {
+        return ldg_nc_f4_hint(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)j * row_bytes), pol_keep);
+    };
+
+    int item = 0;
+    if (lane == 0) item = atomicAdd(a.counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+
+    while (item < a.items) {
+        int next = 0;
+        if (lane == 0) next = atomicAdd(a.counter, 1);
+        const int r0 = __ldg(a.item_row + item), s0 = __ldg(a.item_slot + item);
+        const int r1 = __ldg(a.item_row + item + 1), s1 = __ldg(a.item_slot + item + 1);
+
+        __syncwarp();  // everyone is done with the previous item's tiles
+        for (int q = s0 + lane; q < s1; q += 32) {
+            s_nbr[q - s0] = ldg_nc_s32_hint(a.nbr + q, pol_stream);
+            if (WEIGHTED) s_w[q - s0] = ldg_nc_f32_hint(a.w + q, pol_stream);
+        }
+        const int nrp = (r1 < a.n ? r1 + 1 : (int)a.n) - r0 + 1;
+        for (int i = lane; i < nrp; i += 32) s_rp[i] = __ldg(a.rowptr + r0 + i);
+        __syncwarp();
+
+        const bool cont_first = s0 > s_rp[0];
+        int cur = r0;
+        int re = r0 < a.n ? s_rp[1] : 0x7fffffff;  // slot index at which the current row ends
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        // acc holds this group's share of row `row`: combine the groups, apply the epilogue, store
+        auto finalize = [&](int row) {
+            mpg_reduce_groups<G>(acc);
+            if (row == r0 && cont_first) {  // the row began in an earlier item: partial only
+                if (writer) reinterpret_cast<float4*>(a.head + (int64_t)item * a.f)[gl] = acc;
+            } else if (writer) {
+                float4 r = acc;
+                if (a.reduce == GG_MEAN) {
+                    const int deg = s_rp[row - r0 + 1] - s_rp[row - r0];
+                    const float inv = deg > 0 ? 1.0f / (float)deg : 1.0f;
+                    r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
+                }
+                if (a.x_self)
+                    fma4(r, a.self_scale, __ldg(reinterpret_cast<const float4*>(a.x_self + (int64_t)row * a.ld_self) + gl));
+                if (a.bias) add4(r, __ldg(reinterpret_cast<const float4*>(a.bias) + gl));
+                stg_f4_hint(mpg_out_row<PEER>(a, po, row) + gl, r, pol_stream);
+            }
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+
+        for (int s = s0; s < s1; s += B) {
+            const int g0 = s + grp * U;  // this group's first slot of the batch
+            const int t = g0 - s0;       // multiple of 8: 16-byte aligned inside the tile
+            const int e = s + B < s1 ? s + B : s1;
+            const bool full = s + B <= s1;
+            float4 v[U];
+            float wv[U];
+            if (full) {
+                const int4 i0 = *reinterpret_cast<const int4*>(s_nbr + t);
+                const int4 i1 = *reinterpret_cast<const int4*>(s_nbr + t + 4);
+                const int j[U] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+                for (int u = 0; u < U; ++u) v[u] = gather(j[u]);
+                if (WEIGHTED) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(s_w + t);
+                    const float4 w1 = *reinterpret_cast<const float4*>(s_w + t + 4);
+                    wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
+                    wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+                }
+            } else {  // the item's last, partial batch
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool ok = g0 + u < s1;
+                    v[u] = ok ? gather(s_nbr[t + u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (WEIGHTED) wv[u] = ok ? s_w[t + u] : 0.f;
+                }
+            }
+            if (re >= e && !(re == e && cur < r1)) {  // no row ends inside the batch
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (WEIGHTED) fma4(acc, wv[u], v[u]);
+                    else add4(acc, v[u]);
+                }
+            } else {
+                int pos = s;
+                while (true) {  // warp-uniform: one round per row segment of the batch
+                    const int seg_end = re < e ? re : e;
+                    const int lo = pos - g0, hi = seg_end - g0;  // this group's slots u in [lo, hi) belong to the segment
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (u >= lo && u < hi) {
+                            if (WEIGHTED) fma4(acc, wv[u], v[u]);
+                            else add4(acc, v[u]);
+                        }
+                    }
+                    if (re > e || cur >= r1) break;  // the row continues (or its marker belongs to the next item)
+                    finalize(cur);
+                    ++cur;
+                    re = cur < a.n ? s_rp[cur - r0 + 1] : 0x7fffffff;
+                    pos = seg_end;
+                }
+            }
+        }
+        while (cur < r1) {  // markers after the last slot of the item (empty rows, marker-only items)
+            finalize(cur);
+            ++cur;
+        }
+        // the row still open at the end of the item (row r1): its partial, possibly all zero
+        mpg_reduce_groups<G>(acc);
+        if (writer) reinterpret_cast<float4*>(a.carry + (int64_t)item * a.f)[gl] = acc;
+
+        item = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+// G lanes per item; same combination order as spmm_mp_fixup_kernel.
+template <int G, bool PEER>
+__global__ void __launch_bounds__(kMpThreads)
+    spmm_mpg_fixup_kernel(const __grid_constant__ MpArgs a, const __grid_constant__ PeerOut po) {
+    const int64_t idx = (int64_t)blockIdx.x * kMpThreads + threadIdx.x;
+    const int64_t fi = idx / G;
+    const int gl = (int)(idx % G);
+    if (fi < 1 || fi >= a.items) return;
+    const int f_item = (int)fi;
+    const int r0 = __ldg(a.item_row + f_item), s0 = __ldg(a.item_slot + f_item);
+    const int r1 = __ldg(a.item_row + f_item + 1);
+    if (r0 >= a.n || r0 >= r1) return;
+    const int rb = __ldg(a.rowptr + r0);
+    if (s0 <= rb) return;
+    if (gl >= (a.f >> 2)) return;
+    int k0 = f_item - 1;
+    while (k0 >= 1 && __ldg(a.item_row + k0) == r0 && __ldg(a.item_slot + k0) > rb) --k0;
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = k0; k < f_item; ++k) add4(r, reinterpret_cast<const float4*>(a.carry + (int64_t)k * a.f)[gl]);
+    add4(r, reinterpret_cast<const float4*>(a.head + (int64_t)f_item * a.f)[gl]);
+    if (a.reduce == GG_MEAN) {
+        const int deg = __ldg(a.rowptr + r0 + 1) - rb;
+        const float inv = deg > 0 ? 1.0f / (float)deg : 1.0f;
+        r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
+    }
+    if (a.x_self) fma4(r, a.self_scale, __ldg(reinterpret_cast<const float4*>(a.x_self + (int64_t)r0 * a.ld_self) + gl));
+    if (a.bias) add4(r, __ldg(reinterpret_cast<const float4*>(a.bias) + gl));
+    mpg_out_row<PEER>(a, po, r0)[gl] = r;
+}
+
+template <int G, bool WEIGHTED, bool PEER>
+static void launch_mpg_one(const MpArgs& a, const PeerOut& po, cudaStream_t st) {
+    static bool done = false;
+    if (!done) {
+        cudaFuncSetAttribute(spmm_mpg_kernel<G, WEIGHTED, PEER>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        done = true;
+    }
+    int grid = (int)ceil_div(a.items, kMpWarps);
+    if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+    spmm_mpg_kernel<G, WEIGHTED, PEER><<<grid, kMpThreads, 0, st>>>(a, po);
+    count_launch();
+    spmm_mpg_fixup_kernel<G, PEER><<<(int)ceil_div((int64_t)a.items * G, kMpThreads), kMpThreads, 0, st>>>(a, po);
+    count_launch();
+}
+
+template <int G>
+static void launch_mpg(const MpArgs& a, const PeerOut& po, bool peer, cudaStream_t st) {
+    if (a.w) {
+        if (peer) launch_mpg_one<G, true, true>(a, po, st);
+        else launch_mpg_one<G, true, false>(a, po, st);
+    } else {
+        if (peer) launch_mpg_one<G, false, true>(a, po, st);
+        else launch_mpg_one<G, false, false>(a, po, st);
+    }
+}
+
+static inline int mpg_lanes(int64_t f) {
+    if (f <= 0 || f % 4 != 0 || f > 128) return 0;
+    const int nvec = (int)(f / 4);
+    return nvec <= 4 ? 4 : nvec <= 8 ? 8 : nvec <= 16 ? 16 : 32;
 }
 
 static inline bool mp_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -414,7 +659,8 @@ int gg_spmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slo
     float* head = c.take<float>((size_t)items * f);
     GG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
     MpArgs a{rowptr, nbr, w_slot, item_row, item_slot, (int)items, x, ldx, out, ldo, num_rows, (int)f,
-             reduce, x_self, ld_self, self_scale, bias, counter, carry, head, r1_s, r1_v, r2_s, r2_v};
+             reduce, x_self, ld_self, self_scale, bias, counter, carry, head, r1_s, r1_v, r2_s, r2_v,
+             (stage_mode & 4) ? 1 : 0};
     // TMA staging needs 16-byte aligned index / weight arrays; otherwise plain loads
     // stage_mode bit 0: 0 = cp.async.bulk staging, 1 = plain loads; bit 1: deep gather batches
     bool tma = (stage_mode & 1) == 0 && mp_aligned16(nbr) && (!w_slot || mp_aligned16(w_slot));
@@ -427,6 +673,65 @@ int gg_spmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slo
     else if (nvec <= 64) launch_mp<2>(a, tma, deep, grid, st);
     else if (nvec <= 128) launch_mp<4>(a, tma, deep, grid, st);
     else launch_mp<8>(a, tma, deep, grid, st);
+    GG_CUDA(cudaPeekAtLastError());
+    return GG_OK;
+}
+
+int gg_spmm_group_lanes(int64_t f) { return mpg_lanes(f); }
+
+int gg_spmm_mpg_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, const int32_t* item_row,
+                    const int32_t* item_slot, int64_t items, const float* x, int64_t ldx, float* out,
+                    int64_t ldo, float* const* out_peers_host, int world, int64_t rows_per_rank,
+                    int64_t num_rows, int64_t f, int reduce, const float* x_self, int64_t ld_self,
+                    float self_scale, const float* bias, void* workspace, size_t workspace_bytes, int flags,
+                    gg_stream_t stream) {
+    GG_REQUIRE(num_rows >= 0 && f >= 0 && items >= 0, "gg_spmm_mpg_f32: negative size");
+    GG_REQUIRE(reduce == GG_SUM || reduce == GG_MEAN, "gg_spmm_mpg_f32: reduce=%d", reduce);
+    if (num_rows == 0 || f == 0) return GG_OK;
+    const int g = mpg_lanes(f);
+    if (!g) {
+        set_error("gg_spmm_mpg_f32: needs f %% 4 == 0 and f <= 128 (got %lld)", (long long)f);
+        return GG_ERR_UNSUPPORTED;
+    }
+    const bool peer = out_peers_host != nullptr;
+    GG_REQUIRE(rowptr && item_row && item_slot && x && workspace && (peer || out), "gg_spmm_mpg_f32: null pointer");
+    GG_REQUIRE(items >= 1 && items < ((int64_t)1 << 31) - 1, "gg_spmm_mpg_f32: items out of range");
+    GG_REQUIRE(num_rows < ((int64_t)1 << 31), "gg_spmm_mpg_f32: too many rows");
+    GG_REQUIRE(ldx >= f && ldx < ((int64_t)1 << 30), "gg_spmm_mpg_f32: ldx=%lld out of range", (long long)ldx);
+    GG_REQUIRE((ldx % 4 == 0) && (ldo % 4 == 0) && mp_aligned16(x) && (!x_self || (ld_self % 4 == 0 && mp_aligned16(x_self))) &&
+                   (!bias || mp_aligned16(bias)), "gg_spmm_mpg_f32: rows must be 16-byte aligned");
+    PeerOut po{};
+    po.per = 1;
+    if (peer) {
+        GG_REQUIRE(world >= 1 && world <= GG_PEER_MAX && rows_per_rank >= 1 && rows_per_rank < ((int64_t)1 << 31) &&
+                       rows_per_rank * world >= num_rows,
+                   "gg_spmm_mpg_f32: world=%d rows_per_rank=%lld do not cover %lld rows", world,
+                   (long long)rows_per_rank, (long long)num_rows);
+        for (int i = 0; i < world; ++i) {
+            GG_REQUIRE(out_peers_host[i] && mp_aligned16(out_peers_host[i]), "gg_spmm_mpg_f32: peer block %d null or misaligned", i);
+            po.out[i] = out_peers_host[i];
+        }
+        po.per = (int)rows_per_rank;
+    } else {
+        GG_REQUIRE(mp_aligned16(out), "gg_spmm_mpg_f32: out must be 16-byte aligned");
+    }
+    if (workspace_bytes < gg_spmm_mp_workspace_bytes(items, f)) {
+        set_error("gg_spmm_mpg_f32: workspace %zu < %zu", workspace_bytes, gg_spmm_mp_workspace_bytes(items, f));
+        return GG_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    Carver c(workspace);
+    int* counter = c.take<int>(64);
+    float* carry = c.take<float>((size_t)items * f);
+    float* head = c.take<float>((size_t)items * f);
+    GG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    MpArgs a{rowptr, nbr, w_slot, item_row, item_slot, (int)items, x, ldx, out, ldo, num_rows, (int)f,
+             reduce, x_self, ld_self, self_scale, bias, counter, carry, head, nullptr, nullptr, nullptr, nullptr,
+             (flags & 4) ? 1 : 0};
+    if (g == 4) launch_mpg<4>(a, po, peer, st);
+    else if (g == 8) launch_mpg<8>(a, po, peer, st);
+    else if (g == 16) launch_mpg<16>(a, po, peer, st);
+    else launch_mpg<32>(a, po, peer, st);
     GG_CUDA(cudaPeekAtLastError());
     return GG_OK;
 }

@@ -18,9 +18,14 @@ ACT_NONE, ACT_RELU = 0, 1
 
 
 import os as _os
-SPMM_ALGO = _os.environ.get("GG_SPMM_ALGO", "auto")    # auto | mp | row
+SPMM_ALGO = _os.environ.get("GG_SPMM_ALGO", "auto")    # auto | mp | mpg (sub-warp groups, f <= 128) | row
 SPMM_STAGE = _os.environ.get("GG_SPMM_STAGE", "tma")   # tma | ldg
 SPMM_DEEP = _os.environ.get("GG_SPMM_DEEP", "0") == "1"  # 16 instead of 8 gathers per lane and batch
+SPMM_L2HINT = _os.environ.get("GG_SPMM_L2HINT", "1") == "1"  # gathers evict_last, streams evict_first in L2
+
+
+def _spmm_flags():
+    return (1 if SPMM_STAGE == "ldg" else 0) | (2 if SPMM_DEEP else 0) | (4 if SPMM_L2HINT else 0)
 GEMM_MODE = _os.environ.get("GG_GEMM", "tc")           # tc (tcgen05 3xTF32) | simt (fp32 CUDA cores)
 
 
@@ -69,19 +74,23 @@ class Csr:
         self.policy, self.group_by = policy, group_by
         self._plan = None
 
-    @property
-    def plan(self):
-        """Merge-path work plan of the load-balanced SpMM: (item_row, item_slot, items), built once."""
+    def _build_plan(self, units):
         if self._plan is None:
+            self._plan = {}
+        if units not in self._plan:
             L = lib()
-            units = int(L.gg_spmm_plan_units(self.num_nodes, self.num_slots))
             items = int(L.gg_spmm_plan_items(self.num_nodes, self.num_slots, units))
             item_row = torch.empty(items + 1, dtype=torch.int32, device=self.rowptr.device)
             item_slot = torch.empty(items + 1, dtype=torch.int32, device=self.rowptr.device)
             check(L.gg_spmm_plan_build(_ptr(self.rowptr), self.num_nodes, self.num_slots, units,
                                        _ptr(item_row), _ptr(item_slot), _stream()), "gg_spmm_plan_build")
-            self._plan = (item_row, item_slot, items)
-        return self._plan
+            self._plan[units] = (item_row, item_slot, items)
+        return self._plan[units]
+
+    @property
+    def plan(self):
+        """Merge-path work plan of the load-balanced SpMM: (item_row, item_slot, items), built once."""
+        return self._build_plan(int(lib().gg_spmm_plan_units(self.num_nodes, self.num_slots)))
 
 
 def layout_build(edge_index, num_nodes, policy=LOOPS_KEEP, group_by=BY_TARGET, row_range=None, nbr_range=None):
@@ -192,50 +201,85 @@ def id_count(ids, num_nodes):
 # --------------------------------------------------------------------------------------------
 # aggregation
 # --------------------------------------------------------------------------------------------
+class PeerRows:
+    """Where the rows of a peer-output SpMM go: ``ptrs[o]`` = device pointer (peer memory, already offset
+    to this rank's column slice) of rank o's [rows_per_rank, ld] block."""
+    __slots__ = ("ptrs", "rows_per_rank", "ld", "_arr")
+
+    def __init__(self, ptrs, rows_per_rank, ld):
+        self.ptrs, self.rows_per_rank, self.ld = [int(p) for p in ptrs], int(rows_per_rank), int(ld)
+        self._arr = (ctypes.c_void_p * len(self.ptrs))(*self.ptrs)
+
+
 def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None, out=None, rank1=None,
-         x_row_base=0):
+         x_row_base=0, out_peers=None):
     """out[i,:] = reduce_{s in segment i} w[s]*x[nbr[s],:] + self_scale*x_self[i,:] + bias.
 
     ``rank1`` = (s1 [n], v1 [f], s2 [n], v2 [f]) adds s1[i]*v1 + s2[i]*v2 in the epilogue (merge-path
     kernel only; used by the GAT backward).  ``x_row_base``: ``x`` holds rows [x_row_base, x_row_base +
-    x.size(0)) of the matrix the neighbour ids index (a peer's block in the halo pipeline)."""
+    x.size(0)) of the matrix the neighbour ids index (a peer's block in the halo pipeline).
+    ``out_peers`` (PeerRows): rows are stored into the owning ranks' memory instead of ``out``
+    (feature-sliced exchange of the row-partitioned path); returns None."""
     _need_cuda(x, w_slot, x_self, bias, csr.rowptr)
     x, ldx = _rows(x, "x")
     n, f = csr.num_nodes, x.size(1)
     x_ptr = ctypes.c_void_p(x.data_ptr() - int(x_row_base) * ldx * 4)
-    if out is None:
-        out = torch.empty((n, f), dtype=torch.float32, device=x.device)
-    out_t, ldo = _rows(out, "out")
-    assert out_t is out, "out must have unit inner stride"
     ld_self = 0
     if x_self is not None:
         x_self, ld_self = _rows(x_self, "x_self")
     if bias is not None:
         bias = bias.contiguous()
+    L = lib()
+    if out_peers is not None:
+        if rank1 is not None or out is not None:
+            raise ValueError("out_peers excludes out / rank1")
+        item_row, item_slot, items = csr.plan
+        ws_bytes = int(L.gg_spmm_mp_workspace_bytes(items, f))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        check(L.gg_spmm_mpg_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(item_row), _ptr(item_slot),
+                                items, x_ptr, ldx, None, out_peers.ld, out_peers._arr, len(out_peers.ptrs),
+                                out_peers.rows_per_rank, n, f, reduce, _ptr(x_self), ld_self, float(self_scale),
+                                _ptr(bias), _ptr(ws), ws_bytes, _spmm_flags(), _stream()), "gg_spmm_mpg_f32")
+        return None
+    if out is None:
+        out = torch.empty((n, f), dtype=torch.float32, device=x.device)
+    out_t, ldo = _rows(out, "out")
+    assert out_t is out, "out must have unit inner stride"
     algo = SPMM_ALGO
+    big = n + csr.num_slots >= 1 << 14
     if algo == "auto":
-        # merge-path kernel for wide rows on graphs big enough to need balancing; one-warp-per-row
-        # (with sub-warp groups for narrow features) otherwise
-        algo = "mp" if (f % 4 == 0 and 64 < f <= 1024 and n + csr.num_slots >= 1 << 14) else "row"
+        # merge-path kernels on graphs big enough to need balancing: whole warps per item for wide rows,
+        # sub-warp groups for narrow ones; one-warp-per-row (odd f, tiny graphs) otherwise
+        algo = "row"
+        if f % 4 == 0 and big:
+            algo = "mp" if 64 < f <= 1024 else ("mpg" if f <= 64 else "row")
     if rank1 is not None:
         algo = "mp"
     r1 = [t.contiguous() if t is not None else None for t in (rank1 or (None, None, None, None))]
-    if algo == "mp" and f % 4 == 0 and f <= 1024 and n > 0:
+    if algo == "mpg" and f % 4 == 0 and f <= 128 and n > 0:
         item_row, item_slot, items = csr.plan
-        L = lib()
+        ws_bytes = int(L.gg_spmm_mp_workspace_bytes(items, f))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        check(L.gg_spmm_mpg_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(item_row), _ptr(item_slot),
+                                items, x_ptr, ldx, _ptr(out), ldo, None, 1, max(n, 1), n, f, reduce,
+                                _ptr(x_self), ld_self, float(self_scale), _ptr(bias), _ptr(ws), ws_bytes,
+                                _spmm_flags(), _stream()), "gg_spmm_mpg_f32")
+        return out
+    if algo in ("mp", "mpg") and f % 4 == 0 and f <= 1024 and n > 0:
+        item_row, item_slot, items = csr.plan
         ws_bytes = int(L.gg_spmm_mp_workspace_bytes(items, f))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         check(L.gg_spmm_mp_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(item_row), _ptr(item_slot),
                                items, x_ptr, ldx, _ptr(out), ldo, n, f, reduce, _ptr(x_self), ld_self,
                                float(self_scale), _ptr(bias), _ptr(r1[0]), _ptr(r1[1]), _ptr(r1[2]), _ptr(r1[3]),
-                               _ptr(ws), ws_bytes, (1 if SPMM_STAGE == "ldg" else 0) | (2 if SPMM_DEEP else 0), _stream()),
+                               _ptr(ws), ws_bytes, _spmm_flags(), _stream()),
               "gg_spmm_mp_f32")
         return out
     if rank1 is not None:
         raise ValueError("rank-1 epilogue terms need the merge-path kernel (f % 4 == 0, f <= 1024)")
-    check(lib().gg_spmm_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), x_ptr, ldx, _ptr(out), ldo,
-                            n, f, reduce, _ptr(x_self), ld_self, float(self_scale), _ptr(bias),
-                            _stream()), "gg_spmm_f32")
+    check(L.gg_spmm_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), x_ptr, ldx, _ptr(out), ldo,
+                        n, f, reduce, _ptr(x_self), ld_self, float(self_scale), _ptr(bias),
+                        _stream()), "gg_spmm_f32")
     return out
 
 

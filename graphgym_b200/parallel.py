@@ -11,17 +11,30 @@ their CSR rows (global source ids) and the matching output rows.
             still in flight (per-peer sub-layouts, partial sums accumulated in a fixed block order).
   backward  all-gather of dOut  ->  local CSC SpMM (rows = owned SOURCE nodes, global target ids)
             gives dH_r  ->  dW_r = X_r^T dH_r, all-reduced with the other (tiny) parameter gradients.
+  feature-sliced exchange (``exchange='sliced'``): the all-gather moves N*F*4 bytes INTO every rank however
+            many ranks there are, so at 8 GPUs the two halo all-gathers are 60 % of the step.  Here the
+            exchange is a transposition instead: rank c receives column slice c (F/P wide) of every rank's
+            rows — (P-1)/P^2 * N*F*4 bytes per rank, 8x less at P = 8 — aggregates that slice over the
+            WHOLE graph (every rank holds the full CSR/CSC; narrow rows run on the sub-warp-group kernel) and
+            returns finished rows to their owners.  Inputs and outputs stay row-partitioned.  Both legs run
+            over peer memory (csrc/peer.cu): a column-scatter kernel stores into the peers' slices, and the
+            SpMM's epilogue stores each finished row into the owner's block, i.e. aggregation and exchange
+            are ONE kernel; ranks are ordered by a flag barrier in peer memory — no NCCL on the data path.
+            ``exchange='sliced_nccl'`` is the same algorithm over ``all_to_all_single`` (gloo in the CPU tests).
 Both directions use the same collective, and every reduction on the data path is rank-local in a
 fixed order: the N-GPU result equals the 1-GPU result up to fp32 re-association (rows that the
 merge-path plan splits at different places, and the all-reduced dW).
 
 The collective is issued through ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests).
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
 from . import functional as F_
 from . import ops
+from ._lib import check, lib
 
 
 class RowPartition:
@@ -91,16 +104,31 @@ class PartitionedLayout:
     (``sub_csr[b]`` / ``sub_csc[b]``: slots whose neighbour lives in block b), so that a peer's block can be
     aggregated as soon as it has arrived instead of after a full all-gather."""
 
-    def __init__(self, edge_index, num_nodes, policy, part, group=None, pipelined=False):
+    def __init__(self, edge_index, num_nodes, policy, part, group=None, pipelined=False, exchange=None,
+                 pool=None):
         self.part, self.group, self.policy = part, group, policy
         self.num_nodes = int(num_nodes)
-        self.pipelined = bool(pipelined) and part.world > 1
-        rng = (part.lo, part.hi)
-        self.csr = ops.layout_build(edge_index, num_nodes, policy, ops.BY_TARGET, row_range=rng)
-        self.csc = ops.layout_build(edge_index, num_nodes, policy, ops.BY_SOURCE, row_range=rng)
+        self.exchange = exchange or ('pipelined' if pipelined else 'allgather')
+        if part.world == 1 and self.exchange != 'allgather':
+            self.exchange = 'allgather'
+        if self.exchange not in ('allgather', 'pipelined', 'sliced', 'sliced_nccl'):
+            raise ValueError(f'unknown halo exchange {self.exchange!r}')
+        self.pipelined = self.exchange == 'pipelined'
+        self.sliced = self.exchange in ('sliced', 'sliced_nccl')
+        self.pool = pool
         self._weights = {}
         self._sub_weights = {}
         self.sub_csr = self.sub_csc = None
+        if self.sliced:
+            # every rank aggregates its column slice over the whole graph: full layouts, no row filter
+            self.csr = ops.layout_build(edge_index, num_nodes, policy, ops.BY_TARGET)
+            self.csc = ops.layout_build(edge_index, num_nodes, policy, ops.BY_SOURCE)
+            if self.exchange == 'sliced' and self.pool is None:
+                self.pool = PeerPool.shared(part, group)
+            return
+        rng = (part.lo, part.hi)
+        self.csr = ops.layout_build(edge_index, num_nodes, policy, ops.BY_TARGET, row_range=rng)
+        self.csc = ops.layout_build(edge_index, num_nodes, policy, ops.BY_SOURCE, row_range=rng)
         if self.pipelined:
             blocks = [part.bounds(b) for b in range(part.world)]
             self.sub_csr = [ops.layout_build(edge_index, num_nodes, policy, ops.BY_TARGET, row_range=rng,
@@ -122,6 +150,8 @@ class PartitionedLayout:
         return self._sub_weights[kind]
 
     def _global_degree(self, local_layout):
+        if self.sliced:   # the layout is the whole graph already
+            return ops.segment_degree(local_layout)
         deg_local = ops.segment_degree(local_layout).view(-1, 1)
         return all_gather_rows(deg_local, self.part, self.group).reshape(-1).contiguous()
 
@@ -197,8 +227,178 @@ class _DistAggregatePipelined(torch.autograd.Function):
         return gh, None, None, gb
 
 
+# ------------------------------------------------------------------------------------------------
+# peer memory (csrc/peer.cu) and the feature-sliced exchange
+# ------------------------------------------------------------------------------------------------
+class _RawCuda:
+    """Lets torch view a device allocation it does not own (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {'shape': (int(nbytes),), 'typestr': '|u1', 'data': (int(ptr), False),
+                                         'version': 2}
+
+
+class PeerBuffer:
+    """The same allocation on every rank: ``ptrs[r]`` is rank r's copy as seen from THIS process,
+    ``local`` a uint8 torch view of this rank's copy."""
+
+    def __init__(self, ptrs, nbytes, rank, device):
+        self.ptrs, self.nbytes = ptrs, nbytes
+        self.local = torch.as_tensor(_RawCuda(ptrs[rank], nbytes), device=device)
+
+    def view(self, *shape):
+        n = 1
+        for d in shape:
+            n *= d
+        return self.local[:n * 4].view(torch.float32).view(*shape)
+
+
+class PeerPool:
+    """Peer-visible buffers of one process group (one process per GPU of a box) plus the flag barrier.
+    Allocation is collective: every rank must request the same keys in the same order."""
+    _shared = {}
+
+    @classmethod
+    def shared(cls, part, group=None):
+        key = (id(group), part.world, part.rank)
+        if key not in cls._shared:
+            cls._shared[key] = cls(part.world, part.rank, group)
+        return cls._shared[key]
+
+    def __init__(self, world, rank, group=None):
+        if world > 8:
+            raise ValueError('peer memory exchange: at most 8 ranks (one NVSwitch box)')
+        self.world, self.rank, self.group = world, rank, group
+        self.device = torch.device('cuda', torch.cuda.current_device())
+        self._bufs = {}
+        self._owned, self._opened = [], []
+        self.epoch = 0
+        self.flags = self._alloc(256)
+        self._flag_arr = (ctypes.c_void_p * world)(*self.flags.ptrs)
+
+    def _alloc(self, nbytes):
+        L = lib()
+        hb = int(L.gg_peer_handle_bytes())
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(hb)
+        check(L.gg_peer_alloc(int(nbytes), ctypes.byref(ptr), handle), 'gg_peer_alloc')
+        self._owned.append(ptr.value)
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(self.device)
+        every = torch.empty(self.world * hb, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(every, mine, group=self.group)   # also orders the allocation across ranks
+        every = every.cpu().numpy().tobytes()
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(ptr.value)
+                continue
+            q = ctypes.c_void_p()
+            check(L.gg_peer_open(every[r * hb:(r + 1) * hb], ctypes.byref(q)), 'gg_peer_open')
+            self._opened.append(q.value)
+            ptrs.append(q.value)
+        return PeerBuffer(ptrs, int(nbytes), self.rank, self.device)
+
+    def get(self, key, nbytes):
+        buf = self._bufs.get(key)
+        if buf is None or buf.nbytes < nbytes:
+            buf = self._bufs[key] = self._alloc(max(int(nbytes), 256))
+        return buf
+
+    def barrier(self):
+        """Stream-ordered: kernels enqueued after it see every store the peers enqueued before theirs."""
+        self.epoch += 1
+        check(lib().gg_peer_barrier(self._flag_arr, self.world, self.rank, self.epoch,
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'gg_peer_barrier')
+
+    def close(self):
+        torch.cuda.synchronize()
+        L = lib()
+        for q in self._opened:
+            L.gg_peer_close(ctypes.c_void_p(q))
+        if dist.is_initialized():
+            dist.barrier(group=self.group)   # nobody frees while a peer still maps the buffer
+        for q in self._owned:
+            L.gg_peer_free(ctypes.c_void_p(q))
+        self._opened, self._owned, self._bufs = [], [], {}
+        PeerPool._shared = {k: v for k, v in PeerPool._shared.items() if v is not self}
+
+
+def sliced_width(f, world):
+    """Slice width of the feature-sliced exchange, or 0 when f does not split into 16-byte aligned slices
+    of at most 128 columns (the sub-warp-group kernel's range)."""
+    if world < 1 or f % (4 * world) != 0 or f // world > 128:
+        return 0
+    return f // world
+
+
+def _peer_scatter_cols(local, ptrs, row_base):
+    local, ld = ops._rows(local, 'local')
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    check(lib().gg_peer_scatter_cols_f32(ctypes.c_void_p(local.data_ptr()), ld, local.size(0), local.size(1), arr,
+                                         len(ptrs), int(row_base),
+                                         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+          'gg_peer_scatter_cols_f32')
+
+
+def _sliced_spmm(playout, layout, w, local, reduce, bias):
+    """out_r = (A X)[rows of rank r]: column slices out (transposition), full-graph aggregation of this
+    rank's slice, finished rows back to their owners."""
+    part, group = playout.part, playout.group
+    P, per, n = part.world, part.per, part.n
+    rows, f = local.shape
+    fs = sliced_width(f, P)
+    if not fs:
+        raise ValueError(f'feature-sliced exchange needs f % (4*world) == 0 and f/world <= 128 (f={f}, world={P})')
+    b = bias[part.rank * fs:(part.rank + 1) * fs].contiguous() if bias is not None else None
+    if playout.exchange == 'sliced':
+        pool = playout.pool
+        xs = pool.get(('slice', n, fs), n * fs * 4)
+        ob = pool.get(('rows', per, f), per * f * 4)
+        _peer_scatter_cols(local, xs.ptrs, part.lo)
+        pool.barrier()                                       # my slice is complete
+        ops.spmm(layout, xs.view(n, fs), w, reduce, None, 0.0, b,
+                 out_peers=ops.PeerRows([q + part.rank * fs * 4 for q in ob.ptrs], per, f))
+        pool.barrier()                                       # every slice of my rows has landed
+        return ob.view(per, f)[:rows].clone()                # the block is reused by the next exchange
+    # same algorithm over torch.distributed (NCCL / gloo): two all-to-alls around a plain SpMM
+    send = local.new_zeros((P, per, fs))
+    send[:, :rows] = local.reshape(rows, P, fs).permute(1, 0, 2)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
+    out_slice = ops.spmm(layout, recv.view(P * per, fs)[:n].contiguous(), w, reduce, None, 0.0, b)
+    send = out_slice.new_zeros((P * per, fs))
+    send[:n] = out_slice
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
+    return recv.view(P, per, fs).permute(1, 0, 2).reshape(per, f)[:rows].contiguous()
+
+
+class _DistAggregateSliced(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h_local, playout, kind, bias):
+        w_fwd, _ = playout.weights(kind)
+        out = _sliced_spmm(playout, playout.csr, w_fwd, h_local.contiguous(),
+                           ops.MEAN if kind == 'mean' else ops.SUM, bias)
+        ctx.playout, ctx.kind, ctx.has_bias = playout, kind, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g_local):
+        playout = ctx.playout
+        gh = gb = None
+        g_local = g_local.contiguous()
+        if ctx.needs_input_grad[0]:
+            _, w_bwd = playout.weights(ctx.kind)
+            gh = _sliced_spmm(playout, playout.csc, w_bwd, g_local, ops.SUM, None)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            gb = ops.colsum(g_local)
+        return gh, None, None, gb
+
+
 def dist_aggregate(h_local, playout, kind='sum', bias=None):
     """Row-partitioned ``functional.aggregate``: out_r = (A H)[rows of rank r] (+ bias)."""
+    if playout.sliced:
+        return _DistAggregateSliced.apply(h_local, playout, kind, bias)
     if playout.pipelined:
         return _DistAggregatePipelined.apply(h_local, playout, kind, bias)
     return _DistAggregate.apply(h_local, playout, kind, bias)

@@ -159,7 +159,8 @@ int gg_spmm_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, 
  *   gg_spmm_plan_build -> item_row[items+1], item_slot[items+1]
  * gg_spmm_mp_f32 has the semantics of gg_spmm_f32; it needs f % 4 == 0, f <= 1024, 16-byte aligned rows
  * (GG_ERR_UNSUPPORTED otherwise) and a workspace of gg_spmm_mp_workspace_bytes(items, f).
- * stage_mode: bit 0 = plain loads instead of cp.async.bulk staging, bit 1 = deep (16-wide) gather batches.
+ * stage_mode: bit 0 = plain loads instead of cp.async.bulk staging, bit 1 = deep (16-wide) gather batches,
+ * bit 2 = L2 residency hints (feature-row gathers evict_last; index / weight / output streams evict_first).
  * Same fixed summation order per row in every mode.
  * Optional rank-1 epilogue terms (nullable): out[row,:] += r1_s[row]*r1_v[:] + r2_s[row]*r2_v[:]. */
 int gg_spmm_plan_units(int64_t num_rows, int64_t num_slots);
@@ -173,6 +174,27 @@ int gg_spmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slo
                    const float* x_self, int64_t ld_self, float self_scale, const float* bias,
                    const float* r1_s, const float* r1_v, const float* r2_s, const float* r2_v,
                    void* workspace, size_t workspace_bytes, int stage_mode, gg_stream_t stream);
+
+/* Narrow-row variant (f % 4 == 0, f <= 128): the warp's 32 lanes are cut into 32/G groups of
+ * G = gg_spmm_group_lanes(f) lanes and one warp instruction gathers 32/G different slots of the warp's
+ * item; partial sums are combined across the groups at every row end with a fixed shuffle butterfly.
+ * Uses the same plan as gg_spmm_mp_f32; same semantics; the summation order per row is fixed (but is
+ * not the order of gg_spmm_mp_f32).
+ *
+ * Peer output (row-partitioned path; `out_peers_host` non-null, `out` ignored): this rank
+ * aggregates ITS column slice for all `num_rows` global rows and stores row i into the memory of the
+ * rank that owns it: out_peers_host[i / rows_per_rank] + (i % rows_per_rank) * ldo — HOST array of
+ * `world` DEVICE pointers (peer memory from gg_peer_open, already offset to this rank's columns).  The
+ * stores are plain global stores over NVLink: aggregation and the return leg of the exchange are ONE
+ * kernel.  The caller orders it against the peers with gg_peer_barrier.  flags: bit 2 = L2 residency
+ * hints as in gg_spmm_mp_f32. */
+int gg_spmm_group_lanes(int64_t f);
+int gg_spmm_mpg_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, const int32_t* item_row,
+                    const int32_t* item_slot, int64_t items, const float* x, int64_t ldx, float* out,
+                    int64_t ldo, float* const* out_peers_host, int world, int64_t rows_per_rank,
+                    int64_t num_rows, int64_t f, int reduce, const float* x_self, int64_t ld_self,
+                    float self_scale, const float* bias, void* workspace, size_t workspace_bytes, int flags,
+                    gg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense transform with ID-GNN heterogeneous weights:
@@ -341,6 +363,32 @@ int gg_scatter_add_rows_f32(const float* x, int64_t ldx, const int64_t* id, int6
                             float* out, int64_t ldo, gg_stream_t stream);
 int gg_relu_grad_f32(const float* g, int64_t ldg, const float* y, int64_t ldy, int64_t n, int64_t f,
                      float* out, int64_t ldo, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer memory over NVLink / NVSwitch (SURVEY §8e, §8b `gg_halo_*`): the exchange step of the
+ * row-partitioned path.  The reference is single-process; one process per GPU here.
+ *   gg_peer_alloc   cudaMalloc + zero + export: `handle_host` receives gg_peer_handle_bytes() opaque bytes
+ *                   (a CUDA IPC handle) that the host side ships to the other ranks (torch.distributed);
+ *   gg_peer_open    map a peer's buffer into this process -> device pointer usable by any kernel here;
+ *   gg_peer_close / gg_peer_free  undo the two above;
+ *   gg_peer_barrier stream-ordered barrier between the ranks, no host involvement: `flags_host[r]` is rank
+ *                   r's flag block (>= GG_PEER_MAX u32, zero-initialised peer memory); every call uses
+ *                   the next `epoch` (1, 2, ...).  Stores issued on `stream` before the barrier are visible
+ *                   to kernels the peers launch after theirs.  A peer that never arrives traps the launch
+ *                   after ~20 s instead of hanging the GPU;
+ *   gg_peer_scatter_cols_f32   forward leg of the feature-sliced exchange: this rank's rows
+ *                   src[rows, f] are cut into `world` column slices of f/world and slice c is stored into
+ *                   dst_host[c] (rank c's [N, f/world] matrix, peer memory) at rows row_base + i.
+ * ------------------------------------------------------------------------------------------ */
+#define GG_PEER_MAX 8
+int gg_peer_handle_bytes(void);
+int gg_peer_alloc(size_t bytes, void** ptr_host, unsigned char* handle_host);
+int gg_peer_open(const unsigned char* handle_host, void** ptr_host);
+int gg_peer_close(void* ptr);
+int gg_peer_free(void* ptr);
+int gg_peer_barrier(void* const* flags_host, int world, int rank, uint32_t epoch, gg_stream_t stream);
+int gg_peer_scatter_cols_f32(const float* src, int64_t ld, int64_t rows, int64_t f, float* const* dst_host,
+                             int world, int64_t row_base, gg_stream_t stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

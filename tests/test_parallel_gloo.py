@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, pipelined, ret):
+def _worker(rank, world, port, n, exchange, ret, fout=8):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -34,7 +34,7 @@ def _worker(rank, world, port, n, pipelined, ret):
         from util import random_graph
         fake_ops.install(lambda mod, name, fn: setattr(mod, name, fn))
         torch.manual_seed(0)
-        fin, fout = 12, 8
+        fin = 12
         ei = random_graph(3, n, 6 * n, loops=5, dups=7)
         g = torch.Generator().manual_seed(1)
         x = torch.randn(n, fin, generator=g)
@@ -43,7 +43,7 @@ def _worker(rank, world, port, n, pipelined, ret):
         layer = parallel.RowPartitionedGCN(fin, fout, bias=True)   # same seed on every rank
         with torch.no_grad():
             layer.model.bias.uniform_(-0.5, 0.5)
-        playout = parallel.PartitionedLayout(ei, n, ops.LOOPS_ADD_REMAINING, part, pipelined=pipelined)
+        playout = parallel.PartitionedLayout(ei, n, ops.LOOPS_ADD_REMAINING, part, exchange=exchange)
         xl = x[part.lo:part.hi].clone().requires_grad_(True)
         y = layer(xl, playout)
         y.backward(gy[part.lo:part.hi])
@@ -62,12 +62,13 @@ def _worker(rank, world, port, n, pipelined, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('pipelined', [False, True])   # one all-gather vs per-peer send/recv rounds
+# one all-gather | per-peer send/recv rounds | feature-sliced transposition (all-to-all form of the peer-memory path)
+@pytest.mark.parametrize('exchange', ['allgather', 'pipelined', 'sliced_nccl'])
 @pytest.mark.parametrize('n', [40, 41])   # 41: the last rank's block is shorter -> padded exchange
-def test_row_partitioned_gcn_world2(n, pipelined):
+def test_row_partitioned_gcn_world2(n, exchange):
     world = 2
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), n, pipelined, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n, exchange, ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
 
 
@@ -86,5 +87,22 @@ def test_row_partitioned_gcn_world3_pipelined():
     """three ranks: two exchange rounds with different peers per round"""
     world = 3
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), 50, True, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), 50, 'pipelined', ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_row_partitioned_gcn_world3_sliced():
+    """three ranks, 12 output columns -> slices of 4; 50 rows -> the last block is short"""
+    world = 3
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), 50, 'sliced_nccl', ret, 12), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+def test_sliced_width():
+    sys.path.insert(0, os.path.dirname(HERE))
+    from graphgym_b200.parallel import sliced_width
+    assert sliced_width(128, 8) == 16 and sliced_width(128, 2) == 64 and sliced_width(256, 2) == 128
+    assert sliced_width(100, 2) == 0      # 50-column slices are not 16-byte aligned
+    assert sliced_width(512, 2) == 0      # 256-column slices exceed the sub-warp-group kernel
+    assert sliced_width(128, 1) == 128

@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, pipelined, ret):
+def _worker(rank, world, port, exchange, ret):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -45,10 +45,13 @@ def _worker(rank, world, port, pipelined, ret):
             ref.model.bias.uniform_(-0.5, 0.5)
             layer.model.bias.copy_(ref.model.bias)
         part = parallel.RowPartition(n, world, rank)
-        playout = parallel.PartitionedLayout(ei, n, ops.LOOPS_ADD_REMAINING, part, pipelined=pipelined)
+        playout = parallel.PartitionedLayout(ei, n, ops.LOOPS_ADD_REMAINING, part, exchange=exchange)
         xl = x[part.lo:part.hi].clone().requires_grad_(True)
-        y = layer(xl, playout)
-        y.backward(gy[part.lo:part.hi])
+        for _ in range(3 if exchange == 'sliced' else 1):   # the peer buffers are reused: repeat the exchange
+            layer.zero_grad(set_to_none=True)
+            xl.grad = None
+            y = layer(xl, playout)
+            y.backward(gy[part.lo:part.hi])
         parallel.allreduce_grads(layer)
         xr = x.clone().requires_grad_(True)
         yr = ref(Batch(xr, ei)).node_feature
@@ -59,17 +62,20 @@ def _worker(rank, world, port, pipelined, ret):
         # the merge-path plan cuts rank-local rows at other places than the global plan, so rows split
         # over items re-associate their fp32 partial sums; most rows are bitwise the single-GPU rows
         same = (y.detach() == yr.detach()[part.lo:part.hi]).all(dim=1).float().mean().item()
-        ret[rank] = (max(errs) < 1e-5, same > 0.5, errs)
+        # (the sliced exchanges aggregate with the sub-warp-group plan: another, equally fixed, order)
+        ret[rank] = (max(errs) < 1e-5, same > 0.5 or exchange.startswith('sliced'), errs)
+        if playout.pool is not None:
+            playout.pool.close()
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('pipelined', [False, True])
-def test_two_gpu_row_partition_matches_single_gpu(pipelined):
+@pytest.mark.parametrize('exchange', ['allgather', 'pipelined', 'sliced_nccl', 'sliced'])
+def test_two_gpu_row_partition_matches_single_gpu(exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, _free_port(), pipelined, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), exchange, ret), nprocs=2, join=True)
     for r in range(2):
         ok, bitwise, errs = ret[r]
         assert ok, errs

@@ -132,3 +132,100 @@ def test_one_giant_row(cuda, monkeypatch):
     for reduce in (ops.SUM, ops.MEAN):
         got = run(csr, x.to(cuda), None, reduce, 0.0, None, 'mp', 'tma', monkeypatch)
         assert rel_err(got, oracle(ei, x, None, reduce, 0.0, None)) < FP32_TOL
+
+
+# ---- sub-warp-group kernel (narrow rows) and peer-memory output -------------------------------------
+def check_group_plan(csr, f):
+    lanes = int(ops.lib().gg_spmm_group_lanes(f))
+    assert lanes in (4, 8, 16, 32) and lanes * 4 >= f
+    check_plan(csr)
+
+
+@pytest.mark.parametrize('f', [4, 8, 12, 16, 24, 32, 48, 64, 100, 128])
+def test_group_kernel_parity_random(cuda, monkeypatch, f):
+    n = 997
+    ei = random_graph(f, n, 9000, loops=30, dups=40)
+    g = torch.Generator().manual_seed(f)
+    x = torch.randn(n, f, generator=g)
+    w_edge = torch.rand(ei.size(1), generator=g)
+    bias = torch.randn(f, generator=g)
+    csr = ops.layout_build(ei.to(cuda), n, 0, 0)
+    check_group_plan(csr, f)
+    w_slot = w_edge[csr.perm.cpu().long()].to(cuda)
+    for weighted in (False, True):
+        for reduce in (ops.SUM, ops.MEAN):
+            for self_scale, b in ((0.0, None), (1.25, bias)):
+                got = run(csr, x.to(cuda), w_slot if weighted else None, reduce, self_scale,
+                          b.to(cuda) if b is not None else None, 'mpg', 'tma', monkeypatch)
+                want = oracle(ei, x, w_edge if weighted else None, reduce, self_scale, b)
+                assert rel_err(got, want) < FP32_TOL, (f, weighted, reduce, self_scale)
+
+
+@pytest.mark.parametrize('f', [16, 32, 64, 128])
+def test_group_kernel_powerlaw_and_edge_shapes(cuda, monkeypatch, f):
+    n = 60000
+    ei = powerlaw_graph(6, n, 20)
+    x = torch.randn(n, f, generator=torch.Generator().manual_seed(1))
+    csr = ops.layout_build(ei.to(cuda), n, 1, 0)
+    check_group_plan(csr, f)
+    w = ops.gcn_norm(csr, ops.segment_degree(csr))
+    got = run(csr, x.to(cuda), w, ops.SUM, 0.0, None, 'mpg', 'tma', monkeypatch)
+    a = torch.sparse_coo_tensor(torch.stack([csr.rowid.cpu().long(), csr.nbr.cpu().long()]), w.cpu().double(),
+                                (n, n)).coalesce()
+    assert rel_err(got, torch.sparse.mm(a, x.double())) < FP32_TOL
+    assert torch.equal(got, run(csr, x.to(cuda), w, ops.SUM, 0.0, None, 'mpg', 'tma', monkeypatch))   # deterministic
+    # one giant row, marker-only items, no edges
+    e = 30000
+    g = torch.Generator().manual_seed(0)
+    ei2 = torch.stack([torch.randint(0, 300, (e,), generator=g), torch.full((e,), 7)])
+    x2 = torch.randn(300, f, generator=g)
+    csr2 = ops.layout_build(ei2.to(cuda), 300, 0, 0)
+    for reduce in (ops.SUM, ops.MEAN):
+        got = run(csr2, x2.to(cuda), None, reduce, 0.0, None, 'mpg', 'tma', monkeypatch)
+        assert rel_err(got, oracle(ei2, x2, None, reduce, 0.0, None)) < FP32_TOL
+    cl = torch.combinations(torch.arange(0, 40), 2).t()
+    ei3 = torch.cat([cl, cl.flip(0)], dim=1)
+    x3 = torch.randn(20000, f, generator=g)
+    csr3 = ops.layout_build(ei3.to(cuda), 20000, 0, 0)
+    got = run(csr3, x3.to(cuda), None, ops.MEAN, 2.0, None, 'mpg', 'tma', monkeypatch)
+    assert rel_err(got, oracle(ei3, x3, None, ops.MEAN, 2.0, None)) < FP32_TOL
+    for nn in (1, 5):
+        csr4 = ops.layout_build(torch.zeros((2, 0), dtype=torch.int64, device=cuda), nn, 0, 0)
+        x4 = torch.randn(nn, f, generator=g)
+        got = run(csr4, x4.to(cuda), None, ops.SUM, 1.0, None, 'mpg', 'tma', monkeypatch)
+        assert rel_err(got, x4) < FP32_TOL
+
+
+@pytest.mark.parametrize('world,f_total', [(2, 128), (4, 128), (8, 128), (8, 256), (3, 96)])
+def test_peer_output_and_column_scatter_on_one_gpu(cuda, world, f_total):
+    """The two kernels of the feature-sliced exchange with every 'rank' living on this GPU: the column
+    scatter builds each rank's [N, F/P] slice, the peer-output SpMM of slice c stores rows into the
+    owners' [rows_per_rank, F] blocks; stitched together they must equal the plain aggregation."""
+    import ctypes
+    n = 5003
+    fs = f_total // world
+    ei = powerlaw_graph(9, n, 12)
+    g = torch.Generator().manual_seed(world)
+    x = torch.randn(n, f_total, generator=g).to(cuda)
+    bias = torch.randn(f_total, generator=g).to(cuda)
+    csr = ops.layout_build(ei.to(cuda), n, 1, 0)
+    w = ops.gcn_norm(csr, ops.segment_degree(csr))
+    per = (n + world - 1) // world
+    slices = [torch.full((n, fs), float('nan'), device=cuda) for _ in range(world)]
+    L = ops.lib()
+    for r in range(world):   # rank r scatters its rows
+        lo, hi = min(n, r * per), min(n, (r + 1) * per)
+        dst = (ctypes.c_void_p * world)(*[s.data_ptr() for s in slices])
+        ops.check(L.gg_peer_scatter_cols_f32(ctypes.c_void_p(x[lo:hi].data_ptr()), f_total, hi - lo, f_total, dst,
+                                             world, lo, ops._stream()), 'gg_peer_scatter_cols_f32')
+    for c in range(world):
+        assert torch.equal(slices[c], x[:, c * fs:(c + 1) * fs])
+    blocks = [torch.full((per, f_total), float('nan'), device=cuda) for _ in range(world)]
+    for c in range(world):   # rank c aggregates its slice and stores into the owners' blocks
+        peers = ops.PeerRows([b.data_ptr() + c * fs * 4 for b in blocks], per, f_total)
+        assert ops.spmm(csr, slices[c], w, ops.SUM, None, 0.0, bias[c * fs:(c + 1) * fs].clone(),
+                        out_peers=peers) is None
+    got = torch.cat(blocks)[:n]
+    want = ops.spmm(csr, x, w, ops.SUM, None, 0.0, bias)
+    assert not torch.isnan(got).any()
+    assert rel_err(got, want) < FP32_TOL

@@ -63,7 +63,7 @@ SIGNATURES = {
     "gg_peer_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_ptr)]),
     "gg_peer_close": (c_int, [c_ptr]),
     "gg_peer_free": (c_int, [c_ptr]),
-    "gg_peer_barrier": (c_int, [ctypes.POINTER(c_ptr), c_int, c_int, ctypes.c_uint32, c_ptr]),
+    "gg_peer_barrier": (c_int, [ctypes.POINTER(c_ptr), c_int, c_int, c_ptr]),
     "gg_peer_scatter_cols_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, ctypes.POINTER(c_ptr), c_int, c_i64, c_ptr]),
     "gg_id_gemm_f32": (c_int, [ctypes.POINTER(GemmSegment), c_int, c_int, c_i64, c_i64, c_ptr, c_int,
                                c_ptr, c_i64, c_ptr, c_i64, c_ptr]),

@@ -16,9 +16,11 @@ struct PeerPtrs {
 };
 
 // ---- barrier --------------------------------------------------------------------------------------
-// flags[r] lives on rank r: GG_PEER_MAX u32 epochs, slot s written by rank s only.  Thread t signals peer t
-// (release, system scope: every store this stream issued before the barrier is visible to whoever
-// acquires the flag) and then waits until peer t's signal for the same epoch has landed here.
+// flags[r] lives on rank r: u32 slots [0, GG_PEER_MAX) are arrival epochs, slot s written by rank s only;
+// slot GG_PEER_MAX is rank r's own barrier count.  The kernel takes the next epoch from that counter, so a
+// barrier launch carries no host-side state and can be replayed from a CUDA graph.  Thread t signals peer t
+// (release, system scope: every store this stream issued before the barrier is visible to whoever acquires
+// the flag) and then waits until peer t's signal for the same epoch has landed here.
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -28,16 +30,22 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerPtrs flags, int world, int rank, uint32_t epoch,
+__global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant__ PeerPtrs flags, int world, int rank,
                                                           long long timeout_cycles) {
     const int t = threadIdx.x;
+    uint32_t* mine = static_cast<uint32_t*>(flags.p[rank]);
+    uint32_t epoch = 0;
+    if (t == 0) {
+        epoch = mine[GG_PEER_MAX] + 1u;  // only this kernel touches the counter, launches are stream-ordered
+        mine[GG_PEER_MAX] = epoch;
+    }
+    epoch = __shfl_sync(0xffffffffu, epoch, 0);
     if (t >= world || t == rank) return;
     __threadfence_system();
     st_release_sys(static_cast<uint32_t*>(flags.p[t]) + rank, epoch);
-    const uint32_t* mine = static_cast<const uint32_t*>(flags.p[rank]) + t;
     const long long t0 = clock64();
     // epochs only grow; the signed difference keeps the comparison right across a u32 wrap
-    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+    while ((int32_t)(ld_acquire_sys(mine + t) - epoch) < 0) {
         if (clock64() - t0 > timeout_cycles) __trap();  // a lost peer fails the launch instead of hanging the GPU
         __nanosleep(64);
     }
@@ -106,7 +114,7 @@ int gg_peer_free(void* ptr) {
     return GG_OK;
 }
 
-int gg_peer_barrier(void* const* flags_host, int world, int rank, uint32_t epoch, gg_stream_t stream) {
+int gg_peer_barrier(void* const* flags_host, int world, int rank, gg_stream_t stream) {
     GG_REQUIRE(flags_host && world >= 1 && world <= GG_PEER_MAX && rank >= 0 && rank < world,
                "gg_peer_barrier: world=%d rank=%d (at most %d peers)", world, rank, GG_PEER_MAX);
     if (world == 1) return GG_OK;
@@ -116,7 +124,7 @@ int gg_peer_barrier(void* const* flags_host, int world, int rank, uint32_t epoch
         f.p[i] = flags_host[i];
     }
     // ~20 s at 2 GHz: far beyond any healthy skew between ranks, short enough to fail before a box-level timeout
-    peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(f, world, rank, epoch, 40000000000LL);
+    peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(f, world, rank, 40000000000LL);
     GG_LAUNCHED();
     return GG_OK;
 }

@@ -272,7 +272,6 @@ class PeerPool:
         self.device = torch.device('cuda', torch.cuda.current_device())
         self._bufs = {}
         self._owned, self._opened = [], []
-        self.epoch = 0
         self.flags = self._alloc(256)
         self._flag_arr = (ctypes.c_void_p * world)(*self.flags.ptrs)
 
@@ -306,8 +305,7 @@ class PeerPool:
 
     def barrier(self):
         """Stream-ordered: kernels enqueued after it see every store the peers enqueued before theirs."""
-        self.epoch += 1
-        check(lib().gg_peer_barrier(self._flag_arr, self.world, self.rank, self.epoch,
+        check(lib().gg_peer_barrier(self._flag_arr, self.world, self.rank,
                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'gg_peer_barrier')
 
     def close(self):

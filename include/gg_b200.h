@@ -372,8 +372,10 @@ int gg_relu_grad_f32(const float* g, int64_t ldg, const float* y, int64_t ldy, i
  *   gg_peer_open    map a peer's buffer into this process -> device pointer usable by any kernel here;
  *   gg_peer_close / gg_peer_free  undo the two above;
  *   gg_peer_barrier stream-ordered barrier between the ranks, no host involvement: `flags_host[r]` is rank
- *                   r's flag block (>= GG_PEER_MAX u32, zero-initialised peer memory); every call uses
- *                   the next `epoch` (1, 2, ...).  Stores issued on `stream` before the barrier are visible
+ *                   r's flag block (>= GG_PEER_MAX + 1 u32, zero-initialised peer memory; the last word counts
+ *                   this rank's barriers on the device, so a launch carries no host state and replays from a
+ *                   CUDA graph).  Every rank must issue the same sequence of barriers.  Stores issued on
+ *                   `stream` before the barrier are visible
  *                   to kernels the peers launch after theirs.  A peer that never arrives traps the launch
  *                   after ~20 s instead of hanging the GPU;
  *   gg_peer_scatter_cols_f32   forward leg of the feature-sliced exchange: this rank's rows
@@ -386,7 +388,7 @@ int gg_peer_alloc(size_t bytes, void** ptr_host, unsigned char* handle_host);
 int gg_peer_open(const unsigned char* handle_host, void** ptr_host);
 int gg_peer_close(void* ptr);
 int gg_peer_free(void* ptr);
-int gg_peer_barrier(void* const* flags_host, int world, int rank, uint32_t epoch, gg_stream_t stream);
+int gg_peer_barrier(void* const* flags_host, int world, int rank, gg_stream_t stream);
 int gg_peer_scatter_cols_f32(const float* src, int64_t ld, int64_t rows, int64_t f, float* const* dst_host,
                              int world, int64_t row_base, gg_stream_t stream);
 

@@ -62,8 +62,8 @@ def _worker(rank, world, port, exchange, ret):
         # the merge-path plan cuts rank-local rows at other places than the global plan, so rows split
         # over items re-associate their fp32 partial sums; most rows are bitwise the single-GPU rows
         same = (y.detach() == yr.detach()[part.lo:part.hi]).all(dim=1).float().mean().item()
-        # (the sliced exchanges aggregate with the sub-warp-group plan: another, equally fixed, order)
-        ret[rank] = (max(errs) < 1e-5, same > 0.5 or exchange.startswith('sliced'), errs)
+        # (only the all-gather form: per-peer partial sums and the narrow-row kernel use other, equally fixed, orders)
+        ret[rank] = (max(errs) < 1e-5, same > 0.5 or exchange != 'allgather', errs)
         if playout.pool is not None:
             playout.pool.close()
     finally:

@@ -44,6 +44,14 @@ WORKLOADS = {
     # configs[1]: Cora-shaped, fits L2 entirely -> launch-bound, reported for completeness
     'cora_gcn': dict(layer='gcnconv', graph='uniform', n=2708, e_und=5278, fin=1433, fout=128,
                      desc='gcnconv 1433->128 on Cora-shaped graph (2708 nodes, 10556 directed edges)'),
+    # configs[2] first half: ID-GNN Fast cycle-count augmentation diag(A_hat^p), p = 1..10, on the BA graph
+    'ba1m_cycles': dict(aux='cycles', graph='ba', n=1_000_000, m=5, k=10,
+                        desc='ID-GNN Fast cycle features diag(A_hat^1..10) on BA graph (1M nodes, 10M directed '
+                             'edges): blocks of 128 source nodes, 5 hops each (half-power trick)'),
+    # configs[4] / configs[0] shape: ID-GNN Full — batched 3-hop ego-net extraction, then 3 GIN-ID layers, 256 hidden
+    'ego_idgin': dict(aux='ego', graph='ba_batch', graphs=256, nodes_per_graph=64, m=4, radius=3, hidden=256,
+                      layers=3, desc='ID-GNN Full: 3-hop ego-nets of every node of 256 BA graphs x 64 nodes '
+                                     '(reference dataset shape), then 3 ginidconv layers 256->256 fwd+bwd'),
 }
 DEFAULT_WORKLOAD = 'products_gcn'
 DEFAULT_HALO = 'sliced'
@@ -188,6 +196,126 @@ def loop_policy_for(layer_name):
             'ginidconv': ops.LOOPS_REMOVE}.get(layer_name, ops.LOOPS_KEEP)
 
 
+def _event_ms(fn, steps, warmup):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / steps
+
+
+def gen_ba_batch(spec, device, seed=0):
+    """Block-diagonal batch of small BA graphs (the reference's synthetic datasets are 64-node graphs,
+    ref: syn_graph.py): -> n, edge_index [2,E] int64 symmetric, graph_ptr [G+1]."""
+    G, nn_, m0 = spec['graphs'], spec['nodes_per_graph'], spec['m']
+    g = torch.Generator(device=device).manual_seed(seed)
+    t = torch.arange(m0, nn_, device=device).repeat_interleave(m0)            # arriving node of every edge
+    # preferential attachment approximated per graph by sampling an earlier node with weight ~ (1 + index^-0.5)
+    r = torch.rand((G, t.numel()), device=device, generator=g)
+    tgt = (r * r * t.unsqueeze(0)).long().clamp(max=nn_ - 1)                  # skewed towards early (high-degree) nodes
+    tgt = torch.minimum(tgt, t.unsqueeze(0) - 1)
+    off = (torch.arange(G, device=device) * nn_).unsqueeze(1)
+    a = (t.unsqueeze(0) + off).reshape(-1)
+    b = (tgt + off).reshape(-1)
+    code = torch.unique(torch.minimum(a, b) * (G * nn_) + torch.maximum(a, b))   # simple graphs: no duplicate edges
+    a, b = code // (G * nn_), code % (G * nn_)
+    ei = torch.stack([torch.cat([a, b]), torch.cat([b, a])]).contiguous()
+    return G * nn_, ei, torch.arange(G + 1, device=device, dtype=torch.int32) * nn_
+
+
+def run_aux(args, spec, dev):
+    """Secondary hot-path rows: their own units, same JSON shape."""
+    from graphgym_b200 import ops
+    from graphgym_b200.contrib.transform import identity as gid
+    from graphgym_b200.models import transform as gtr
+    from graphgym_b200.models.layer import Batch, layer_dict
+    peak, peak_src = load_peaks()
+    clocks = ClockSampler(dev.index or 0)
+    if spec['aux'] == 'cycles':
+        n, ei = gen_graph(spec, dev, seed=0)
+        k = spec['k']
+        csr = ops.layout_build(ei, n, ops.LOOPS_ADD_REMAINING, ops.BY_TARGET)
+        csc = ops.layout_build(ei, n, ops.LOOPS_ADD_REMAINING, ops.BY_SOURCE)
+        w = ops.gcn_norm(csr, ops.segment_degree(csc))
+        L = ops.lib()
+        ws = torch.empty(int(L.gg_cycle_diag_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+        out = torch.empty((128, k), dtype=torch.float32, device=dev)
+        blk = [0]
+
+        def one_block():   # 128 consecutive sources: 5 hops over the whole graph + 10 dot products
+            sb = (blk[0] * 128) % (n - 128)
+            blk[0] += 1
+            ops.check(L.gg_cycle_diag_f32(ops._ptr(csr.rowptr), ops._ptr(csr.nbr), ops._ptr(w), 0, n, k, 1, sb, 128,
+                                          ops._ptr(out), k, ops._ptr(ws), ws.numel(), ops._stream()), 'gg_cycle_diag_f32')
+        launches0 = ops.launch_count()
+        with clocks:
+            ms = _event_ms(one_block, args.steps, args.warmup)
+        launches = (ops.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+        hops = (k + 1) // 2
+        slots = csr.num_slots
+        visits = slots * 128 * hops
+        step_bytes = hops * (slots * 512 + n * 512 + slots * 8 + (n + 1) * 4) + k * 2 * n * 512
+        ach = step_bytes / (ms * 1e-3) / 1e9
+        return {'metric': 'cycle-feature edge-visits/s (one visit = one slot x one source column x one hop)',
+                'value': round(visits / (ms * 1e-3) / 1e9, 3), 'unit': 'G edge-visits/s', 'n_gpus': 1,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms, 4), 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (seeded BA generator in bench.py)',
+                'config': {'workload': spec['desc'], 'nodes': n, 'slots': slots, 'k': k, 'sources_per_step': 128,
+                           'whole_graph_seconds_1gpu': round(ms * 1e-3 * (n / 128), 1),
+                           'l2_policy': 'inputs larger than L2 (two 512 MB walk matrices)'},
+                'clocks': clocks.summary(), 'e2e': None, 'gpu_launches': int(launches),
+                'roofline': {'bound': 'hbm', 'kernel': 'walk_step_kernel (+ walk_dot) over one block of 128 sources',
+                             'achieved': round(ach, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4),
+                             'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_step': step_bytes},
+                'cpu_baseline': None}
+    # ---- ID-GNN Full ----
+    n, ei, gptr = gen_ba_batch(spec, dev)
+    radius, hid, nl = spec['radius'], spec['hidden'], spec['layers']
+    res = gtr.ego_nets_batch(ei, n, radius, gptr)     # warm + sizes
+    torch.cuda.synchronize()
+    with clocks:
+        ego_ms = _event_ms(lambda: gtr.ego_nets_batch(ei, n, radius, gptr), max(3, args.steps // 2), 2)
+        n_out, e_out = res['num_nodes'], int(res['edge_index'].size(1))
+        torch.manual_seed(0)
+        layers = [layer_dict['ginidconv'](hid, hid, bias=True).to(dev) for _ in range(nl)]
+        x = gen_features(n_out, hid, dev)
+        gy = gen_features(n_out, hid, dev, seed=7)
+        eo, ids = res['edge_index'], res['node_id_index']
+
+        def step():
+            for l in layers:
+                l.zero_grad(set_to_none=True)
+            h = x.detach().requires_grad_(True)
+            b = Batch(h, eo, ids)
+            for l in layers:
+                b = l(b)
+                b.node_feature = torch.relu(b.node_feature)   # GeneralLayer's activation (ref: layer.py:31-33)
+            b.node_feature.backward(gy)
+        launches0 = ops.launch_count()
+        ms = _event_ms(step, args.steps, args.warmup)
+    launches = (ops.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+    ef = e_out * hid * 2 * nl
+    ego_bytes = e_out * 8 + n_out * 8 + int(ei.size(1)) * 4   # output edges (2 x int64 written) + ids + adjacency read
+    return {'metric': 'layer fwd+bwd GEdge-feat/s', 'value': round(ef / (ms * 1e-3) / 1e9, 3), 'unit': 'GEdge-feat/s',
+            'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms, 4),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic (seeded BA-batch generator in bench.py; random-init weights)',
+            'config': {'workload': spec['desc'], 'centres': n, 'ego_batch_nodes': n_out, 'ego_batch_edges_directed': e_out,
+                       'hidden': hid, 'layers': nl,
+                       'l2_policy': 'inputs larger than L2 (feature matrix %.0f MB)' % (n_out * hid * 4 / 1e6)},
+            'clocks': clocks.summary(), 'e2e': None, 'gpu_launches': int(launches),
+            'ego_extraction': {'ms': round(ego_ms, 3), 'centres_per_s': round(n / (ego_ms * 1e-3), 1),
+                               'output_edges_per_s': round(e_out / (ego_ms * 1e-3), 1),
+                               'output_GBps': round(ego_bytes / (ego_ms * 1e-3) / 1e9, 2),
+                               'includes': 'adjacency layout build, sizes pass, fill pass (two kernel launches + scans)'},
+            'roofline': None, 'cpu_baseline': None}
+
+
 def run_ours(args, spec, rank, world, dev):
     import torch.distributed as dist
 
@@ -197,8 +325,8 @@ def run_ours(args, spec, rank, world, dev):
     name, fin, fout = spec['layer'], spec['fin'], spec['fout']
     multi = world > 1
     if multi:
-        if name != 'gcnconv':
-            raise SystemExit(f'--gpus {world}: the row-partitioned path is wired for gcnconv workloads '
+        if name not in parallel.ROW_PARTITIONED:
+            raise SystemExit(f'--gpus {world}: the row-partitioned path serves {sorted(parallel.ROW_PARTITIONED)} '
                              f'(got {name}); run this workload with --gpus 1')
         dist.init_process_group('nccl', device_id=dev)
     t0 = time.time()
@@ -211,7 +339,7 @@ def run_ours(args, spec, rank, world, dev):
     torch.manual_seed(0)
     part = parallel.RowPartition(n, world, rank)
     if multi:
-        layer = parallel.RowPartitionedGCN(fin, fout, bias=True).to(dev)
+        layer = parallel.ROW_PARTITIONED[name][0](fin, fout, bias=True).to(dev)
         x_loc, gy_loc = x[part.lo:part.hi].contiguous(), gy[part.lo:part.hi].contiguous()
     else:
         layer = layer_dict[name](fin, fout, bias=True).to(dev)
@@ -277,10 +405,12 @@ def run_ours(args, spec, rank, world, dev):
     # allgather | pipelined (per-peer send/recv rounds) | sliced (feature-sliced transposition over peer memory,
     # SpMM epilogue stores to the owners) | sliced_nccl (same over all_to_all)
     halo = os.environ.get('GG_HALO', DEFAULT_HALO)
-    if multi and halo.startswith('sliced') and not parallel.sliced_width(fout, world):
+    agg_kind = parallel.ROW_PARTITIONED[name][2] if multi else None
+    f_exchanged = fout if name == 'gcnconv' else fin
+    if multi and halo.startswith('sliced') and not parallel.sliced_width(f_exchanged, world):
         halo = 'allgather'
     mk_layout = lambda e: parallel.PartitionedLayout(e, n, policy, part, exchange=halo)
-    warm_weights = lambda pl: pl.sub_weights('gcn_tgt') if pl.pipelined else pl.weights('gcn_tgt')
+    warm_weights = lambda pl: pl.sub_weights(agg_kind) if pl.pipelined else pl.weights(agg_kind)
     if multi:
         playout = mk_layout(ei)
         warm_weights(playout)
@@ -519,6 +649,8 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     if args.impl == 'reference':
+        if spec.get('aux'):
+            raise SystemExit('--impl reference covers the layer workloads')
         out = run_reference(args, spec, rank, world)
         if out is not None:
             emit(out)
@@ -529,7 +661,12 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', 0))
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
-    out = run_ours(args, spec, rank, world, dev)
+    if spec.get('aux'):
+        if world > 1:
+            raise SystemExit('the secondary workloads shard by independent units: run them with --gpus 1')
+        out = run_aux(args, spec, dev)
+    else:
+        out = run_ours(args, spec, rank, world, dev)
     if rank == 0:
         emit(out)
 

@@ -381,6 +381,57 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
     }
 }
 
+// Vector variant (f % 4 == 0, f <= 128, 16-byte aligned rows): a warp covers one row per 128-bit load, eight
+// rows in flight per warp; warps are combined in shared memory in a fixed order.
+__global__ void __launch_bounds__(256) colsum_partial_vec_kernel(const float* __restrict__ g, int64_t ldg, int64_t n,
+                                                                 int nvec, int64_t chunk, float* __restrict__ part) {
+    __shared__ float4 s_acc[8][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t r_beg = (int64_t)blockIdx.x * chunk;
+    const int64_t r_end = r_beg + chunk < n ? r_beg + chunk : n;
+    float4 acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < nvec) {
+        int64_t r = r_beg + wid;
+        for (; r + 56 < r_end; r += 64) {  // rows r, r+8, ..., r+56: eight independent loads
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = ldg_nc_f4(reinterpret_cast<const float4*>(g + (r + 8 * u) * ldg) + lane);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) add4(acc[u & 3], v[u]);
+        }
+        for (; r < r_end; r += 8) add4(acc[0], ldg_nc_f4(reinterpret_cast<const float4*>(g + r * ldg) + lane));
+    }
+    add4(acc[0], acc[1]);
+    add4(acc[2], acc[3]);
+    add4(acc[0], acc[2]);
+    s_acc[wid][lane] = acc[0];
+    __syncthreads();
+    if (wid == 0 && lane < nvec) {
+        float4 t = s_acc[0][lane];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) add4(t, s_acc[q][lane]);
+        reinterpret_cast<float4*>(part + (int64_t)blockIdx.x * (nvec * 4))[lane] = t;
+    }
+}
+// out[c] = sum_b part[b][c] in block order, four independent chains per thread
+__global__ void __launch_bounds__(128) colsum_final_kernel(const float* __restrict__ part, int64_t blocks, int f,
+                                                           float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= f) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int64_t b = 0;
+    for (; b + 3 < blocks; b += 4) {
+        a0 += part[b * f + c];
+        a1 += part[(b + 1) * f + c];
+        a2 += part[(b + 2) * f + c];
+        a3 += part[(b + 3) * f + c];
+    }
+    for (; b < blocks; ++b) a0 += part[b * f + c];
+    out[c] = (a0 + a1) + (a2 + a3);
+}
+
 static int64_t colsum_blocks(int64_t n) {
     int64_t b = ceil_div(n, 256);
     int64_t cap = (int64_t)kNumSMs * 8;
@@ -533,6 +584,19 @@ int gg_colsum_f32(const float* g, int64_t ldg, int64_t n, int64_t f, float* out,
     int64_t chunk = ceil_div(n, blocks);
     blocks = ceil_div(n, chunk);
     float* part = static_cast<float*>(workspace);
+    if (f % 4 == 0 && f <= 128 && ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+        int64_t vb = ceil_div(n, 512);  // >= 64 rows per warp before a block is worth launching
+        if (vb > (int64_t)kNumSMs * 4) vb = (int64_t)kNumSMs * 4;
+        if (vb > blocks) vb = blocks;   // the workspace is sized for `blocks` partial rows
+        if (vb < 1) vb = 1;
+        const int64_t vchunk = ceil_div(n, vb);
+        vb = ceil_div(n, vchunk);
+        colsum_partial_vec_kernel<<<(int)vb, 256, 0, st>>>(g, ldg, n, (int)(f / 4), vchunk, part);
+        GG_LAUNCHED();
+        colsum_final_kernel<<<(int)ceil_div(f, 128), 128, 0, st>>>(part, vb, (int)f, out);
+        GG_LAUNCHED();
+        return GG_OK;
+    }
     int threads = f >= 256 ? 256 : (int)(ceil_div(f, 32) * 32);
     colsum_partial_kernel<<<(int)blocks, threads, 0, st>>>(g, ldg, n, f, chunk, part);
     GG_LAUNCHED();

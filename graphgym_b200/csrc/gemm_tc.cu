@@ -192,24 +192,39 @@ __device__ __forceinline__ uint32_t tc_free_parity(int i, int z) { return (uint3
 constexpr int TC_ROLE_THREADS = 128;
 constexpr int TC_BLOCK = 2 * TC_ROLE_THREADS + 32;
 
-// ---- NN kernel shared-memory plan: raw ring (3 x 8 KB) | A operand stages (2 x 16 KB) | B ring (3 x 16 KB)
-constexpr int NN_RAW_SLOTS = 3, NN_A_STAGES = 2, NN_B_SLOTS = 3;
+// ---- NN kernel shared-memory plan: raw ring (5 x 8 KB) | A_lo stages (2 x 8 KB) | B ring (3 x 16 KB)
+// The raw fp32 slab IS the hi operand: the loaders already write it in the canonical layout and the tensor
+// core reads only the TF32 bits of every word (truncation), so hi = trunc_tf32(x) costs nothing.  The
+// converters only produce lo = x - trunc_tf32(x) (exact in fp32; <= 13 significant bits, of which the
+// hardware keeps the top 11): |x - hi - lo_tf32| <= 2^-21 |x|, biased towards zero by ~2^-22 on average —
+// two orders of magnitude inside the 1e-5 parity band.  A scaled (ID) segment is scaled in place first.
+#ifndef GG_TC_CTAS_PER_SM
+#define GG_TC_CTAS_PER_SM 3
+#endif
+#if GG_TC_CTAS_PER_SM == 3
+constexpr int NN_RAW_SLOTS = 3, NN_A_STAGES = 2, NN_B_SLOTS = 2;   // 72 KB: three CTAs per SM
+#else
+constexpr int NN_RAW_SLOTS = 5, NN_A_STAGES = 2, NN_B_SLOTS = 3;   // 104 KB: two CTAs per SM
+#endif
 constexpr int NN_RAW_BYTES = TC_TILE_BYTES;
 constexpr int NN_OFF_A = NN_RAW_SLOTS * NN_RAW_BYTES;
-constexpr int NN_OFF_B = NN_OFF_A + NN_A_STAGES * 2 * TC_TILE_BYTES;
-constexpr int NN_SMEM_BYTES = NN_OFF_B + NN_B_SLOTS * 2 * TC_TILE_BYTES;  // 104 KB: two CTAs per SM
+constexpr int NN_OFF_B = NN_OFF_A + NN_A_STAGES * TC_TILE_BYTES;
+constexpr int NN_RING_BYTES = NN_OFF_B + NN_B_SLOTS * 2 * TC_TILE_BYTES;
 constexpr int TC_EPI_STRIDE = TC_BN + 4;
-static_assert(TC_BM * TC_EPI_STRIDE * 4 <= NN_SMEM_BYTES, "epilogue tile must fit in the operand rings");
+constexpr int NN_EPI_BYTES = TC_BM * TC_EPI_STRIDE * 4;  // the epilogue tile reuses the rings
+constexpr int NN_SMEM_BYTES = NN_RING_BYTES > NN_EPI_BYTES ? NN_RING_BYTES : NN_EPI_BYTES;
+
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 template <bool VEC_A>
-__global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_kernel(TcArgs g) {
+__global__ void __launch_bounds__(TC_BLOCK, GG_TC_CTAS_PER_SM) tc_gemm_kernel(TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t raw_full[NN_RAW_SLOTS], raw_empty[NN_RAW_SLOTS];
     __shared__ __align__(8) uint64_t op_full[NN_A_STAGES], a_free[NN_A_STAGES];
     __shared__ __align__(8) uint64_t b_full[NN_B_SLOTS], b_free[NN_B_SLOTS];
     __shared__ __align__(8) uint64_t all_done;
     __shared__ uint32_t tmem_base_smem;
-    __shared__ int s_slabs[GG_GEMM_MAX_SEGMENTS];
+    __shared__ int s_slabs[GG_GEMM_MAX_SEGMENTS + 1];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
@@ -218,7 +233,7 @@ __global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_kernel(TcArgs g) {
     if (tid == 0) {
         for (int i = 0; i < NN_RAW_SLOTS; ++i) {
             tc_mbar_init(&raw_full[i], TC_ROLE_THREADS);
-            tc_mbar_init(&raw_empty[i], TC_ROLE_THREADS);
+            tc_mbar_init(&raw_empty[i], 1);
         }
         for (int i = 0; i < NN_A_STAGES; ++i) {
             tc_mbar_init(&op_full[i], TC_ROLE_THREADS);
@@ -229,6 +244,7 @@ __global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_kernel(TcArgs g) {
             tc_mbar_init(&b_free[i], 1);
         }
         tc_mbar_init(&all_done, 1);
+        s_slabs[GG_GEMM_MAX_SEGMENTS] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {  // TMEM: 128 fp32 accumulator columns for this CTA
@@ -261,100 +277,120 @@ __global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_kernel(TcArgs g) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
-    int seg_slabs[GG_GEMM_MAX_SEGMENTS];
     int total = 0;
 #pragma unroll
-    for (int sg = 0; sg < GG_GEMM_MAX_SEGMENTS; ++sg) {
-        seg_slabs[sg] = s_slabs[sg];
-        total += seg_slabs[sg];
-    }
-    // slab i of the flattened sequence -> (segment, slab inside the segment)
-    auto locate = [&](int i, int& sg, int& ks) {
-        sg = 0;
-#pragma unroll
-        for (int t = 0; t < GG_GEMM_MAX_SEGMENTS - 1; ++t)
-            if (i >= seg_slabs[sg] && sg < GG_GEMM_MAX_SEGMENTS - 1) { i -= seg_slabs[sg]; ++sg; }
-        ks = i;
+    for (int sg = 0; sg < GG_GEMM_MAX_SEGMENTS; ++sg) total += s_slabs[sg];
+    // walking the flattened slab sequence: (sg, ks) = segment and slab inside it; s_slabs[MAX] = 0 ends the skip
+    int sg = 0, ks = 0, seg_left = s_slabs[0];
+    auto skip_empty = [&]() {
+        while (seg_left == 0 && sg < GG_GEMM_MAX_SEGMENTS - 1) seg_left = s_slabs[++sg];
     };
+    auto advance = [&]() {
+        ++ks;
+        if (--seg_left == 0) { ks = 0; skip_empty(); }
+    };
+    skip_empty();
 
     if (warp < 4) {
-        // ===== loaders: this thread's row, 64 B per slab, straight into the raw ring =====
+        // ===== loaders: this thread's row, 64 B per slab, straight into the raw ring (= the hi operand) =====
+        int slot = 0, round = 0;
         for (int i = 0; i < total; ++i) {
-            const int slot = i % NN_RAW_SLOTS;
-            if (i >= NN_RAW_SLOTS) tc_mbar_wait(&raw_empty[slot], tc_free_parity(i, NN_RAW_SLOTS));
-            int sg, ks;
-            locate(i, sg, ks);
+            if (round > 0) tc_mbar_wait(&raw_empty[slot], (uint32_t)(round - 1) & 1u);
             const TcSegment& s = g.seg[sg];
             const float* arow = s.a + (row_ok ? grow : 0) * s.lda;
             uint8_t* dst = smem + slot * NN_RAW_BYTES + my_row * 16;
+            const int k0 = ks * TC_BK;
+            if (VEC_A && row_ok && k0 + TC_BK <= s.k) {  // interior slab: four full 16-byte copies
 #pragma unroll
-            for (int c = 0; c < TC_BK / 4; ++c) {
-                const int k = ks * TC_BK + c * 4;
-                if (VEC_A) {
-                    const int left = row_ok ? (s.k - k) * 4 : 0;
-                    tc_cp_async16(dst + c * TC_LBO, arow + (k < s.k ? k : 0), left >= 16 ? 16u : (left > 0 ? (uint32_t)left : 0u));
-                } else {
+                for (int c = 0; c < TC_BK / 4; ++c) tc_cp_async16(dst + c * TC_LBO, arow + k0 + c * 4, 16u);
+            } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const bool ok = row_ok && k + e < s.k;
-                        tc_cp_async4(dst + c * TC_LBO + e * 4, arow + (ok ? k + e : 0), ok ? 4u : 0u);
+                for (int c = 0; c < TC_BK / 4; ++c) {
+                    const int k = k0 + c * 4;
+                    if (VEC_A) {
+                        const int left = row_ok ? (s.k - k) * 4 : 0;
+                        tc_cp_async16(dst + c * TC_LBO, arow + (k < s.k ? k : 0), left >= 16 ? 16u : (left > 0 ? (uint32_t)left : 0u));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const bool ok = row_ok && k + e < s.k;
+                            tc_cp_async4(dst + c * TC_LBO + e * 4, arow + (ok ? k + e : 0), ok ? 4u : 0u);
+                        }
                     }
                 }
             }
             tc_cp_async_arrive(&raw_full[slot]);
+            if (++slot == NN_RAW_SLOTS) { slot = 0; ++round; }
+            advance();
         }
     } else if (warp < 8) {
-        // ===== converters: raw slab -> scale, hi/lo split -> operand stage =====
+        // ===== converters: lo = x - trunc_tf32(x) into the lo stage (an ID segment scales the slab in place first) =====
+        int slot = 0, round = 0;
         for (int i = 0; i < total; ++i) {
-            const int slot = i % NN_RAW_SLOTS, stage = i % NN_A_STAGES;
-            int sg, ks;
-            locate(i, sg, ks);
-            const float sc = seg_scale[sg];
-            tc_mbar_wait(&raw_full[slot], tc_full_parity(i, NN_RAW_SLOTS));
+            const int stage = i & (NN_A_STAGES - 1);
+            const float sc = seg_scale[0] * (sg == 0) + seg_scale[1] * (sg == 1) + seg_scale[2] * (sg == 2) +
+                             seg_scale[3] * (sg == 3);
+            const bool scaled = g.seg[sg].scale != nullptr;
+            tc_mbar_wait(&raw_full[slot], (uint32_t)round & 1u);
+            uint8_t* raw = smem + slot * NN_RAW_BYTES + my_row * 16;
             float4 v[TC_BK / 4];
 #pragma unroll
-            for (int c = 0; c < TC_BK / 4; ++c)
-                v[c] = *reinterpret_cast<const float4*>(smem + slot * NN_RAW_BYTES + c * TC_LBO + my_row * 16);
-            tc_arrive(&raw_empty[slot]);
-            if (i >= NN_A_STAGES) tc_mbar_wait(&a_free[stage], tc_free_parity(i, NN_A_STAGES));
-            uint8_t* st = smem + NN_OFF_A + stage * 2 * TC_TILE_BYTES;
+            for (int c = 0; c < TC_BK / 4; ++c) v[c] = *reinterpret_cast<const float4*>(raw + c * TC_LBO);
+            if (scaled) {
+#pragma unroll
+                for (int c = 0; c < TC_BK / 4; ++c) {
+                    v[c].x *= sc; v[c].y *= sc; v[c].z *= sc; v[c].w *= sc;
+                    *reinterpret_cast<float4*>(raw + c * TC_LBO) = v[c];
+                }
+            }
+            if (i >= NN_A_STAGES) tc_mbar_wait(&a_free[stage], (uint32_t)(i / NN_A_STAGES - 1) & 1u);
+            uint8_t* st = smem + NN_OFF_A + stage * TC_TILE_BYTES + my_row * 16;
 #pragma unroll
             for (int c = 0; c < TC_BK / 4; ++c) {
-                float4 h, l;
-                split_tf32(v[c].x * sc, h.x, l.x);
-                split_tf32(v[c].y * sc, h.y, l.y);
-                split_tf32(v[c].z * sc, h.z, l.z);
-                split_tf32(v[c].w * sc, h.w, l.w);
-                const int off = c * (int)TC_LBO + my_row * 16;
-                *reinterpret_cast<float4*>(st + off) = h;
-                *reinterpret_cast<float4*>(st + TC_TILE_BYTES + off) = l;
+                float4 l;
+                l.x = v[c].x - trunc_tf32(v[c].x);
+                l.y = v[c].y - trunc_tf32(v[c].y);
+                l.z = v[c].z - trunc_tf32(v[c].z);
+                l.w = v[c].w - trunc_tf32(v[c].w);
+                *reinterpret_cast<float4*>(st + c * TC_LBO) = l;
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic smem writes -> async proxy
+            // generic-proxy writes (the loaders' cp.async data this thread has observed, and the stores above)
+            // -> visible to the tensor core's async-proxy reads
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_arrive(&op_full[stage]);
+            if (++slot == NN_RAW_SLOTS) { slot = 0; ++round; }
+            advance();
         }
     } else if (lane == 0) {
         // ===== issuer: B image slabs by TMA (two ahead), then the six MMAs of every slab =====
+        int bsg = sg, bks = ks, bleft = seg_left;  // the B prefetch runs two slabs ahead with its own cursor
         auto issue_b = [&](int i) {
-            int sg, ks;
-            locate(i, sg, ks);
-            const TcSegment& s = g.seg[sg];
-            const float* src = s.b_image + ((int64_t)nt * s.k_slabs + ks) * (2 * TC_TILE_BYTES / 4);
+            const TcSegment& s = g.seg[bsg];
+            const float* src = s.b_image + ((int64_t)nt * s.k_slabs + bks) * (2 * TC_TILE_BYTES / 4);
             const int slot = i % NN_B_SLOTS;
             tc_expect_tx(&b_full[slot], 2 * TC_TILE_BYTES);
             tc_bulk_g2s(smem + NN_OFF_B + slot * 2 * TC_TILE_BYTES, src, 2 * TC_TILE_BYTES, &b_full[slot]);
+            ++bks;
+            if (--bleft == 0) {
+                bks = 0;
+                while (bleft == 0 && bsg < GG_GEMM_MAX_SEGMENTS - 1) bleft = s_slabs[++bsg];
+            }
         };
-        if (total > 0) issue_b(0);
-        if (total > 1) issue_b(1);
+        constexpr int kAhead = NN_B_SLOTS - 1;  // B slabs in flight ahead of the MMA
+        for (int i = 0; i < kAhead && i < total; ++i) issue_b(i);
+        int rslot = 0;
         for (int i = 0; i < total; ++i) {
-            const int stage = i % NN_A_STAGES, slot = i % NN_B_SLOTS;
-            if (i + 2 < total) {  // slot (i+2)%3 was last read by slab i-1
-                if (i + 2 >= NN_B_SLOTS) tc_mbar_wait(&b_free[(i + 2) % NN_B_SLOTS], tc_free_parity(i + 2, NN_B_SLOTS));
-                issue_b(i + 2);
+            const int stage = i & (NN_A_STAGES - 1), slot = i % NN_B_SLOTS;
+            if (i + kAhead < total) {  // slot (i+kAhead) % NN_B_SLOTS was last read by slab i-1
+                if (i + kAhead >= NN_B_SLOTS)
+                    tc_mbar_wait(&b_free[(i + kAhead) % NN_B_SLOTS], tc_free_parity(i + kAhead, NN_B_SLOTS));
+                issue_b(i + kAhead);
             }
             tc_mbar_wait(&op_full[stage], tc_full_parity(i, NN_A_STAGES));
             tc_mbar_wait(&b_full[slot], tc_full_parity(i, NN_B_SLOTS));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = tc_smem_u32(smem + NN_OFF_A + stage * 2 * TC_TILE_BYTES), a_lo = a_hi + TC_TILE_BYTES;
+            const uint32_t a_hi = tc_smem_u32(smem + rslot * NN_RAW_BYTES);
+            const uint32_t a_lo = tc_smem_u32(smem + NN_OFF_A + stage * TC_TILE_BYTES);
             const uint32_t b_hi = tc_smem_u32(smem + NN_OFF_B + slot * 2 * TC_TILE_BYTES), b_lo = b_hi + TC_TILE_BYTES;
 #pragma unroll
             for (int j = 0; j < TC_BK / 8; ++j) {  // one MMA consumes 8 k = two 16-byte chunks
@@ -363,8 +399,10 @@ __global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_kernel(TcArgs g) {
                 tc_mma(tmem_base, tc_smem_desc(a_hi + ko), tc_smem_desc(b_lo + ko), 1u);
                 tc_mma(tmem_base, tc_smem_desc(a_lo + ko), tc_smem_desc(b_hi + ko), 1u);
             }
+            tc_commit(&raw_empty[rslot]);
             tc_commit(&a_free[stage]);
             tc_commit(&b_free[slot]);
+            if (++rslot == NN_RAW_SLOTS) rslot = 0;
         }
         tc_commit(&all_done);  // completes when every MMA issued above has completed
     }
@@ -405,6 +443,18 @@ __global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_kernel(TcArgs g) {
                          (!g.relu_mask || (g.ld_mask % 4 == 0 && (reinterpret_cast<uintptr_t>(g.relu_mask) & 15) == 0)) &&
                          (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0);
     const int c = nt * TC_BN + lane * 4;  // this lane's 4 columns
+    const bool plain = vec_out && !g.accumulate_out &&
+                       (!g.final_chunk || (!g.bias && g.act != GG_ACT_RELU && !g.relu_mask));
+    if (plain) {  // nothing to fuse: per row one 128-bit shared load and one 128-bit coalesced store per lane
+        if (c + 3 < g.f) {
+            const int rows = (int)(g.n - row0 < TC_BM ? g.n - row0 : TC_BM);
+            float* orow = g.out + (row0 + warp) * g.ldo + c;
+#pragma unroll 4
+            for (int rr = warp; rr < rows; rr += 8, orow += 8 * g.ldo)
+                *reinterpret_cast<float4*>(orow) = *reinterpret_cast<const float4*>(tile + rr * TC_EPI_STRIDE + lane * 4);
+        }
+        return;
+    }
     for (int rr = warp; rr < TC_BM; rr += 8) {
         const int64_t r = row0 + rr;
         if (r >= g.n) break;

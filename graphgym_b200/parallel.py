@@ -173,32 +173,38 @@ class PartitionedLayout:
 
 class _DistAggregate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h_local, playout, kind, bias):
+    def forward(ctx, h_local, playout, kind, bias, self_scale):
         part = playout.part
-        h_full = all_gather_rows(h_local.contiguous(), part, playout.group)
+        h_local = h_local.contiguous()
+        h_full = all_gather_rows(h_local, part, playout.group)
         w_fwd, _ = playout.weights(kind)
-        out = ops.spmm(playout.csr, h_full, w_fwd, ops.MEAN if kind == 'mean' else ops.SUM, None, 0.0, bias)
-        ctx.playout, ctx.kind, ctx.has_bias = playout, kind, bias is not None
+        out = ops.spmm(playout.csr, h_full, w_fwd, ops.MEAN if kind == 'mean' else ops.SUM,
+                       h_local if self_scale != 0.0 else None, self_scale, bias)
+        ctx.playout, ctx.kind, ctx.has_bias, ctx.self_scale = playout, kind, bias is not None, self_scale
         return out
 
     @staticmethod
     def backward(ctx, g_local):
         playout = ctx.playout
         gh = gb = None
+        g_local = g_local.contiguous()
         if ctx.needs_input_grad[0]:
-            g_full = all_gather_rows(g_local.contiguous(), playout.part, playout.group)
+            g_full = all_gather_rows(g_local, playout.part, playout.group)
             _, w_bwd = playout.weights(ctx.kind)
-            gh = ops.spmm(playout.csc, g_full, w_bwd, ops.SUM)
+            gh = ops.spmm(playout.csc, g_full, w_bwd, ops.SUM, g_local if ctx.self_scale != 0.0 else None,
+                          ctx.self_scale)
         if ctx.has_bias and ctx.needs_input_grad[3]:
-            gb = ops.colsum(g_local.contiguous())
-        return gh, None, None, gb
+            gb = ops.colsum(g_local)
+        return gh, None, None, gb, None
 
 
-def _pipelined_spmm(subs, weights, local, playout, bias):
-    """out = sum_b A_b X_b: the local block first, then every peer block as its round completes."""
+def _pipelined_spmm(subs, weights, local, playout, bias, self_scale=0.0):
+    """out = sum_b A_b X_b (+ self_scale * X_local): the local block first, then every peer block as its
+    round completes."""
     part = playout.part
     rounds = exchange_blocks(local, part, playout.group)
-    out = ops.spmm(subs[part.rank], local, weights[part.rank], ops.SUM, None, 0.0, bias, x_row_base=part.lo)
+    out = ops.spmm(subs[part.rank], local, weights[part.rank], ops.SUM, local if self_scale != 0.0 else None,
+                   self_scale, bias, x_row_base=part.lo)
     for src, buf, works in rounds:
         for w in works:
             w.wait()
@@ -208,10 +214,10 @@ def _pipelined_spmm(subs, weights, local, playout, bias):
 
 class _DistAggregatePipelined(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h_local, playout, kind, bias):
+    def forward(ctx, h_local, playout, kind, bias, self_scale):
         w_fwd, _ = playout.sub_weights(kind)
-        out = _pipelined_spmm(playout.sub_csr, w_fwd, h_local.contiguous(), playout, bias)
-        ctx.playout, ctx.kind, ctx.has_bias = playout, kind, bias is not None
+        out = _pipelined_spmm(playout.sub_csr, w_fwd, h_local.contiguous(), playout, bias, self_scale)
+        ctx.playout, ctx.kind, ctx.has_bias, ctx.self_scale = playout, kind, bias is not None, self_scale
         return out
 
     @staticmethod
@@ -221,10 +227,10 @@ class _DistAggregatePipelined(torch.autograd.Function):
         g_local = g_local.contiguous()
         if ctx.needs_input_grad[0]:
             _, w_bwd = playout.sub_weights(ctx.kind)
-            gh = _pipelined_spmm(playout.sub_csc, w_bwd, g_local, playout, None)
+            gh = _pipelined_spmm(playout.sub_csc, w_bwd, g_local, playout, None, ctx.self_scale)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             gb = ops.colsum(g_local)
-        return gh, None, None, gb
+        return gh, None, None, gb, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -338,7 +344,7 @@ def _peer_scatter_cols(local, ptrs, row_base):
           'gg_peer_scatter_cols_f32')
 
 
-def _sliced_spmm(playout, layout, w, local, reduce, bias):
+def _sliced_spmm(playout, layout, w, local, reduce, bias, self_scale=0.0):
     """out_r = (A X)[rows of rank r]: column slices out (transposition), full-graph aggregation of this
     rank's slice, finished rows back to their owners."""
     part, group = playout.part, playout.group
@@ -354,7 +360,8 @@ def _sliced_spmm(playout, layout, w, local, reduce, bias):
         ob = pool.get(('rows', per, f), per * f * 4)
         _peer_scatter_cols(local, xs.ptrs, part.lo)
         pool.barrier()                                       # my slice is complete
-        ops.spmm(layout, xs.view(n, fs), w, reduce, None, 0.0, b,
+        x_slice = xs.view(n, fs)
+        ops.spmm(layout, x_slice, w, reduce, x_slice if self_scale != 0.0 else None, self_scale, b,
                  out_peers=ops.PeerRows([q + part.rank * fs * 4 for q in ob.ptrs], per, f))
         pool.barrier()                                       # every slice of my rows has landed
         return ob.view(per, f)[:rows].clone()                # the block is reused by the next exchange
@@ -363,7 +370,8 @@ def _sliced_spmm(playout, layout, w, local, reduce, bias):
     send[:, :rows] = local.reshape(rows, P, fs).permute(1, 0, 2)
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
-    out_slice = ops.spmm(layout, recv.view(P * per, fs)[:n].contiguous(), w, reduce, None, 0.0, b)
+    x_slice = recv.view(P * per, fs)[:n].contiguous()
+    out_slice = ops.spmm(layout, x_slice, w, reduce, x_slice if self_scale != 0.0 else None, self_scale, b)
     send = out_slice.new_zeros((P * per, fs))
     send[:n] = out_slice
     recv = torch.empty_like(send)
@@ -373,11 +381,11 @@ def _sliced_spmm(playout, layout, w, local, reduce, bias):
 
 class _DistAggregateSliced(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h_local, playout, kind, bias):
+    def forward(ctx, h_local, playout, kind, bias, self_scale):
         w_fwd, _ = playout.weights(kind)
         out = _sliced_spmm(playout, playout.csr, w_fwd, h_local.contiguous(),
-                           ops.MEAN if kind == 'mean' else ops.SUM, bias)
-        ctx.playout, ctx.kind, ctx.has_bias = playout, kind, bias is not None
+                           ops.MEAN if kind == 'mean' else ops.SUM, bias, self_scale)
+        ctx.playout, ctx.kind, ctx.has_bias, ctx.self_scale = playout, kind, bias is not None, self_scale
         return out
 
     @staticmethod
@@ -387,19 +395,26 @@ class _DistAggregateSliced(torch.autograd.Function):
         g_local = g_local.contiguous()
         if ctx.needs_input_grad[0]:
             _, w_bwd = playout.weights(ctx.kind)
-            gh = _sliced_spmm(playout, playout.csc, w_bwd, g_local, ops.SUM, None)
+            gh = _sliced_spmm(playout, playout.csc, w_bwd, g_local, ops.SUM, None, ctx.self_scale)
         if ctx.has_bias and ctx.needs_input_grad[3]:
             gb = ops.colsum(g_local)
-        return gh, None, None, gb
+        return gh, None, None, gb, None
 
 
-def dist_aggregate(h_local, playout, kind='sum', bias=None):
-    """Row-partitioned ``functional.aggregate``: out_r = (A H)[rows of rank r] (+ bias)."""
+def dist_aggregate(h_local, playout, kind='sum', bias=None, self_scale=0.0):
+    """Row-partitioned ``functional.aggregate``: out_r = (A H + self_scale * H)[rows of rank r] (+ bias).
+    A feature width the sliced exchange cannot cut into aligned slices falls back to the all-to-all form."""
+    self_scale = float(self_scale)
     if playout.sliced:
-        return _DistAggregateSliced.apply(h_local, playout, kind, bias)
+        if playout.exchange == 'sliced' and not sliced_width(h_local.size(1), playout.part.world):
+            raise ValueError(f'feature-sliced exchange: {h_local.size(1)} columns do not split into 16-byte aligned '
+                             f'slices over {playout.part.world} ranks; build the layout with exchange="allgather"')
+        return _DistAggregateSliced.apply(h_local, playout, kind, bias, self_scale)
     if playout.pipelined:
-        return _DistAggregatePipelined.apply(h_local, playout, kind, bias)
-    return _DistAggregate.apply(h_local, playout, kind, bias)
+        if kind == 'mean':
+            raise NotImplementedError('pipelined halo exchange: mean aggregation (use allgather or sliced)')
+        return _DistAggregatePipelined.apply(h_local, playout, kind, bias, self_scale)
+    return _DistAggregate.apply(h_local, playout, kind, bias, self_scale)
 
 
 def allreduce_grads(module, group=None):
@@ -424,3 +439,39 @@ class RowPartitionedGCN(torch.nn.Module):
     def forward(self, x_local, playout):
         h = F_.seg_linear([x_local], [self.model.weight], [(0, 0, False)])
         return dist_aggregate(h, playout, 'gcn_tgt', self.model.bias)
+
+
+class RowPartitionedSAGE(torch.nn.Module):
+    """``sageconv`` on a row partition (parameters / init of models.layer._SAGEConvLayer): the mean over the
+    neighbours is the exchanged aggregation (F_in wide), both linear maps are row-local."""
+
+    def __init__(self, dim_in, dim_out, bias=True):
+        super().__init__()
+        from .models.layer import _SAGEConvLayer
+        self.model = _SAGEConvLayer(dim_in, dim_out, bias=bias)
+
+    def forward(self, x_local, playout):
+        m = self.model
+        mean = dist_aggregate(x_local, playout, 'mean')
+        return F_.seg_linear([mean, x_local], [m.lin_l.weight, m.lin_r.weight], [(0, 0, False), (1, 1, False)],
+                             None, m.lin_l.bias, w_trans=True)
+
+
+class RowPartitionedGIN(torch.nn.Module):
+    """``ginconv`` on a row partition: z = (1 + eps) x + sum_j x_j exchanged, the MLP row-local."""
+
+    def __init__(self, dim_in, dim_out, bias=True):
+        super().__init__()
+        from .models.layer import _GINConvLayer
+        self.model = _GINConvLayer(torch.nn.Sequential(torch.nn.Linear(dim_in, dim_out), torch.nn.ReLU(),
+                                                       torch.nn.Linear(dim_out, dim_out)))
+
+    def forward(self, x_local, playout):
+        from .contrib.layer.idconv import _mlp
+        z = dist_aggregate(x_local, playout, 'sum', None, 1.0 + float(self.model.initial_eps))
+        return _mlp(self.model.nn, z)
+
+
+ROW_PARTITIONED = {'gcnconv': (RowPartitionedGCN, ops.LOOPS_ADD_REMAINING, 'gcn_tgt'),
+                   'sageconv': (RowPartitionedSAGE, ops.LOOPS_KEEP, 'mean'),
+                   'ginconv': (RowPartitionedGIN, ops.LOOPS_KEEP, 'sum')}

@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, exchange, ret, fout=8):
+def _worker(rank, world, port, n, exchange, ret, fout=8, name='gcnconv'):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -40,10 +40,16 @@ def _worker(rank, world, port, n, exchange, ret, fout=8):
         x = torch.randn(n, fin, generator=g)
         gy = torch.randn(n, fout, generator=g)
         part = parallel.RowPartition(n, world, rank)
-        layer = parallel.RowPartitionedGCN(fin, fout, bias=True)   # same seed on every rank
+        cls, policy, _ = parallel.ROW_PARTITIONED[name]
+        if name != 'gcnconv':
+            fin = fout if exchange.startswith('sliced') else fin   # SAGE / GIN aggregate the INPUT features
+            x = torch.randn(n, fin, generator=g)
+        layer = cls(fin, fout, bias=True)   # same seed on every rank
         with torch.no_grad():
-            layer.model.bias.uniform_(-0.5, 0.5)
-        playout = parallel.PartitionedLayout(ei, n, ops.LOOPS_ADD_REMAINING, part, exchange=exchange)
+            for prm in layer.parameters():
+                if prm.dim() == 1:
+                    prm.uniform_(-0.5, 0.5)
+        playout = parallel.PartitionedLayout(ei, n, policy, part, exchange=exchange)
         xl = x[part.lo:part.hi].clone().requires_grad_(True)
         y = layer(xl, playout)
         y.backward(gy[part.lo:part.hi])
@@ -51,12 +57,17 @@ def _worker(rank, world, port, n, exchange, ret, fout=8):
         # single-process oracle
         P = {k: v.detach().clone().requires_grad_(True) for k, v in layer.model.named_parameters()}
         xo = x.clone().requires_grad_(True)
-        yo = olayers.gcnconv(xo, ei, P['weight'], P['bias'])
+        if name == 'gcnconv':
+            yo = olayers.gcnconv(xo, ei, P['weight'], P['bias'])
+        elif name == 'sageconv':
+            yo = olayers.sageconv(xo, ei, P['lin_l.weight'], P['lin_l.bias'], P['lin_r.weight'])
+        else:
+            yo = olayers.ginconv(xo, ei, P['nn.0.weight'], P['nn.0.bias'], P['nn.2.weight'], P['nn.2.bias'])
         yo.backward(gy)
         ok = torch.allclose(y.detach(), yo.detach()[part.lo:part.hi], atol=1e-5)
         ok &= torch.allclose(xl.grad, xo.grad[part.lo:part.hi], atol=1e-5)
-        ok &= torch.allclose(layer.model.weight.grad, P['weight'].grad, atol=1e-4)
-        ok &= torch.allclose(layer.model.bias.grad, P['bias'].grad, atol=1e-4)
+        for k, v in layer.model.named_parameters():
+            ok &= torch.allclose(v.grad, P[k].grad, atol=1e-4)
         ret[rank] = bool(ok) and part.rows == (part.hi - part.lo)
     finally:
         dist.destroy_process_group()
@@ -96,6 +107,16 @@ def test_row_partitioned_gcn_world3_sliced():
     world = 3
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), 50, 'sliced_nccl', ret, 12), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+@pytest.mark.parametrize('exchange', ['allgather', 'sliced_nccl'])
+@pytest.mark.parametrize('name', ['sageconv', 'ginconv'])
+def test_row_partitioned_sage_gin_world2(name, exchange):
+    """mean aggregation with global degrees (SAGE), self term through the exchange (GIN)"""
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), 41, exchange, ret, 8, name), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
 
 

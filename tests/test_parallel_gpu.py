@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, exchange, ret):
+def _worker(rank, world, port, exchange, ret, name='gcnconv'):
     sys.path.insert(0, HERE)
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -32,20 +32,23 @@ def _worker(rank, world, port, exchange, ret):
         from graphgym_b200 import ops, parallel
         from graphgym_b200.models.layer import Batch, layer_dict
         from util import powerlaw_graph, rel_err
-        n, fin, fout = 30001, 100, 128
+        n, fin, fout = 30001, (100 if name == 'gcnconv' else 128), 128
         ei = powerlaw_graph(2, n, 12).to(dev)
         g = torch.Generator().manual_seed(1)
         x = torch.randn(n, fin, generator=g).to(dev)
         gy = torch.randn(n, fout, generator=g).to(dev)
         torch.manual_seed(0)
-        ref = layer_dict['gcnconv'](fin, fout, bias=True).to(dev)
+        cls, policy, _ = parallel.ROW_PARTITIONED[name]
+        ref = layer_dict[name](fin, fout, bias=True).to(dev)
         torch.manual_seed(0)
-        layer = parallel.RowPartitionedGCN(fin, fout, bias=True).to(dev)
+        layer = cls(fin, fout, bias=True).to(dev)
         with torch.no_grad():
-            ref.model.bias.uniform_(-0.5, 0.5)
-            layer.model.bias.copy_(ref.model.bias)
+            for pr, pl in zip(ref.model.parameters(), layer.model.parameters()):
+                if pr.dim() == 1:
+                    pr.uniform_(-0.5, 0.5)
+                pl.copy_(pr)
         part = parallel.RowPartition(n, world, rank)
-        playout = parallel.PartitionedLayout(ei, n, ops.LOOPS_ADD_REMAINING, part, exchange=exchange)
+        playout = parallel.PartitionedLayout(ei, n, policy, part, exchange=exchange)
         xl = x[part.lo:part.hi].clone().requires_grad_(True)
         for _ in range(3 if exchange == 'sliced' else 1):   # the peer buffers are reused: repeat the exchange
             layer.zero_grad(set_to_none=True)
@@ -56,14 +59,15 @@ def _worker(rank, world, port, exchange, ret):
         xr = x.clone().requires_grad_(True)
         yr = ref(Batch(xr, ei)).node_feature
         yr.backward(gy)
-        errs = [rel_err(y.detach(), yr.detach()[part.lo:part.hi]), rel_err(xl.grad, xr.grad[part.lo:part.hi]),
-                rel_err(layer.model.weight.grad, ref.model.weight.grad),
-                rel_err(layer.model.bias.grad, ref.model.bias.grad)]
+        errs = [rel_err(y.detach(), yr.detach()[part.lo:part.hi]), rel_err(xl.grad, xr.grad[part.lo:part.hi])]
+        errs += [rel_err(pl.grad, pr.grad) for pr, pl in zip(ref.model.parameters(), layer.model.parameters())]
         # the merge-path plan cuts rank-local rows at other places than the global plan, so rows split
         # over items re-associate their fp32 partial sums; most rows are bitwise the single-GPU rows
         same = (y.detach() == yr.detach()[part.lo:part.hi]).all(dim=1).float().mean().item()
         # (only the all-gather form: per-peer partial sums and the narrow-row kernel use other, equally fixed, orders)
-        ret[rank] = (max(errs) < 1e-5, same > 0.5 or exchange != 'allgather', errs)
+        # GIN's ReLU gates may flip on pre-activations within rounding of zero (see test_layers_gpu._check_gates)
+        tol = 1e-5 if name != 'ginconv' else 5e-5
+        ret[rank] = (max(errs) < tol, same > 0.5 or exchange != 'allgather' or name != 'gcnconv', errs)
         if playout.pool is not None:
             playout.pool.close()
     finally:
@@ -80,3 +84,15 @@ def test_two_gpu_row_partition_matches_single_gpu(exchange):
         ok, bitwise, errs = ret[r]
         assert ok, errs
         assert bitwise
+
+
+@pytest.mark.parametrize('exchange', ['allgather', 'sliced'])
+@pytest.mark.parametrize('name', ['sageconv', 'ginconv'])
+def test_two_gpu_sage_gin(name, exchange):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, _free_port(), exchange, ret, name), nprocs=2, join=True)
+    for r in range(2):
+        ok, _, errs = ret[r]
+        assert ok, errs

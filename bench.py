@@ -406,7 +406,7 @@ def run_ours(args, spec, rank, world, dev):
     # SpMM epilogue stores to the owners) | sliced_nccl (same over all_to_all)
     halo = os.environ.get('GG_HALO', DEFAULT_HALO)
     agg_kind = parallel.ROW_PARTITIONED[name][2] if multi else None
-    f_exchanged = fout if name == 'gcnconv' else fin
+    f_exchanged = fout if name in ('gcnconv', 'gatconv') else fin
     if multi and halo.startswith('sliced') and not parallel.sliced_width(f_exchanged, world):
         halo = 'allgather'
     mk_layout = lambda e: parallel.PartitionedLayout(e, n, policy, part, exchange=halo)

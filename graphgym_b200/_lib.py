@@ -56,8 +56,8 @@ SIGNATURES = {
                                c_size, c_int, c_ptr]),
     "gg_spmm_group_lanes": (c_int, [c_i64]),
     "gg_spmm_mpg_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64,
-                                c_ptr, c_int, c_i64, c_i64, c_i64, c_int, c_ptr, c_i64, c_f32, c_ptr, c_ptr,
-                                c_size, c_int, c_ptr]),
+                                c_ptr, c_int, c_i64, c_i64, c_i64, c_int, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_ptr,
+                                c_ptr, c_ptr, c_ptr, c_size, c_int, c_ptr]),
     "gg_peer_handle_bytes": (c_int, []),
     "gg_peer_alloc": (c_int, [c_size, ctypes.POINTER(c_ptr), ctypes.c_char_p]),
     "gg_peer_open": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_ptr)]),
@@ -103,6 +103,8 @@ SIGNATURES = {
     "gg_gat_alpha_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_ptr, c_ptr]),
     "gg_gat_sddmm_mp_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64,
                                     c_ptr, c_ptr, c_ptr]),
+    "gg_gat_sddmm_mpg_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64,
+                                     c_ptr, c_ptr, c_ptr]),
     "gg_gat_dz_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_ptr]),
     "gg_gat_csc_gather_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "gg_gather_rows_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr]),

@@ -235,6 +235,87 @@ __global__ void __launch_bounds__(kGmThreads, VPL == 1 ? 4 : 2) gat_sddmm_mp_ker
     }
 }
 
+// ---- narrow-row SDDMM (f <= 128): the feature-sliced exchange's share of dalpha ---------------------------
+// Rank c of the row-partitioned path holds column slice c of H and of g for ALL nodes; its contribution to
+// dalpha[s] is the dot product over its f = F/P columns (the ranks' contributions are summed afterwards).  Same
+// warp layout as spmm_mpg_kernel: 32/G groups of G lanes, a batch = 32/G x 8 consecutive slots, group k owns
+// slots [8k, 8k+8); the row of every slot is staged next to its neighbour id, the g row comes through L1
+// (consecutive slots share it), the H row is a no-allocate gather; G-lane shuffle reduction per slot.
+template <int G>
+__global__ void __launch_bounds__(kGmThreads, 4) gat_sddmm_mpg_kernel(const __grid_constant__ SddmmArgs a) {
+    constexpr int S = 32 / G, U = 8, B = S * U;
+    __shared__ __align__(16) int32_t s_nbr_all[kGmWarps][kSdTile];
+    __shared__ __align__(16) int32_t s_row_all[kGmWarps][kSdTile];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int grp = lane / G, gl = lane % G;
+    int32_t* s_nbr = s_nbr_all[wid];
+    int32_t* s_row = s_row_all[wid];
+    const int nvec = a.f >> 2;
+    const int col = (gl < nvec ? gl : nvec - 1) * 16;  // idle lanes (f/4 < G) read a duplicate, masked below
+    const float keep = gl < nvec ? 1.f : 0.f;
+    const char* __restrict__ hb = reinterpret_cast<const char*>(a.h) + col;
+    const char* __restrict__ gb = reinterpret_cast<const char*>(a.g) + col;
+    const uint32_t h_bytes = (uint32_t)a.ldh * 4u, g_bytes = (uint32_t)a.ldg * 4u;
+
+    int item = 0;
+    if (lane == 0) item = atomicAdd(a.counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    while (item < a.items) {
+        int next = 0;
+        if (lane == 0) next = atomicAdd(a.counter, 1);
+        const int r0 = __ldg(a.item_row + item), s0 = __ldg(a.item_slot + item);
+        const int s1 = __ldg(a.item_slot + item + 1);
+        __syncwarp();
+        int rr = r0;  // row of this lane's current slot: slots ascend with the lane's stride, rows follow
+        for (int q = s0 + lane; q < s1; q += 32) {
+            while (__ldg(a.rowptr + rr + 1) <= q) ++rr;
+            s_nbr[q - s0] = __ldg(a.nbr + q);
+            s_row[q - s0] = rr;
+        }
+        __syncwarp();
+        for (int s = s0; s < s1; s += B) {
+            const int g0 = s + grp * U;
+            const int t = g0 - s0;
+            float dot[U];
+            if (s + B <= s1) {
+                const int4 j0 = *reinterpret_cast<const int4*>(s_nbr + t), j1 = *reinterpret_cast<const int4*>(s_nbr + t + 4);
+                const int4 i0 = *reinterpret_cast<const int4*>(s_row + t), i1 = *reinterpret_cast<const int4*>(s_row + t + 4);
+                const int j[U] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w};
+                const int i[U] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+                float4 v[U], w[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    v[u] = ldg_nc_f4(reinterpret_cast<const float4*>(hb + (uint64_t)(uint32_t)j[u] * h_bytes));
+                    w[u] = __ldg(reinterpret_cast<const float4*>(gb + (uint64_t)(uint32_t)i[u] * g_bytes));
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    dot[u] = keep * (v[u].x * w[u].x + v[u].y * w[u].y + v[u].z * w[u].z + v[u].w * w[u].w);
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    dot[u] = 0.f;
+                    if (g0 + u < s1) {
+                        const float4 v = ldg_nc_f4(reinterpret_cast<const float4*>(hb + (uint64_t)(uint32_t)s_nbr[t + u] * h_bytes));
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(gb + (uint64_t)(uint32_t)s_row[t + u] * g_bytes));
+                        dot[u] = keep * (v.x * w.x + v.y * w.y + v.z * w.z + v.w * w.w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int m = 1; m < G; m <<= 1) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], m);
+            }
+            // every lane of the group holds the 8 sums; lane gl stores slot gl (and gl + 4 when G = 4)
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if ((u % G) == gl && g0 + u < s1) a.dalpha[g0 + u] = dot[u];
+        }
+        item = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
 static inline bool gm_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace gg
@@ -298,6 +379,31 @@ int gg_gat_sddmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const int32_t
     else if (nvec <= 64) gat_sddmm_mp_kernel<2><<<grid, kGmThreads, 0, st>>>(a);
     else if (nvec <= 128) gat_sddmm_mp_kernel<4><<<grid, kGmThreads, 0, st>>>(a);
     else gat_sddmm_mp_kernel<8><<<grid, kGmThreads, 0, st>>>(a);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
+int gg_gat_sddmm_mpg_f32(const int32_t* rowptr, const int32_t* nbr, const int32_t* item_row,
+                         const int32_t* item_slot, int64_t items, const float* h, int64_t ldh, const float* g,
+                         int64_t ldg, int64_t n, int64_t f, float* dalpha, int32_t* counter, gg_stream_t stream) {
+    GG_REQUIRE(n >= 0 && f >= 0 && items >= 0, "gg_gat_sddmm_mpg_f32: negative size");
+    if (n == 0 || f == 0 || items == 0) return GG_OK;
+    GG_REQUIRE(rowptr && item_row && item_slot && h && g && dalpha && counter, "gg_gat_sddmm_mpg_f32: null pointer");
+    if (!((f % 4 == 0) && f <= 128 && ldh % 4 == 0 && ldg % 4 == 0 && gm_al16(h) && gm_al16(g) &&
+          ldh < ((int64_t)1 << 30) && ldg < ((int64_t)1 << 30))) {
+        set_error("gg_gat_sddmm_mpg_f32: needs f %% 4 == 0, f <= 128 and 16-byte aligned rows");
+        return GG_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = as_stream(stream);
+    GG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    SddmmArgs a{rowptr, nbr, item_row, item_slot, (int)items, h, ldh, g, ldg, n, (int)f, counter, dalpha};
+    const int nvec = (int)(f / 4);
+    int grid = (int)ceil_div(items, kGmWarps);
+    if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+    if (nvec <= 4) gat_sddmm_mpg_kernel<4><<<grid, kGmThreads, 0, st>>>(a);
+    else if (nvec <= 8) gat_sddmm_mpg_kernel<8><<<grid, kGmThreads, 0, st>>>(a);
+    else if (nvec <= 16) gat_sddmm_mpg_kernel<16><<<grid, kGmThreads, 0, st>>>(a);
+    else gat_sddmm_mpg_kernel<32><<<grid, kGmThreads, 0, st>>>(a);
     GG_LAUNCHED();
     return GG_OK;
 }

@@ -417,6 +417,8 @@ __global__ void __launch_bounds__(kMpThreads, 4)
                 if (a.x_self)
                     fma4(r, a.self_scale, __ldg(reinterpret_cast<const float4*>(a.x_self + (int64_t)row * a.ld_self) + gl));
                 if (a.bias) add4(r, __ldg(reinterpret_cast<const float4*>(a.bias) + gl));
+                if (a.r1_s) fma4(r, __ldg(a.r1_s + row), __ldg(reinterpret_cast<const float4*>(a.r1_v) + gl));
+                if (a.r2_s) fma4(r, __ldg(a.r2_s + row), __ldg(reinterpret_cast<const float4*>(a.r2_v) + gl));
                 stg_f4_hint(mpg_out_row<PEER>(a, po, row) + gl, r, pol_stream);
             }
             acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -514,6 +516,8 @@ __global__ void __launch_bounds__(kMpThreads)
     }
     if (a.x_self) fma4(r, a.self_scale, __ldg(reinterpret_cast<const float4*>(a.x_self + (int64_t)r0 * a.ld_self) + gl));
     if (a.bias) add4(r, __ldg(reinterpret_cast<const float4*>(a.bias) + gl));
+    if (a.r1_s) fma4(r, __ldg(a.r1_s + r0), __ldg(reinterpret_cast<const float4*>(a.r1_v) + gl));
+    if (a.r2_s) fma4(r, __ldg(a.r2_s + r0), __ldg(reinterpret_cast<const float4*>(a.r2_v) + gl));
     mpg_out_row<PEER>(a, po, r0)[gl] = r;
 }
 
@@ -683,9 +687,11 @@ int gg_spmm_mpg_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_sl
                     const int32_t* item_slot, int64_t items, const float* x, int64_t ldx, float* out,
                     int64_t ldo, float* const* out_peers_host, int world, int64_t rows_per_rank,
                     int64_t num_rows, int64_t f, int reduce, const float* x_self, int64_t ld_self,
-                    float self_scale, const float* bias, void* workspace, size_t workspace_bytes, int flags,
-                    gg_stream_t stream) {
+                    float self_scale, const float* bias, const float* r1_s, const float* r1_v, const float* r2_s,
+                    const float* r2_v, void* workspace, size_t workspace_bytes, int flags, gg_stream_t stream) {
     GG_REQUIRE(num_rows >= 0 && f >= 0 && items >= 0, "gg_spmm_mpg_f32: negative size");
+    GG_REQUIRE((!r1_s || (r1_v && mp_aligned16(r1_v))) && (!r2_s || (r2_v && mp_aligned16(r2_v))),
+               "gg_spmm_mpg_f32: rank-1 term without its (16-byte aligned) vector");
     GG_REQUIRE(reduce == GG_SUM || reduce == GG_MEAN, "gg_spmm_mpg_f32: reduce=%d", reduce);
     if (num_rows == 0 || f == 0) return GG_OK;
     const int g = mpg_lanes(f);
@@ -726,7 +732,7 @@ int gg_spmm_mpg_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_sl
     float* head = c.take<float>((size_t)items * f);
     GG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
     MpArgs a{rowptr, nbr, w_slot, item_row, item_slot, (int)items, x, ldx, out, ldo, num_rows, (int)f,
-             reduce, x_self, ld_self, self_scale, bias, counter, carry, head, nullptr, nullptr, nullptr, nullptr,
+             reduce, x_self, ld_self, self_scale, bias, counter, carry, head, r1_s, r1_v, r2_s, r2_v,
              (flags & 4) ? 1 : 0};
     if (g == 4) launch_mpg<4>(a, po, peer, st);
     else if (g == 8) launch_mpg<8>(a, po, peer, st);

@@ -230,16 +230,18 @@ def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None
     if bias is not None:
         bias = bias.contiguous()
     L = lib()
+    r1 = [t.contiguous() if t is not None else None for t in (rank1 or (None, None, None, None))]
     if out_peers is not None:
-        if rank1 is not None or out is not None:
-            raise ValueError("out_peers excludes out / rank1")
+        if out is not None:
+            raise ValueError("out_peers excludes out")
         item_row, item_slot, items = csr.plan
         ws_bytes = int(L.gg_spmm_mp_workspace_bytes(items, f))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         check(L.gg_spmm_mpg_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(item_row), _ptr(item_slot),
                                 items, x_ptr, ldx, None, out_peers.ld, out_peers._arr, len(out_peers.ptrs),
                                 out_peers.rows_per_rank, n, f, reduce, _ptr(x_self), ld_self, float(self_scale),
-                                _ptr(bias), _ptr(ws), ws_bytes, _spmm_flags(), _stream()), "gg_spmm_mpg_f32")
+                                _ptr(bias), _ptr(r1[0]), _ptr(r1[1]), _ptr(r1[2]), _ptr(r1[3]), _ptr(ws), ws_bytes,
+                                _spmm_flags(), _stream()), "gg_spmm_mpg_f32")
         return None
     if out is None:
         out = torch.empty((n, f), dtype=torch.float32, device=x.device)
@@ -253,17 +255,17 @@ def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None
         algo = "row"
         if f % 4 == 0 and big:
             algo = "mp" if 64 < f <= 1024 else ("mpg" if f <= 64 else "row")
-    if rank1 is not None:
+    if rank1 is not None and algo == "row":
         algo = "mp"
-    r1 = [t.contiguous() if t is not None else None for t in (rank1 or (None, None, None, None))]
     if algo == "mpg" and f % 4 == 0 and f <= 128 and n > 0:
         item_row, item_slot, items = csr.plan
         ws_bytes = int(L.gg_spmm_mp_workspace_bytes(items, f))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         check(L.gg_spmm_mpg_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(item_row), _ptr(item_slot),
                                 items, x_ptr, ldx, _ptr(out), ldo, None, 1, max(n, 1), n, f, reduce,
-                                _ptr(x_self), ld_self, float(self_scale), _ptr(bias), _ptr(ws), ws_bytes,
-                                _spmm_flags(), _stream()), "gg_spmm_mpg_f32")
+                                _ptr(x_self), ld_self, float(self_scale), _ptr(bias), _ptr(r1[0]), _ptr(r1[1]),
+                                _ptr(r1[2]), _ptr(r1[3]), _ptr(ws), ws_bytes, _spmm_flags(), _stream()),
+              "gg_spmm_mpg_f32")
         return out
     if algo in ("mp", "mpg") and f % 4 == 0 and f <= 1024 and n > 0:
         item_row, item_slot, items = csr.plan
@@ -496,3 +498,68 @@ def gat_backward(csr, csc, csc2csr, h, att, heads, slope, bias, alpha, a_tgt, a_
     check(L.gg_gat_att_grad_f32(_ptr(h), ldh, _ptr(da_tgt), _ptr(da_src), n, heads, c, _ptr(datt), _ptr(ws),
                                 ws_bytes, _stream()), "gg_gat_att_grad_f32")
     return dh, datt
+
+
+def gat_sddmm_slice(csr, h_slice, g_slice):
+    """This rank's share of dalpha over its column slice: [E'] = <g_slice[row(s)], h_slice[nbr[s]]> (f <= 128)."""
+    _need_cuda(h_slice, g_slice)
+    h_slice, ldh = _rows(h_slice, "h_slice")
+    g_slice, ldg = _rows(g_slice, "g_slice")
+    n, f = csr.num_nodes, h_slice.size(1)
+    item_row, item_slot, items = csr.plan
+    dalpha = _f32((csr.num_slots,), h_slice.device)
+    counter = torch.empty(64, dtype=torch.int32, device=h_slice.device)
+    check(lib().gg_gat_sddmm_mpg_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(item_row), _ptr(item_slot), items,
+                                     _ptr(h_slice), ldh, _ptr(g_slice), ldg, n, f, _ptr(dalpha), _ptr(counter),
+                                     _stream()), "gg_gat_sddmm_mpg_f32")
+    return dalpha
+
+
+# ---- the GAT passes one by one (heads = 1), as the row-partitioned layer composes them ------------------
+def gat_scores(h, att_row):
+    """a_tgt[i] = <att[:c], h_i>, a_src[i] = <att[c:], h_i> for the rows of ``h``; ``att_row``: [1, 2c]."""
+    _need_cuda(h, att_row)
+    h, ldh = _rows(h, "h")
+    n, c = h.shape
+    a_tgt, a_src = _f32((n, 1), h.device), _f32((n, 1), h.device)
+    check(lib().gg_gat_scores_f32(_ptr(h), ldh, _ptr(att_row.contiguous()), n, 1, c, _ptr(a_tgt), _ptr(a_src),
+                                  _stream()), "gg_gat_scores_f32")
+    return a_tgt.view(-1), a_src.view(-1)
+
+
+def gat_alpha(csr, a_tgt, a_src, slope):
+    alpha = _f32((csr.num_slots,), a_tgt.device)
+    check(lib().gg_gat_alpha_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(a_tgt.contiguous()), _ptr(a_src.contiguous()),
+                                 csr.num_nodes, float(slope), _ptr(alpha), _stream()), "gg_gat_alpha_f32")
+    return alpha
+
+
+def gat_dz(csr, a_tgt, a_src, alpha, dalpha, slope):
+    """-> dz [E'] (gradient of the pre-softmax logits), da_tgt [n]."""
+    dev = alpha.device
+    dz, da_tgt = _f32((csr.num_slots,), dev), _f32((csr.num_nodes,), dev)
+    check(lib().gg_gat_dz_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(a_tgt), _ptr(a_src), _ptr(alpha), _ptr(dalpha),
+                              csr.num_nodes, float(slope), _ptr(dz), _ptr(da_tgt), _stream()), "gg_gat_dz_f32")
+    return dz, da_tgt
+
+
+def gat_csc_gather(csc, csc2csr, alpha, dz):
+    """-> alpha in CSC slot order, da_src [n] = per-source sums of dz."""
+    dev = alpha.device
+    alpha_t, da_src = _f32((csc.num_slots,), dev), _f32((csc.num_nodes,), dev)
+    check(lib().gg_gat_csc_gather_f32(_ptr(csc.rowptr), _ptr(csc2csr), _ptr(alpha), _ptr(dz), csc.num_nodes,
+                                      _ptr(alpha_t), _ptr(da_src), _stream()), "gg_gat_csc_gather_f32")
+    return alpha_t, da_src
+
+
+def gat_att_grad(h, da_tgt, da_src):
+    """datt [1, 2c] = [da_tgt^T h | da_src^T h] over the rows of ``h``."""
+    h, ldh = _rows(h, "h")
+    n, c = h.shape
+    L = lib()
+    datt = torch.empty((1, 2 * c), dtype=torch.float32, device=h.device)
+    ws_bytes = int(L.gg_gat_att_grad_workspace_bytes(n, 1, c))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=h.device)
+    check(L.gg_gat_att_grad_f32(_ptr(h), ldh, _ptr(da_tgt.contiguous()), _ptr(da_src.contiguous()), n, 1, c, _ptr(datt),
+                                _ptr(ws), ws_bytes, _stream()), "gg_gat_att_grad_f32")
+    return datt

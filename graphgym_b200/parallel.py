@@ -118,6 +118,7 @@ class PartitionedLayout:
         self.pool = pool
         self._weights = {}
         self._sub_weights = {}
+        self._csc2csr = None
         self.sub_csr = self.sub_csc = None
         if self.sliced:
             # every rank aggregates its column slice over the whole graph: full layouts, no row filter
@@ -135,6 +136,15 @@ class PartitionedLayout:
                                              nbr_range=b) for b in blocks]
             self.sub_csc = [ops.layout_build(edge_index, num_nodes, policy, ops.BY_SOURCE, row_range=rng,
                                              nbr_range=b) for b in blocks]
+
+    @property
+    def csc2csr(self):
+        """CSC slot -> CSR slot of the same edge (full-graph layouts of the sliced exchange only)."""
+        if not self.sliced:
+            raise NotImplementedError('slot map across rank-local layouts')
+        if self._csc2csr is None:
+            self._csc2csr = ops.slot_map(self.csr, self.csc)
+        return self._csc2csr
 
     def sub_weights(self, kind):
         """Per-block (w_csr[b], w_csc[b]) lists; the normalisation uses the GLOBAL degrees."""
@@ -344,39 +354,59 @@ def _peer_scatter_cols(local, ptrs, row_base):
           'gg_peer_scatter_cols_f32')
 
 
-def _sliced_spmm(playout, layout, w, local, reduce, bias, self_scale=0.0):
-    """out_r = (A X)[rows of rank r]: column slices out (transposition), full-graph aggregation of this
-    rank's slice, finished rows back to their owners."""
+def _to_slices(playout, local):
+    """Forward leg of the exchange: this rank's rows [rows, F] -> its column slice of ALL rows [N, F/P].
+    Peer form: a view of the pool's slice buffer, valid until the next ``_to_slices`` of the same shape."""
     part, group = playout.part, playout.group
     P, per, n = part.world, part.per, part.n
     rows, f = local.shape
     fs = sliced_width(f, P)
     if not fs:
         raise ValueError(f'feature-sliced exchange needs f % (4*world) == 0 and f/world <= 128 (f={f}, world={P})')
-    b = bias[part.rank * fs:(part.rank + 1) * fs].contiguous() if bias is not None else None
     if playout.exchange == 'sliced':
         pool = playout.pool
         xs = pool.get(('slice', n, fs), n * fs * 4)
-        ob = pool.get(('rows', per, f), per * f * 4)
         _peer_scatter_cols(local, xs.ptrs, part.lo)
         pool.barrier()                                       # my slice is complete
-        x_slice = xs.view(n, fs)
-        ops.spmm(layout, x_slice, w, reduce, x_slice if self_scale != 0.0 else None, self_scale, b,
-                 out_peers=ops.PeerRows([q + part.rank * fs * 4 for q in ob.ptrs], per, f))
-        pool.barrier()                                       # every slice of my rows has landed
-        return ob.view(per, f)[:rows].clone()                # the block is reused by the next exchange
-    # same algorithm over torch.distributed (NCCL / gloo): two all-to-alls around a plain SpMM
+        return xs.view(n, fs)
     send = local.new_zeros((P, per, fs))
     send[:, :rows] = local.reshape(rows, P, fs).permute(1, 0, 2)
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
-    x_slice = recv.view(P * per, fs)[:n].contiguous()
-    out_slice = ops.spmm(layout, x_slice, w, reduce, x_slice if self_scale != 0.0 else None, self_scale, b)
+    return recv.view(P * per, fs)[:n].contiguous()
+
+
+def _from_slices(playout, layout, w, x_slice, rows, reduce, bias, self_scale=0.0, rank1=None):
+    """Aggregate this rank's slice over the whole graph and return the finished rows of THIS rank [rows, F]
+    (return leg of the exchange).  ``bias`` / the rank-1 vectors are full-width; their slice is cut here."""
+    part, group = playout.part, playout.group
+    P, per, n = part.world, part.per, part.n
+    fs = x_slice.size(1)
+    f = fs * P
+    cut = lambda v: v[part.rank * fs:(part.rank + 1) * fs].contiguous() if v is not None else None
+    b = cut(bias)
+    if rank1 is not None:
+        rank1 = (rank1[0], cut(rank1[1]), rank1[2], cut(rank1[3]))
+    x_self = x_slice if self_scale != 0.0 else None
+    if playout.exchange == 'sliced':
+        pool = playout.pool
+        ob = pool.get(('rows', per, f), per * f * 4)
+        ops.spmm(layout, x_slice, w, reduce, x_self, self_scale, b, rank1=rank1,
+                 out_peers=ops.PeerRows([q + part.rank * fs * 4 for q in ob.ptrs], per, f))
+        pool.barrier()                                       # every slice of my rows has landed
+        return ob.view(per, f)[:rows].clone()                # the block is reused by the next exchange
+    out_slice = ops.spmm(layout, x_slice, w, reduce, x_self, self_scale, b, rank1=rank1)
     send = out_slice.new_zeros((P * per, fs))
     send[:n] = out_slice
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
     return recv.view(P, per, fs).permute(1, 0, 2).reshape(per, f)[:rows].contiguous()
+
+
+def _sliced_spmm(playout, layout, w, local, reduce, bias, self_scale=0.0):
+    """out_r = (A X)[rows of rank r]: column slices out (transposition), full-graph aggregation of this
+    rank's slice, finished rows back to their owners."""
+    return _from_slices(playout, layout, w, _to_slices(playout, local), local.size(0), reduce, bias, self_scale)
 
 
 class _DistAggregateSliced(torch.autograd.Function):
@@ -471,7 +501,69 @@ class RowPartitionedGIN(torch.nn.Module):
         z = dist_aggregate(x_local, playout, 'sum', None, 1.0 + float(self.model.initial_eps))
         return _mlp(self.model.nn, z)
 
+class _DistGatSliced(torch.autograd.Function):
+    """GAT aggregation (heads = 1, ref: idconv.py:299-342) on a row partition with the feature-sliced exchange.
+
+    The per-node logit halves are computed where the rows live and all-gathered (2 floats per node); the
+    softmax weights alpha and their backward are light per-slot passes that every rank runs on the full
+    layout; the two heavy passes (sum_j alpha_ij H_j and its transpose) are sliced aggregations; the edge
+    gradient dalpha_e = <g_i, H_j> is a sliced SDDMM whose per-rank shares are all-reduced."""
+
+    @staticmethod
+    def forward(ctx, h_local, att, bias, playout, slope):
+        part, group = playout.part, playout.group
+        h_local = h_local.contiguous()
+        c = h_local.size(1)
+        att_row = att.contiguous().view(1, 2 * c)
+        a_tgt_l, a_src_l = ops.gat_scores(h_local, att_row)
+        a_tgt = all_gather_rows(a_tgt_l.view(-1, 1), part, group).reshape(-1).contiguous()
+        a_src = all_gather_rows(a_src_l.view(-1, 1), part, group).reshape(-1).contiguous()
+        alpha = ops.gat_alpha(playout.csr, a_tgt, a_src, slope)
+        h_slice = _to_slices(playout, h_local)
+        out = _from_slices(playout, playout.csr, alpha, h_slice, h_local.size(0), ops.SUM, bias)
+        ctx.playout, ctx.slope, ctx.has_bias = playout, slope, bias is not None
+        ctx.save_for_backward(h_local, att_row, alpha, a_tgt, a_src, h_slice.clone())
+        return out
+
+    @staticmethod
+    def backward(ctx, g_local):
+        playout = ctx.playout
+        part, group = playout.part, playout.group
+        h_local, att_row, alpha, a_tgt, a_src, h_slice = ctx.saved_tensors
+        c = h_local.size(1)
+        g_local = g_local.contiguous()
+        g_slice = _to_slices(playout, g_local)
+        dalpha = ops.gat_sddmm_slice(playout.csr, h_slice, g_slice)
+        dist.all_reduce(dalpha, op=dist.ReduceOp.SUM, group=group)
+        dz, da_tgt = ops.gat_dz(playout.csr, a_tgt, a_src, alpha, dalpha, ctx.slope)
+        alpha_t, da_src = ops.gat_csc_gather(playout.csc, playout.csc2csr, alpha, dz)
+        # dH = A_alpha^T g + da_src att_src + da_tgt att_tgt   (att = [tgt half | src half])
+        dh = _from_slices(playout, playout.csc, alpha_t, g_slice, h_local.size(0), ops.SUM, None,
+                          rank1=(da_src, att_row[0, c:], da_tgt, att_row[0, :c]))
+        datt = ops.gat_att_grad(h_local, da_tgt[part.lo:part.hi], da_src[part.lo:part.hi])   # this rank's rows
+        gb = ops.colsum(g_local) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dh, datt.view(1, 1, 2 * c), gb, None, None
+
+
+class RowPartitionedGAT(torch.nn.Module):
+    """``gatconv`` (heads = 1) on a row partition with the feature-sliced exchange: parameters / init of
+    models.layer._GATConvLayer; datt / dW / dbias are per-rank partial sums (``allreduce_grads``)."""
+
+    def __init__(self, dim_in, dim_out, bias=True):
+        super().__init__()
+        from .models.layer import _GATConvLayer
+        self.model = _GATConvLayer(dim_in, dim_out, heads=1, bias=bias)
+
+    def forward(self, x_local, playout):
+        if not playout.sliced:
+            raise NotImplementedError('row-partitioned gatconv runs on the feature-sliced exchange '
+                                      '(exchange="sliced" or "sliced_nccl")')
+        m = self.model
+        h = F_.seg_linear([x_local], [m.weight], [(0, 0, False)])
+        return _DistGatSliced.apply(h, m.att, m.bias, playout, float(m.negative_slope))
+
 
 ROW_PARTITIONED = {'gcnconv': (RowPartitionedGCN, ops.LOOPS_ADD_REMAINING, 'gcn_tgt'),
                    'sageconv': (RowPartitionedSAGE, ops.LOOPS_KEEP, 'mean'),
-                   'ginconv': (RowPartitionedGIN, ops.LOOPS_KEEP, 'sum')}
+                   'ginconv': (RowPartitionedGIN, ops.LOOPS_KEEP, 'sum'),
+                   'gatconv': (RowPartitionedGAT, ops.LOOPS_REMOVE_ADD, 'sum')}

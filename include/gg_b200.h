@@ -187,14 +187,15 @@ int gg_spmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slo
  * `world` DEVICE pointers (peer memory from gg_peer_open, already offset to this rank's columns).  The
  * stores are plain global stores over NVLink: aggregation and the return leg of the exchange are ONE
  * kernel.  The caller orders it against the peers with gg_peer_barrier.  flags: bit 2 = L2 residency
- * hints as in gg_spmm_mp_f32. */
+ * hints as in gg_spmm_mp_f32.  r1_s/r1_v, r2_s/r2_v: the optional rank-1 epilogue terms of gg_spmm_mp_f32
+ * (scalars indexed by the global row, vectors already offset to this call's columns). */
 int gg_spmm_group_lanes(int64_t f);
 int gg_spmm_mpg_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, const int32_t* item_row,
                     const int32_t* item_slot, int64_t items, const float* x, int64_t ldx, float* out,
                     int64_t ldo, float* const* out_peers_host, int world, int64_t rows_per_rank,
                     int64_t num_rows, int64_t f, int reduce, const float* x_self, int64_t ld_self,
-                    float self_scale, const float* bias, void* workspace, size_t workspace_bytes, int flags,
-                    gg_stream_t stream);
+                    float self_scale, const float* bias, const float* r1_s, const float* r1_v, const float* r2_s,
+                    const float* r2_v, void* workspace, size_t workspace_bytes, int flags, gg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Dense transform with ID-GNN heterogeneous weights:
@@ -346,6 +347,12 @@ int gg_gat_alpha_f32(const int32_t* rowptr, const int32_t* nbr, const float* a_t
 int gg_gat_sddmm_mp_f32(const int32_t* rowptr, const int32_t* nbr, const int32_t* item_row,
                         const int32_t* item_slot, int64_t items, const float* h, int64_t ldh, const float* g,
                         int64_t ldg, int64_t n, int64_t f, float* dalpha, int32_t* counter, gg_stream_t stream);
+/* Narrow-row SDDMM (f % 4 == 0, f <= 128) for the feature-sliced exchange: this rank's share
+ * dalpha[s] = <g[row(s), 0:f], h[nbr[s], 0:f]> over ITS column slice; the ranks' shares are summed by the
+ * caller (all-reduce).  Same plan and counter conventions as gg_gat_sddmm_mp_f32. */
+int gg_gat_sddmm_mpg_f32(const int32_t* rowptr, const int32_t* nbr, const int32_t* item_row,
+                         const int32_t* item_slot, int64_t items, const float* h, int64_t ldh, const float* g,
+                         int64_t ldg, int64_t n, int64_t f, float* dalpha, int32_t* counter, gg_stream_t stream);
 int gg_gat_dz_f32(const int32_t* rowptr, const int32_t* nbr, const float* a_tgt, const float* a_src,
                   const float* alpha, const float* dalpha, int64_t n, float slope, float* dz, float* da_tgt,
                   gg_stream_t stream);

@@ -32,7 +32,7 @@ def _worker(rank, world, port, exchange, ret, name='gcnconv'):
         from graphgym_b200 import ops, parallel
         from graphgym_b200.models.layer import Batch, layer_dict
         from util import powerlaw_graph, rel_err
-        n, fin, fout = 30001, (100 if name == 'gcnconv' else 128), 128
+        n, fin, fout = 30001, (100 if name in ('gcnconv', 'gatconv') else 128), 128
         ei = powerlaw_graph(2, n, 12).to(dev)
         g = torch.Generator().manual_seed(1)
         x = torch.randn(n, fin, generator=g).to(dev)
@@ -84,6 +84,18 @@ def test_two_gpu_row_partition_matches_single_gpu(exchange):
         ok, bitwise, errs = ret[r]
         assert ok, errs
         assert bitwise
+
+
+@pytest.mark.parametrize('exchange', ['sliced_nccl', 'sliced'])
+def test_two_gpu_gat(exchange):
+    """edge-softmax layer: per-node logits all-gathered, sliced aggregations, sliced SDDMM + all-reduce"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, _free_port(), exchange, ret, 'gatconv'), nprocs=2, join=True)
+    for r in range(2):
+        ok, _, errs = ret[r]
+        assert ok, errs
 
 
 @pytest.mark.parametrize('exchange', ['allgather', 'sliced'])

@@ -229,3 +229,32 @@ def test_peer_output_and_column_scatter_on_one_gpu(cuda, world, f_total):
     want = ops.spmm(csr, x, w, ops.SUM, None, 0.0, bias)
     assert not torch.isnan(got).any()
     assert rel_err(got, want) < FP32_TOL
+
+
+@pytest.mark.parametrize('f', [16, 32, 64, 128])
+def test_narrow_sddmm_and_rank1_epilogue(cuda, monkeypatch, f):
+    """The two extra pieces of the row-partitioned GAT: this rank's share of dalpha over a narrow column slice,
+    and the rank-1 epilogue terms of the narrow-row aggregation."""
+    n = 40000
+    ei = powerlaw_graph(11, n, 14)
+    g = torch.Generator().manual_seed(f)
+    h = torch.randn(n, f, generator=g).to(cuda)
+    gr = torch.randn(n, f, generator=g).to(cuda)
+    csr = ops.layout_build(ei.to(cuda), n, 2, 0)
+    got = ops.gat_sddmm_slice(csr, h, gr)
+    rows, nbr = csr.rowid.long(), csr.nbr.long()
+    want = (gr.double()[rows] * h.double()[nbr]).sum(1)
+    assert rel_err(got, want) < FP32_TOL
+    # odd tail: f/4 not a power of two
+    if f == 32:
+        got = ops.gat_sddmm_slice(csr, h[:, :24].contiguous(), gr[:, :24].contiguous())
+        want = (gr.double()[rows, :24] * h.double()[nbr, :24]).sum(1)
+        assert rel_err(got, want) < FP32_TOL
+    w = torch.rand(csr.num_slots, generator=g).to(cuda)
+    s1, s2 = torch.randn(n, generator=g).to(cuda), torch.randn(n, generator=g).to(cuda)
+    v1, v2 = torch.randn(f, generator=g).to(cuda), torch.randn(f, generator=g).to(cuda)
+    monkeypatch.setattr(ops, 'SPMM_ALGO', 'mpg')
+    got = ops.spmm(csr, h, w, ops.SUM, rank1=(s1, v1, s2, v2))
+    base = ops.spmm(csr, h, w, ops.SUM)
+    want = base.double() + s1.double().view(-1, 1) * v1.double() + s2.double().view(-1, 1) * v2.double()
+    assert rel_err(got, want) < FP32_TOL

@@ -409,6 +409,20 @@ def run_ours(args, spec, rank, world, dev):
     f_exchanged = fout if name in ('gcnconv', 'gatconv') else fin
     if multi and halo.startswith('sliced') and not parallel.sliced_width(f_exchanged, world):
         halo = 'allgather'
+    if multi and halo == 'sliced':
+        # peer memory needs CUDA IPC between the ranks' processes: probe it once, all ranks agree on the outcome
+        ok = 1
+        try:
+            parallel.PeerPool.shared(part).barrier()
+            torch.cuda.synchronize()
+        except Exception as exc:  # noqa: BLE001
+            print(f'[bench] rank {rank}: peer memory unavailable ({type(exc).__name__}: {exc}); '
+                  'falling back to the NCCL all-to-all form', file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            halo = 'sliced_nccl'
     mk_layout = lambda e: parallel.PartitionedLayout(e, n, policy, part, exchange=halo)
     warm_weights = lambda pl: pl.sub_weights(agg_kind) if pl.pipelined else pl.weights(agg_kind)
     if multi:

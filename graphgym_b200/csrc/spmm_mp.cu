@@ -318,7 +318,9 @@ __global__ void __launch_bounds__(256) spmm_plan_kernel(const int32_t* __restric
 // a row end costs one predicated sweep + log2(S) shuffle stages, never a divergent branch.
 // (The first design made every group an independent item consumer; the union of 8 groups' row-end
 // branches serialised the warp at 65 instructions per slot and 33 G slots/s whatever the row width —
-// profiles/r01_mpg16_v0_ncu_raw.csv.)
+// profiles/r01_mpg16_v0_ncu_raw.csv.  A third design — private walks per group, one segmented scan of the
+// groups' tails per batch, row ends finished by the owning group — was correct but slower, 1.73 vs 1.46 ms at
+// F/P = 16: the divergent out-of-line row stores and spills cost more than the sweeps they replaced.)
 //
 // PEER: the row-partitioned path's feature-sliced exchange (parallel.py).  This rank aggregates its
 // F/P-wide column slice for ALL rows; a finished row is stored straight into the memory of the rank that

@@ -93,6 +93,9 @@ SIGNATURES = {
     "gg_cycle_diag_workspace_bytes": (c_size, [c_i64]),
     "gg_cycle_diag_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_int, c_ptr, c_i64,
                                   c_ptr, c_size, c_ptr]),
+    "gg_cycle_diag_mp_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "gg_cycle_diag_mp_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_int, c_ptr,
+                                     c_i64, c_ptr, c_size, c_ptr]),
     "gg_cycle_diag_i64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_int, c_ptr, c_i64, c_ptr,
                                   c_ptr, c_size, c_ptr]),
     "gg_egonet_workspace_bytes": (c_size, [c_i64, c_i64]),

@@ -8,10 +8,15 @@ through the sparse layout by ``gg_cycle_diag_*`` (csrc/cycle.cu).
 ``closed_walk_counts`` is the exact int64 variant diag(A^p) the north star names; the reference has no
 integer mode, so its parity target is the dense int64 oracle.
 """
+import os
+
 import torch
 
 from graphgym_b200 import ops
 from graphgym_b200.ops import _ptr, _stream, check, lib
+
+
+MP_STEP = os.environ.get("GG_CYCLE_STEP", "mp") == "mp"   # mp (merge-path aggregation kernel) | row (one warp per row)
 
 
 def _ranges(n, graph_ptr, block):
@@ -40,9 +45,13 @@ def _run(layout_csr, w_slot, n, k, symmetric, graph_ptr, integer):
     out = torch.empty((n, k), dtype=torch.int64 if integer else torch.float32, device=dev)
     overflow = torch.zeros(1, dtype=torch.int32, device=dev)
     gp = graph_ptr.cpu() if graph_ptr is not None else None
+    # one big graph in float mode: every hop is a whole-graph aggregation -> the load-balanced merge-path kernel
+    use_mp = (not integer) and gp is None and n + layout_csr.num_slots >= (1 << 14) and MP_STEP
+    if use_mp:
+        item_row, item_slot, items = layout_csr.plan
     ws = None
     for rb, re, sb, sc in _ranges(n, gp, block):
-        need = int(L.gg_cycle_diag_workspace_bytes(re - rb))
+        need = int(L.gg_cycle_diag_mp_workspace_bytes(n, items)) if use_mp else int(L.gg_cycle_diag_workspace_bytes(re - rb))
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, dtype=torch.uint8, device=dev)
         dst = out[sb:sb + sc]
@@ -50,6 +59,10 @@ def _run(layout_csr, w_slot, n, k, symmetric, graph_ptr, integer):
             check(L.gg_cycle_diag_i64(_ptr(layout_csr.rowptr), _ptr(layout_csr.nbr), rb, re, k, int(symmetric),
                                       sb, sc, _ptr(dst), k, _ptr(overflow), _ptr(ws), ws.numel(), _stream()),
                   "gg_cycle_diag_i64")
+        elif use_mp:
+            check(L.gg_cycle_diag_mp_f32(_ptr(layout_csr.rowptr), _ptr(layout_csr.nbr), _ptr(w_slot), _ptr(item_row),
+                                         _ptr(item_slot), items, n, k, int(symmetric), sb, sc, _ptr(dst), k, _ptr(ws),
+                                         ws.numel(), _stream()), "gg_cycle_diag_mp_f32")
         else:
             check(L.gg_cycle_diag_f32(_ptr(layout_csr.rowptr), _ptr(layout_csr.nbr), _ptr(w_slot), rb, re, k,
                                       int(symmetric), sb, sc, _ptr(dst), k, _ptr(ws), ws.numel(), _stream()),

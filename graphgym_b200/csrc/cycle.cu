@@ -191,10 +191,17 @@ size_t cycle_ws_bytes(int64_t rows) {
            512;
 }
 
+// merge-path plan of the whole-graph layout: the float propagation step then runs on gg_spmm_mp_f32
+struct WalkPlan {
+    const int32_t* item_row;
+    const int32_t* item_slot;
+    int64_t items;
+};
+
 template <typename T, typename Out>
 int cycle_diag(const int32_t* rowptr, const int32_t* nbr, const float* w, int64_t row_begin, int64_t row_end,
                int k, int symmetric, int64_t src_begin, int src_count, Out* out, int64_t ld_out, int* overflow,
-               void* workspace, size_t workspace_bytes, cudaStream_t st) {
+               void* workspace, size_t workspace_bytes, cudaStream_t st, const WalkPlan* plan = nullptr) {
     using W = Walk<T>;
     using Vec = typename W::Vec;
     const int64_t rows = row_end - row_begin;
@@ -203,8 +210,9 @@ int cycle_diag(const int32_t* rowptr, const int32_t* nbr, const float* w, int64_
     GG_REQUIRE(src_begin >= row_begin && src_begin + src_count <= row_end,
                "gg_cycle_diag: sources outside the row range");
     GG_REQUIRE(rowptr && out && workspace && ld_out >= k, "gg_cycle_diag: bad operands");
-    if (workspace_bytes < cycle_ws_bytes<T>(rows)) {
-        set_error("gg_cycle_diag: workspace %zu < %zu", workspace_bytes, cycle_ws_bytes<T>(rows));
+    const size_t mp_bytes = plan ? align_up(gg_spmm_mp_workspace_bytes(plan->items, W::kCols), 256) : 0;
+    if (workspace_bytes < cycle_ws_bytes<T>(rows) + mp_bytes) {
+        set_error("gg_cycle_diag: workspace %zu < %zu", workspace_bytes, cycle_ws_bytes<T>(rows) + mp_bytes);
         return GG_ERR_WORKSPACE;
     }
     Carver c(workspace);
@@ -221,7 +229,17 @@ int cycle_diag(const int32_t* rowptr, const int32_t* nbr, const float* w, int64_
     walk_init_kernel<T><<<init_grid, kWalkThreads, 0, st>>>(prev, rows, src_local, src_count);
     GG_LAUNCHED();
     const int step_grid = (int)ceil_div(rows, kWalkWarps);
+    void* mp_ws = plan ? c.take<char>(mp_bytes) : nullptr;
+    int step_rc = GG_OK;
     auto step = [&](const Vec* in, Vec* o) {
+        if (plan) {  // load-balanced, TMA-staged aggregation kernel (hub rows no longer serialise one warp)
+            const int rc = gg_spmm_mp_f32(rowptr, nbr, w, plan->item_row, plan->item_slot, plan->items,
+                                          reinterpret_cast<const float*>(in), W::kCols, reinterpret_cast<float*>(o),
+                                          W::kCols, rows, W::kCols, GG_SUM, nullptr, 0, 0.f, nullptr, nullptr, nullptr,
+                                          nullptr, nullptr, mp_ws, mp_bytes, 4, reinterpret_cast<gg_stream_t>(st));
+            if (rc != GG_OK) step_rc = rc;
+            return;
+        }
         if (w) walk_step_kernel<T, true><<<step_grid, kWalkThreads, 0, st>>>(rowptr, nbr, w, row_begin, rows, in, o);
         else walk_step_kernel<T, false><<<step_grid, kWalkThreads, 0, st>>>(rowptr, nbr, w, row_begin, rows, in, o);
         count_launch();
@@ -247,6 +265,7 @@ int cycle_diag(const int32_t* rowptr, const int32_t* nbr, const float* w, int64_
             Vec* t = prev; prev = cur; cur = t;
         }
     }
+    if (step_rc != GG_OK) return step_rc;
     GG_CUDA(cudaPeekAtLastError());
     return GG_OK;
 }
@@ -268,6 +287,21 @@ int gg_cycle_diag_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_
                       int64_t ld_out, void* workspace, size_t workspace_bytes, gg_stream_t stream) {
     return cycle_diag<float, float>(rowptr, nbr, w_slot, row_begin, row_end, k, symmetric, src_begin, src_count,
                                     out, ld_out, nullptr, workspace, workspace_bytes, as_stream(stream));
+}
+
+size_t gg_cycle_diag_mp_workspace_bytes(int64_t num_rows, int64_t items) {
+    return gg_cycle_diag_workspace_bytes(num_rows) + align_up(gg_spmm_mp_workspace_bytes(items, 128), 256) + 256;
+}
+
+int gg_cycle_diag_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, const int32_t* item_row,
+                         const int32_t* item_slot, int64_t items, int64_t num_rows, int k, int symmetric,
+                         int64_t src_begin, int src_count, float* out, int64_t ld_out, void* workspace,
+                         size_t workspace_bytes, gg_stream_t stream) {
+    GG_REQUIRE(item_row && item_slot && items >= 1, "gg_cycle_diag_mp_f32: missing merge-path plan");
+    if constexpr (sizeof(float4) != 16) return GG_ERR_UNSUPPORTED;
+    WalkPlan plan{item_row, item_slot, items};
+    return cycle_diag<float, float>(rowptr, nbr, w_slot, 0, num_rows, k, symmetric, src_begin, src_count, out, ld_out,
+                                    nullptr, workspace, workspace_bytes, as_stream(stream), &plan);
 }
 
 int gg_cycle_diag_i64(const int32_t* rowptr, const int32_t* nbr, int64_t row_begin, int64_t row_end, int k,

@@ -304,6 +304,13 @@ size_t gg_cycle_diag_workspace_bytes(int64_t num_rows_in_range);
 int gg_cycle_diag_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, int64_t row_begin,
                       int64_t row_end, int k, int symmetric, int64_t src_begin, int src_count, float* out,
                       int64_t ld_out, void* workspace, size_t workspace_bytes, gg_stream_t stream);
+/* Whole-graph float variant for large skewed graphs: the propagation step runs on the merge-path aggregation
+ * kernel (plan of the same layout from gg_spmm_plan_build) instead of one warp per row. */
+size_t gg_cycle_diag_mp_workspace_bytes(int64_t num_rows, int64_t items);
+int gg_cycle_diag_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, const int32_t* item_row,
+                         const int32_t* item_slot, int64_t items, int64_t num_rows, int k, int symmetric,
+                         int64_t src_begin, int src_count, float* out, int64_t ld_out, void* workspace,
+                         size_t workspace_bytes, gg_stream_t stream);
 int gg_cycle_diag_i64(const int32_t* rowptr, const int32_t* nbr, int64_t row_begin, int64_t row_end, int k,
                       int symmetric, int64_t src_begin, int src_count, int64_t* out, int64_t ld_out,
                       int32_t* overflow_count, void* workspace, size_t workspace_bytes, gg_stream_t stream);

@@ -86,3 +86,22 @@ def test_closed_walk_known_answers_and_overflow(cuda):
         else:
             assert (got[:, p] == torch.iinfo(torch.int64).max).all()
     assert overflow == n * sum(e >= 2 ** 63 for e in exact)
+
+
+def test_merge_path_propagation_step(cuda, monkeypatch):
+    """large enough for the whole-graph float mode to run its hops on the merge-path aggregation kernel: same values
+    as the one-warp-per-row step and as the dense oracle, with hub rows that span several work items"""
+    from graphgym_b200.contrib.transform import identity as gid
+    from util import powerlaw_graph
+    n, k = 3000, 6
+    ei = powerlaw_graph(4, n, 14)
+    assert n + ei.size(1) >= 1 << 14
+    want = oid.compute_identity(ei, n, k, torch.float64)
+    monkeypatch.setattr(gid, 'MP_STEP', True)
+    got_mp = compute_identity(ei.to(cuda), n, k)
+    got_mp_general = compute_identity(ei.to(cuda), n, k, symmetric=False)
+    monkeypatch.setattr(gid, 'MP_STEP', False)
+    got_row = compute_identity(ei.to(cuda), n, k)
+    assert rel_err(got_mp, want) < FP32_TOL
+    assert rel_err(got_mp_general, want) < FP32_TOL
+    assert rel_err(got_row, want) < FP32_TOL

@@ -563,7 +563,26 @@ class RowPartitionedGAT(torch.nn.Module):
         return _DistGatSliced.apply(h, m.att, m.bias, playout, float(m.negative_slope))
 
 
+class RowPartitionedGCNID(torch.nn.Module):
+    """``gcnidconv`` (ID-GNN's GCN layer, ref: idconv.py:104-189) on a row partition: the heterogeneous transform
+    X W (+ X W_id on the centre rows) is row-local — ``node_id_index`` is cut to this rank's rows — and the
+    normalised aggregation (degree over edge_index[0]) is the exchanged step."""
+
+    def __init__(self, dim_in, dim_out, bias=True):
+        super().__init__()
+        from .contrib.layer.idconv import GCNIDConvLayer
+        self.model = GCNIDConvLayer(dim_in, dim_out, bias=bias)
+
+    def forward(self, x_local, playout, node_id_index):
+        from .graph import IdIndex
+        part = playout.part
+        ids = node_id_index[(node_id_index >= part.lo) & (node_id_index < part.hi)] - part.lo
+        h = F_.id_linear(x_local, self.model.weight, self.model.weight_id, IdIndex(ids, x_local.size(0)))
+        return dist_aggregate(h, playout, 'gcn_src', self.model.bias)
+
+
 ROW_PARTITIONED = {'gcnconv': (RowPartitionedGCN, ops.LOOPS_ADD_REMAINING, 'gcn_tgt'),
+                   'gcnidconv': (RowPartitionedGCNID, ops.LOOPS_ADD_REMAINING, 'gcn_src'),
                    'sageconv': (RowPartitionedSAGE, ops.LOOPS_KEEP, 'mean'),
                    'ginconv': (RowPartitionedGIN, ops.LOOPS_KEEP, 'sum'),
                    'gatconv': (RowPartitionedGAT, ops.LOOPS_REMOVE_ADD, 'sum')}

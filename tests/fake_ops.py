@@ -88,7 +88,11 @@ def relu_grad(g, y):
     return g * (y > 0)
 
 
+def id_count(ids, num_nodes):
+    return torch.bincount(ids.long(), minlength=num_nodes).float()
+
+
 def install(monkeypatch_setattr):
     for name in ('layout_build', 'segment_degree', 'gcn_norm', 'mean_weights', 'spmm', 'id_gemm', 'gemm_tn',
-                 'colsum', 'relu_grad'):
+                 'colsum', 'relu_grad', 'id_count'):
         monkeypatch_setattr(ops, name, globals()[name])

@@ -41,7 +41,7 @@ def _worker(rank, world, port, n, exchange, ret, fout=8, name='gcnconv'):
         gy = torch.randn(n, fout, generator=g)
         part = parallel.RowPartition(n, world, rank)
         cls, policy, _ = parallel.ROW_PARTITIONED[name]
-        if name != 'gcnconv':
+        if name not in ('gcnconv', 'gcnidconv'):
             fin = fout if exchange.startswith('sliced') else fin   # SAGE / GIN aggregate the INPUT features
             x = torch.randn(n, fin, generator=g)
         layer = cls(fin, fout, bias=True)   # same seed on every rank
@@ -51,7 +51,8 @@ def _worker(rank, world, port, n, exchange, ret, fout=8, name='gcnconv'):
                     prm.uniform_(-0.5, 0.5)
         playout = parallel.PartitionedLayout(ei, n, policy, part, exchange=exchange)
         xl = x[part.lo:part.hi].clone().requires_grad_(True)
-        y = layer(xl, playout)
+        ids = torch.arange(0, n, 3)                        # ID-GNN centres on both ranks
+        y = layer(xl, playout, ids) if name == 'gcnidconv' else layer(xl, playout)
         y.backward(gy[part.lo:part.hi])
         parallel.allreduce_grads(layer)
         # single-process oracle
@@ -59,6 +60,8 @@ def _worker(rank, world, port, n, exchange, ret, fout=8, name='gcnconv'):
         xo = x.clone().requires_grad_(True)
         if name == 'gcnconv':
             yo = olayers.gcnconv(xo, ei, P['weight'], P['bias'])
+        elif name == 'gcnidconv':
+            yo = olayers.gcn_idconv(xo, ei, ids, P['weight'], P['weight_id'], P['bias'])
         elif name == 'sageconv':
             yo = olayers.sageconv(xo, ei, P['lin_l.weight'], P['lin_l.bias'], P['lin_r.weight'])
         else:
@@ -111,7 +114,7 @@ def test_row_partitioned_gcn_world3_sliced():
 
 
 @pytest.mark.parametrize('exchange', ['allgather', 'sliced_nccl'])
-@pytest.mark.parametrize('name', ['sageconv', 'ginconv'])
+@pytest.mark.parametrize('name', ['sageconv', 'ginconv', 'gcnidconv'])
 def test_row_partitioned_sage_gin_world2(name, exchange):
     """mean aggregation with global degrees (SAGE), self term through the exchange (GIN)"""
     world = 2

@@ -32,7 +32,7 @@ def _worker(rank, world, port, exchange, ret, name='gcnconv'):
         from graphgym_b200 import ops, parallel
         from graphgym_b200.models.layer import Batch, layer_dict
         from util import powerlaw_graph, rel_err
-        n, fin, fout = 30001, (100 if name in ('gcnconv', 'gatconv') else 128), 128
+        n, fin, fout = 30001, (100 if name in ('gcnconv', 'gatconv', 'gcnidconv') else 128), 128
         ei = powerlaw_graph(2, n, 12).to(dev)
         g = torch.Generator().manual_seed(1)
         x = torch.randn(n, fin, generator=g).to(dev)
@@ -50,14 +50,16 @@ def _worker(rank, world, port, exchange, ret, name='gcnconv'):
         part = parallel.RowPartition(n, world, rank)
         playout = parallel.PartitionedLayout(ei, n, policy, part, exchange=exchange)
         xl = x[part.lo:part.hi].clone().requires_grad_(True)
+        ids = torch.arange(0, n, 17, device=dev)          # ID-GNN centres (node_id_index), spread over both ranks
+        extra = (ids,) if name == 'gcnidconv' else ()
         for _ in range(3 if exchange == 'sliced' else 1):   # the peer buffers are reused: repeat the exchange
             layer.zero_grad(set_to_none=True)
             xl.grad = None
-            y = layer(xl, playout)
+            y = layer(xl, playout, *extra)
             y.backward(gy[part.lo:part.hi])
         parallel.allreduce_grads(layer)
         xr = x.clone().requires_grad_(True)
-        yr = ref(Batch(xr, ei)).node_feature
+        yr = ref(Batch(xr, ei, ids)).node_feature
         yr.backward(gy)
         errs = [rel_err(y.detach(), yr.detach()[part.lo:part.hi]), rel_err(xl.grad, xr.grad[part.lo:part.hi])]
         errs += [rel_err(pl.grad, pr.grad) for pr, pl in zip(ref.model.parameters(), layer.model.parameters())]
@@ -99,8 +101,8 @@ def test_two_gpu_gat(exchange):
 
 
 @pytest.mark.parametrize('exchange', ['allgather', 'sliced'])
-@pytest.mark.parametrize('name', ['sageconv', 'ginconv'])
-def test_two_gpu_sage_gin(name, exchange):
+@pytest.mark.parametrize('name', ['sageconv', 'ginconv', 'gcnidconv'])
+def test_two_gpu_sage_gin_gcnid(name, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     ret = mp.Manager().dict()

@@ -583,6 +583,8 @@ def run_ours(args, spec, rank, world, dev):
         'layout_first_call_s': round(layout_first_s, 3),
     }
     if multi:
+        if parallel._TRACE and rank == 0:
+            print('[bench] exchange phases (ms, count):', json.dumps(parallel.trace_report()), file=sys.stderr)
         if playout.pool is not None:
             playout.pool.close()
         dist.barrier()

@@ -28,6 +28,7 @@ merge-path plan splits at different places, and the all-reduced dW).
 The collective is issued through ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests).
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -337,6 +338,26 @@ class PeerPool:
         PeerPool._shared = {k: v for k, v in PeerPool._shared.items() if v is not self}
 
 
+_TRACE = os.environ.get('GG_PEER_TRACE', '0') == '1'   # CUDA-event timing of the exchange phases (diagnostics)
+_trace_events = []
+
+
+def _mark(name):
+    if _TRACE:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        _trace_events.append((name, ev))
+
+
+def trace_report():
+    """Mean milliseconds between consecutive marks, keyed by 'from->to' (call after a synchronize)."""
+    acc = {}
+    for (a, ea), (b, eb) in zip(_trace_events, _trace_events[1:]):
+        acc.setdefault(f'{a}->{b}', []).append(ea.elapsed_time(eb))
+    _trace_events.clear()
+    return {k: (round(sum(v) / len(v), 4), len(v)) for k, v in acc.items()}
+
+
 def sliced_width(f, world):
     """Slice width of the feature-sliced exchange, or 0 when f does not split into 16-byte aligned slices
     of at most 128 columns (the sub-warp-group kernel's range)."""
@@ -366,8 +387,11 @@ def _to_slices(playout, local):
     if playout.exchange == 'sliced':
         pool = playout.pool
         xs = pool.get(('slice', n, fs), n * fs * 4)
+        _mark('enter')
         _peer_scatter_cols(local, xs.ptrs, part.lo)
+        _mark('scattered')
         pool.barrier()                                       # my slice is complete
+        _mark('barrier1')
         return xs.view(n, fs)
     send = local.new_zeros((P, per, fs))
     send[:, :rows] = local.reshape(rows, P, fs).permute(1, 0, 2)
@@ -393,8 +417,12 @@ def _from_slices(playout, layout, w, x_slice, rows, reduce, bias, self_scale=0.0
         ob = pool.get(('rows', per, f), per * f * 4)
         ops.spmm(layout, x_slice, w, reduce, x_self, self_scale, b, rank1=rank1,
                  out_peers=ops.PeerRows([q + part.rank * fs * 4 for q in ob.ptrs], per, f))
+        _mark('aggregated')
         pool.barrier()                                       # every slice of my rows has landed
-        return ob.view(per, f)[:rows].clone()                # the block is reused by the next exchange
+        _mark('barrier2')
+        res = ob.view(per, f)[:rows].clone()                 # the block is reused by the next exchange
+        _mark('cloned')
+        return res
     out_slice = ops.spmm(layout, x_slice, w, reduce, x_self, self_scale, b, rank1=rank1)
     send = out_slice.new_zeros((P * per, fs))
     send[:n] = out_slice

@@ -175,10 +175,10 @@ def edge_feat_per_step(layer_name, n, num_slots, fin, fout):
     return num_slots * f_agg * 2, f_agg
 
 
-def spmm_bytes(n, slots, f, weighted):
+def spmm_bytes(n, slots, f, weighted, gather_bytes=4):
     """Algorithmic bytes of one aggregation launch: gathered rows + output rows + nbr
-    indices + rowptr (+ per-slot weights)."""
-    return slots * f * 4 + n * f * 4 + slots * 4 + (n + 1) * 4 + (slots * 4 if weighted else 0)
+    indices + rowptr (+ per-slot weights); ``gather_bytes`` = 2 in the bf16-gather mode."""
+    return slots * f * gather_bytes + n * f * 4 + slots * 4 + (n + 1) * 4 + (slots * 4 if weighted else 0)
 
 
 def load_peaks():
@@ -331,6 +331,9 @@ def run_ours(args, spec, rank, world, dev):
     from graphgym_b200.models.layer import Batch, layer_dict
     name, fin, fout = spec['layer'], spec['fin'], spec['fout']
     multi = world > 1
+    from graphgym_b200.config import cfg as gg_cfg
+    gg_cfg.b200.gather_dtype = args.gather_dtype
+    half = args.gather_dtype == 'bf16' and not multi
     if multi:
         if name not in parallel.ROW_PARTITIONED:
             raise SystemExit(f'--gpus {world}: the row-partitioned path serves {sorted(parallel.ROW_PARTITIONED)} '
@@ -470,7 +473,7 @@ def run_ours(args, spec, rank, world, dev):
     spmm_ms = [s.elapsed_time(e) for s, e in spmm_events]
     weighted = name in ('gcnconv', 'gcnidconv', 'gatconv', 'gatidconv')
     f_launch = f_agg // world if (multi and playout.sliced) else f_agg
-    per_launch_bytes = spmm_bytes(rows_local, slots_local, f_launch, weighted)
+    per_launch_bytes = spmm_bytes(rows_local, slots_local, f_launch, weighted, 2 if half else 4)
     avg_spmm_ms = float(np.mean(spmm_ms)) if spmm_ms else float('nan')
     peak, peak_src = load_peaks()
     achieved = per_launch_bytes / (avg_spmm_ms * 1e-3) / 1e9
@@ -568,7 +571,8 @@ def run_ours(args, spec, rank, world, dev):
     out = {
         'metric': 'layer fwd+bwd GEdge-feat/s', 'value': round(value, 3), 'unit': 'GEdge-feat/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms, 4),
-        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32',
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32' if not half else 'f32 arithmetic, gathered operand stored in bf16 (1e-2 mode)',
         'data': 'synthetic (seeded power-law / BA / uniform generators in bench.py; random-init glorot weights)',
         'config': {'workload': spec['desc'], 'layer': name, 'nodes': n, 'edges_directed': int(ei.size(1)),
                    'slots_after_loop_policy': slots, 'f_in': fin, 'f_out': fout, 'f_aggregated': f_agg,
@@ -684,6 +688,9 @@ def main():
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--gather-dtype', default='f32', choices=['f32', 'bf16'],
+                    help="storage of the aggregation's gathered operand: f32 (reference arithmetic, the default and "
+                         "the headline) or bf16 (the north star's 1e-2 mode; single GPU)")
     args = ap.parse_args()
     spec = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', 0))

@@ -29,6 +29,9 @@ def _defaults():
     c.train = _Node(batch_size=16)
     c.num_threads = 6
     c.device = 'auto'
+    # not a reference key: storage type of the operand the aggregation gathers.  'f32' = the reference's arithmetic
+    # (1e-5 parity); 'bf16' = the north star's 1e-2 mode (rows gathered in bf16, fp32 products and sums)
+    c.b200 = _Node(gather_dtype='f32')
     return c
 
 

@@ -12,12 +12,13 @@ from . import ops
 
 class _Aggregate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, layout, kind, self_scale, bias):
+    def forward(ctx, x, layout, kind, self_scale, bias, half):
         w_fwd, _ = layout.weights(kind)
         reduce = ops.MEAN if kind == "mean" else ops.SUM
         x = x.contiguous()
-        out = ops.spmm(layout.csr, x, w_fwd, reduce, x if self_scale != 0.0 else None, self_scale, bias)
-        ctx.layout, ctx.kind, ctx.self_scale = layout, kind, self_scale
+        gathered = ops.cast_bf16(x) if half else x        # 1e-2 mode: the gathered operand in bf16, fp32 arithmetic
+        out = ops.spmm(layout.csr, gathered, w_fwd, reduce, x if self_scale != 0.0 else None, self_scale, bias)
+        ctx.layout, ctx.kind, ctx.self_scale, ctx.half = layout, kind, self_scale, half
         ctx.has_bias = bias is not None
         return out
 
@@ -28,16 +29,20 @@ class _Aggregate(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             _, w_bwd = ctx.layout.weights(ctx.kind)
             # d/dx = A^T g (+ self_scale * g): the same kernel on the transposed layout
-            gx = ops.spmm(ctx.layout.csc, g, w_bwd, ops.SUM, g if ctx.self_scale != 0.0 else None,
+            gathered = ops.cast_bf16(g) if ctx.half else g
+            gx = ops.spmm(ctx.layout.csc, gathered, w_bwd, ops.SUM, g if ctx.self_scale != 0.0 else None,
                           ctx.self_scale, None)
         if ctx.has_bias and ctx.needs_input_grad[4]:
             gb = ops.colsum(g)
-        return gx, None, None, None, gb
+        return gx, None, None, None, gb, None
 
 
 def aggregate(x, layout, kind="sum", self_scale=0.0, bias=None):
-    """out[i] = reduce_{j->i} w_ji x[j] + self_scale * x[i] + bias."""
-    return _Aggregate.apply(x, layout, kind, float(self_scale), bias)
+    """out[i] = reduce_{j->i} w_ji x[j] + self_scale * x[i] + bias.  ``cfg.b200.gather_dtype = 'bf16'`` stores the
+    gathered operand in bf16 (forward and backward) when the width allows it (f % 8 == 0, f <= 256)."""
+    from .config import cfg
+    half = cfg.b200.gather_dtype == "bf16" and ops.bf16_gather_ok(x.size(1))
+    return _Aggregate.apply(x, layout, kind, float(self_scale), bias, half)
 
 
 class _SegLinear(torch.autograd.Function):

@@ -201,6 +201,44 @@ def id_count(ids, num_nodes):
 # --------------------------------------------------------------------------------------------
 # aggregation
 # --------------------------------------------------------------------------------------------
+def cast_bf16(x):
+    """fp32 [n, f] -> bf16 [n, f], round to nearest even (f % 4 == 0)."""
+    _need_cuda(x)
+    x, ld = _rows(x, "x")
+    n, f = x.shape
+    out = torch.empty((n, f), dtype=torch.bfloat16, device=x.device)
+    check(lib().gg_cast_f32_bf16(_ptr(x), ld, n, f, _ptr(out), max(f, 1), _stream()), "gg_cast_f32_bf16")
+    return out
+
+
+def bf16_gather_ok(f):
+    return f % 8 == 0 and 0 < f <= 256
+
+
+def _spmm_bf16(csr, x, w_slot, reduce, x_self, self_scale, bias):
+    if x.dim() != 2 or not x.is_contiguous():
+        x = x.contiguous()
+    n, f = csr.num_nodes, x.size(1)
+    if not bf16_gather_ok(f):
+        raise ValueError(f"bf16-gather aggregation needs f % 8 == 0 and f <= 256, got f={f}")
+    out = torch.empty((n, f), dtype=torch.float32, device=x.device)
+    if n == 0:
+        return out
+    ld_self = 0
+    if x_self is not None:
+        x_self, ld_self = _rows(x_self, "x_self")
+    if bias is not None:
+        bias = bias.contiguous()
+    L = lib()
+    item_row, item_slot, items = csr.plan
+    ws_bytes = int(L.gg_spmm_mp_workspace_bytes(items, f))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    check(L.gg_spmm_mp_bf16(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(w_slot), _ptr(item_row), _ptr(item_slot), items,
+                            _ptr(x), f, _ptr(out), f, n, f, reduce, _ptr(x_self), ld_self, float(self_scale),
+                            _ptr(bias), _ptr(ws), ws_bytes, _spmm_flags(), _stream()), "gg_spmm_mp_bf16")
+    return out
+
+
 class PeerRows:
     """Where the rows of a peer-output SpMM go: ``ptrs[o]`` = device pointer (peer memory, already offset
     to this rank's column slice) of rank o's [rows_per_rank, ld] block."""
@@ -221,6 +259,10 @@ def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None
     ``out_peers`` (PeerRows): rows are stored into the owning ranks' memory instead of ``out``
     (feature-sliced exchange of the row-partitioned path); returns None."""
     _need_cuda(x, w_slot, x_self, bias, csr.rowptr)
+    if x.dtype == torch.bfloat16:
+        if out is not None or rank1 is not None or out_peers is not None or x_row_base:
+            raise ValueError("bf16-gather aggregation: out / rank1 / out_peers / x_row_base are fp32-only")
+        return _spmm_bf16(csr, x, w_slot, reduce, x_self, self_scale, bias)
     x, ldx = _rows(x, "x")
     n, f = csr.num_nodes, x.size(1)
     x_ptr = ctypes.c_void_p(x.data_ptr() - int(x_row_base) * ldx * 4)

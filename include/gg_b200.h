@@ -197,6 +197,18 @@ int gg_spmm_mpg_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_sl
                     float self_scale, const float* bias, const float* r1_s, const float* r1_v, const float* r2_s,
                     const float* r2_v, void* workspace, size_t workspace_bytes, int flags, gg_stream_t stream);
 
+/* bf16-gather variant (the north star's 1e-2 mode): x is stored in bf16 (`x_bf16`: raw bf16 bits, ldx in
+ * elements, rows 16-byte aligned), products and sums are fp32, out / x_self / bias are fp32.  Same plan and the
+ * same fixed summation order as gg_spmm_mpg_f32; needs f % 8 == 0 and f <= 256.  gg_cast_f32_bf16 converts a
+ * feature matrix with round-to-nearest-even (f % 4 == 0). */
+int gg_cast_f32_bf16(const float* src, int64_t ld, int64_t rows, int64_t f, uint16_t* dst, int64_t ld_dst,
+                     gg_stream_t stream);
+int gg_spmm_mp_bf16(const int32_t* rowptr, const int32_t* nbr, const float* w_slot, const int32_t* item_row,
+                    const int32_t* item_slot, int64_t items, const uint16_t* x_bf16, int64_t ldx, float* out,
+                    int64_t ldo, int64_t num_rows, int64_t f, int reduce, const float* x_self, int64_t ld_self,
+                    float self_scale, const float* bias, void* workspace, size_t workspace_bytes, int flags,
+                    gg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * Dense transform with ID-GNN heterogeneous weights:
  *   out[N,F] = act( sum_g diag(scale_g) * A_g[N,K_g] * B_g  + bias ) (.* mask>0)

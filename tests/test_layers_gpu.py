@@ -250,3 +250,32 @@ def test_gat_merge_path_and_row_kernels_agree_with_oracle(cuda, monkeypatch, alg
     assert rel_err(gx, xd.grad) < FP32_TOL
     for k, gk in grads.items():
         assert rel_err(gk, P[k].grad) < FP32_TOL, k
+
+
+def test_bf16_gather_mode_layers(cuda):
+    """cfg.b200.gather_dtype = 'bf16': gcnconv / sageconv / ginconv outputs and gradients within 1e-2 of the fp32 path."""
+    from graphgym_b200.config import cfg
+    from graphgym_b200.models.layer import Batch, layer_dict
+    from util import powerlaw_graph
+    n, fin, fout = 20000, 64, 128
+    ei = powerlaw_graph(8, n, 10).to(cuda)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, fin, generator=g).to(cuda)
+    gy = torch.randn(n, fout, generator=g).to(cuda)
+    for name in ('gcnconv', 'sageconv', 'ginconv'):
+        torch.manual_seed(0)
+        layer = layer_dict[name](fin, fout, bias=True).to(cuda)
+        res = {}
+        for mode in ('f32', 'bf16'):
+            cfg.b200.gather_dtype = mode
+            try:
+                layer.zero_grad(set_to_none=True)
+                xi = x.clone().requires_grad_(True)
+                y = layer(Batch(xi, ei)).node_feature
+                y.backward(gy)
+                res[mode] = [y.detach(), xi.grad] + [p.grad.clone() for p in layer.parameters()]
+            finally:
+                cfg.b200.gather_dtype = 'f32'
+        for a, b in zip(res['bf16'], res['f32']):
+            assert rel_err(a, b) < 1e-2, name
+        assert any(not torch.equal(a, b) for a, b in zip(res['bf16'], res['f32'])), 'bf16 mode did not engage'

@@ -258,3 +258,40 @@ def test_narrow_sddmm_and_rank1_epilogue(cuda, monkeypatch, f):
     base = ops.spmm(csr, h, w, ops.SUM)
     want = base.double() + s1.double().view(-1, 1) * v1.double() + s2.double().view(-1, 1) * v2.double()
     assert rel_err(got, want) < FP32_TOL
+
+
+@pytest.mark.parametrize('f', [32, 64, 104, 128, 256])
+def test_bf16_gather_aggregation(cuda, f):
+    """1e-2 mode: the gathered operand in bf16, fp32 products and sums.  Against an fp64 aggregation of the SAME
+    bf16-rounded rows the kernel must be fp32-accurate; against the unrounded rows it is inside 1e-2."""
+    n = 30000
+    ei = powerlaw_graph(3, n, 16)
+    g = torch.Generator().manual_seed(f)
+    x = torch.randn(n, f, generator=g)
+    bias = torch.randn(f, generator=g)
+    csr = ops.layout_build(ei.to(cuda), n, 1, 0)
+    w = ops.gcn_norm(csr, ops.segment_degree(csr))
+    xb = ops.cast_bf16(x.to(cuda))
+    assert xb.dtype == torch.bfloat16 and torch.equal(xb.cpu(), x.to(torch.bfloat16))      # round to nearest even
+    a = torch.sparse_coo_tensor(torch.stack([csr.rowid.cpu().long(), csr.nbr.cpu().long()]), w.cpu().double(),
+                                (n, n)).coalesce()
+    for reduce, wts, self_scale, b in ((ops.SUM, w, 0.0, bias), (ops.SUM, None, 1.5, None), (ops.MEAN, None, 0.0, bias)):
+        got = ops.spmm(csr, xb, wts, reduce, x.to(cuda) if self_scale else None, self_scale,
+                       b.to(cuda) if b is not None else None)
+        assert got.dtype == torch.float32
+        if wts is not None:
+            want_r = torch.sparse.mm(a, xb.cpu().double())
+            want_x = torch.sparse.mm(a, x.double())
+        else:
+            ones = torch.sparse_coo_tensor(a.indices(), torch.ones_like(a.values()), (n, n))
+            want_r, want_x = torch.sparse.mm(ones, xb.cpu().double()), torch.sparse.mm(ones, x.double())
+            if reduce == ops.MEAN:
+                deg = torch.diff(csr.rowptr.cpu()).clamp(min=1).double().view(-1, 1)
+                want_r, want_x = want_r / deg, want_x / deg
+        if self_scale:
+            want_r, want_x = want_r + self_scale * x.double(), want_x + self_scale * x.double()
+        if b is not None:
+            want_r, want_x = want_r + b.double(), want_x + b.double()
+        assert rel_err(got, want_r) < FP32_TOL, (f, reduce)
+        assert rel_err(got, want_x) < 1e-2, (f, reduce)
+    assert torch.equal(ops.spmm(csr, xb, w), ops.spmm(csr, xb, w))      # deterministic

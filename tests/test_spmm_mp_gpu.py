@@ -283,7 +283,9 @@ def test_bf16_gather_aggregation(cuda, f):
             want_r = torch.sparse.mm(a, xb.cpu().double())
             want_x = torch.sparse.mm(a, x.double())
         else:
-            ones = torch.sparse_coo_tensor(a.indices(), torch.ones_like(a.values()), (n, n))
+            # unweighted: every slot counts once (the generator emits duplicate edges, so not the coalesced pattern)
+            ones = torch.sparse_coo_tensor(torch.stack([csr.rowid.cpu().long(), csr.nbr.cpu().long()]),
+                                           torch.ones(csr.num_slots, dtype=torch.float64), (n, n)).coalesce()
             want_r, want_x = torch.sparse.mm(ones, xb.cpu().double()), torch.sparse.mm(ones, x.double())
             if reduce == ops.MEAN:
                 deg = torch.diff(csr.rowptr.cpu()).clamp(min=1).double().view(-1, 1)

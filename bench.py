@@ -55,6 +55,9 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = 'products_gcn'
 DEFAULT_HALO = 'sliced'
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE aggregation launch from an `ncu --set full` capture of this bench
+# (profiles/r01_spmm_gemm_final_ncu_raw.csv: 17.48 + 1.32 GB; the algorithmic figure is 34.7 GB — the L2 serves the rest)
+NCU_TRAFFIC = {'products_gcn': 18_799_640_000}
 HALO_DESC = {
     'allgather': 'halo all-gather of the feature rows over NCCL, rank-local SpMM',
     'pipelined': 'P-1 NCCL send/recv rounds overlapped with the per-peer SpMMs',
@@ -482,7 +485,8 @@ def run_ours(args, spec, rank, world, dev):
                           + ((' — rank 0 of %d, ' % world) + ('all rows x F/%d columns (sub-warp-group kernel, rows stored '
                              'to their owners over NVLink)' % world if playout.sliced else 'rank-local rows') if multi else ''),
                 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
-                'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': peak_src,
+                'frac': round(achieved / peak, 4), 'traffic': NCU_TRAFFIC.get(args.workload) if not (multi or half) else None,
+                'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': per_launch_bytes,
                 'avg_launch_ms': round(avg_spmm_ms, 4), 'launches_timed': len(spmm_ms),
                 'share_of_step': round(sum(spmm_ms) / args.steps / ms, 3)}

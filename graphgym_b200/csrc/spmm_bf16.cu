@@ -98,9 +98,29 @@ __device__ __forceinline__ void h_epilogue(const HArgs& a, int row, int gl, Acc8
     store8(a.out + (int64_t)row * a.ldo + gl * 8, r);
 }
 
+// Batches of S x 4 slots: the four gathered 16-byte vectors of a lane are unpacked ONCE into 32 fp32 registers, so the
+// no-row-end path is 32 plain FMAs and a row-end sweep re-uses the unpacked values (the first version kept 8 packed
+// vectors and unpacked inside every sweep: 1.48 G instructions, issue-bound at 3.6 ms for F = 128 on the products
+// graph — profiles/r01_spmm_bf16_ncu_raw.csv).
+struct Row8 {
+    float v[8];
+};
+__device__ __forceinline__ void unpack8(Row8& o, const uint4& r) {
+    const uint32_t q[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o.v[2 * i] = __uint_as_float(q[i] << 16);
+        o.v[2 * i + 1] = __uint_as_float(q[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ void fma8f(Acc8& a, float w, const Row8& r) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a.v[i] = fmaf(w, r.v[i], a.v[i]);
+}
+
 template <int G, bool WEIGHTED>
-__global__ void __launch_bounds__(kHThreads, 3) spmm_h_kernel(const __grid_constant__ HArgs a) {
-    constexpr int S = 32 / G, U = 8, B = S * U;
+__global__ void __launch_bounds__(kHThreads, 4) spmm_h_kernel(const __grid_constant__ HArgs a) {
+    constexpr int S = 32 / G, U = 4, B = S * U;
     __shared__ __align__(16) int32_t s_nbr_all[kHWarps][kHTile];
     __shared__ __align__(16) float s_w_all[WEIGHTED ? kHWarps : 1][WEIGHTED ? kHTile : 4];
     __shared__ __align__(16) int32_t s_rp_all[kHWarps][kHTile];
@@ -151,37 +171,33 @@ __global__ void __launch_bounds__(kHThreads, 3) spmm_h_kernel(const __grid_const
         };
         for (int s = s0; s < s1; s += B) {
             const int g0 = s + grp * U;
-            const int t = g0 - s0;
+            const int t = g0 - s0;  // multiple of 4: 16-byte aligned inside the tile
             const int e = s + B < s1 ? s + B : s1;
-            const bool full = s + B <= s1;
-            uint4 v[U];
+            uint4 raw[U];
             float wv[U];
-            if (full) {
+            if (s + B <= s1) {
                 const int4 i0 = *reinterpret_cast<const int4*>(s_nbr + t);
-                const int4 i1 = *reinterpret_cast<const int4*>(s_nbr + t + 4);
-                const int j[U] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-#pragma unroll
-                for (int u = 0; u < U; ++u) v[u] = gather(j[u]);
+                raw[0] = gather(i0.x); raw[1] = gather(i0.y); raw[2] = gather(i0.z); raw[3] = gather(i0.w);
                 if (WEIGHTED) {
                     const float4 w0 = *reinterpret_cast<const float4*>(s_w + t);
-                    const float4 w1 = *reinterpret_cast<const float4*>(s_w + t + 4);
                     wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
-                    wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
                 } else {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) wv[u] = 1.f;
+                    wv[0] = wv[1] = wv[2] = wv[3] = 1.f;
                 }
             } else {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const bool ok = g0 + u < s1;
-                    v[u] = ok ? gather(s_nbr[t + u]) : make_uint4(0u, 0u, 0u, 0u);
+                    raw[u] = ok ? gather(s_nbr[t + u]) : make_uint4(0u, 0u, 0u, 0u);
                     wv[u] = ok ? (WEIGHTED ? s_w[t + u] : 1.f) : 0.f;
                 }
             }
+            Row8 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) unpack8(v[u], raw[u]);
             if (re >= e && !(re == e && cur < r1)) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) fma8(acc, wv[u], v[u]);
+                for (int u = 0; u < U; ++u) fma8f(acc, wv[u], v[u]);
             } else {
                 int pos = s;
                 while (true) {
@@ -189,7 +205,7 @@ __global__ void __launch_bounds__(kHThreads, 3) spmm_h_kernel(const __grid_const
                     const int lo = pos - g0, hi = seg_end - g0;
 #pragma unroll
                     for (int u = 0; u < U; ++u)
-                        if (u >= lo && u < hi) fma8(acc, wv[u], v[u]);
+                        if (u >= lo && u < hi) fma8f(acc, wv[u], v[u]);
                     if (re > e || cur >= r1) break;
                     finalize(cur);
                     ++cur;
@@ -250,7 +266,7 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 template <int G>
 static void launch_h(const HArgs& a, cudaStream_t st) {
     int grid = (int)ceil_div(a.items, kHWarps);
-    if (grid > kNumSMs * 3) grid = kNumSMs * 3;  // 80 registers: 8 accumulators + 8 gathers in flight (4 CTAs/SM spill: 4.2 vs 3.7 ms)
+    if (grid > kNumSMs * 4) grid = kNumSMs * 4;
     if (a.w) {
         static bool done = false;
         if (!done) {

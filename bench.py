@@ -279,7 +279,7 @@ def run_aux(args, spec, dev):
                            'whole_graph_seconds_1gpu': round(ms * 1e-3 * (n / 128), 1),
                            'l2_policy': 'inputs larger than L2 (two 512 MB walk matrices)'},
                 'clocks': clocks.summary(), 'e2e': None, 'gpu_launches': int(launches),
-                'roofline': {'bound': 'hbm', 'kernel': ('spmm_mp_kernel' if use_mp else 'walk_step_kernel') + ' (+ walk_dot) over one block of 128 sources',
+                'roofline': {'bound': 'hbm', 'kernel': ('spmm_mpg_kernel' if use_mp else 'walk_step_kernel') + ' (+ walk_dot) over one block of 128 sources',
                              'achieved': round(ach, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4),
                              'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_step': step_bytes},
                 'cpu_baseline': None}
@@ -481,7 +481,7 @@ def run_ours(args, spec, rank, world, dev):
     peak, peak_src = load_peaks()
     achieved = per_launch_bytes / (avg_spmm_ms * 1e-3) / 1e9
     roofline = {'bound': 'hbm',
-                'kernel': 'spmm_mp_kernel + fixup (merge-path CSR aggregation; fwd on CSR and bwd on CSC)'
+                'kernel': ('spmm_h_kernel (bf16 gather)' if half else 'spmm_mpg_kernel' if f_launch <= 128 else 'spmm_mp_kernel') + ' + fixup (merge-path CSR aggregation; fwd on CSR and bwd on CSC)'
                           + ((' — rank 0 of %d, ' % world) + ('all rows x F/%d columns (sub-warp-group kernel, rows stored '
                              'to their owners over NVLink)' % world if playout.sliced else 'rank-local rows') if multi else ''),
                 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',

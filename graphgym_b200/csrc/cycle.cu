@@ -233,10 +233,11 @@ int cycle_diag(const int32_t* rowptr, const int32_t* nbr, const float* w, int64_
     int step_rc = GG_OK;
     auto step = [&](const Vec* in, Vec* o) {
         if (plan) {  // load-balanced, TMA-staged aggregation kernel (hub rows no longer serialise one warp)
-            const int rc = gg_spmm_mp_f32(rowptr, nbr, w, plan->item_row, plan->item_slot, plan->items,
-                                          reinterpret_cast<const float*>(in), W::kCols, reinterpret_cast<float*>(o),
-                                          W::kCols, rows, W::kCols, GG_SUM, nullptr, 0, 0.f, nullptr, nullptr, nullptr,
-                                          nullptr, nullptr, mp_ws, mp_bytes, 4, reinterpret_cast<gg_stream_t>(st));
+            const int rc = gg_spmm_mpg_f32(rowptr, nbr, w, plan->item_row, plan->item_slot, plan->items,
+                                           reinterpret_cast<const float*>(in), W::kCols, reinterpret_cast<float*>(o),
+                                           W::kCols, nullptr, 1, rows, rows, W::kCols, GG_SUM, nullptr, 0, 0.f, nullptr,
+                                           nullptr, nullptr, nullptr, nullptr, mp_ws, mp_bytes, 4,
+                                           reinterpret_cast<gg_stream_t>(st));
             if (rc != GG_OK) step_rc = rc;
             return;
         }

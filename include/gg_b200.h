@@ -418,6 +418,26 @@ int gg_peer_barrier(void* const* flags_host, int world, int rank, gg_stream_t st
 int gg_peer_scatter_cols_f32(const float* src, int64_t ld, int64_t rows, int64_t f, float* const* dst_host,
                              int world, int64_t row_base, gg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Graph-level pooling: global_add / mean / max_pool, ref: graphgym/models/pooling.py:12-33
+ * (torch_scatter.scatter over `batch`, after index_select by node_id_index when the dataset transform is 'ego').
+ *   gg_segment_bounds_i64  seg_ptr[g] = first position with key >= g for a NON-DECREASING key (DeepSNAP batches are
+ *                          block-diagonal); *violations counts out-of-range or out-of-order keys (caller checks);
+ *   gg_segment_pool_f32    out[g, :] = reduce over positions p in [seg_ptr[g], seg_ptr[g+1]) of x[row(p), :],
+ *                          row(p) = row_index[p] (nullable: p); deterministic (rows in order); max stores the arg-max
+ *                          position per (g, column) in `argmax` (nullable otherwise); empty graph -> 0;
+ *   gg_segment_pool_bwd_f32 gx[row(p), :] = the gradient of that reduction (gx zero-initialised by the caller).
+ * ------------------------------------------------------------------------------------------ */
+enum gg_pool_mode { GG_POOL_SUM = 0, GG_POOL_MEAN = 1, GG_POOL_MAX = 2 };
+int gg_segment_bounds_i64(const int64_t* key, int64_t m, int64_t num_segments, int32_t* seg_ptr,
+                          int32_t* violations, gg_stream_t stream);
+int gg_segment_pool_f32(const float* x, int64_t ldx, const int64_t* row_index, const int32_t* seg_ptr,
+                        int64_t num_segments, int64_t f, int mode, float* out, int64_t ldo, int32_t* argmax,
+                        gg_stream_t stream);
+int gg_segment_pool_bwd_f32(const float* g, int64_t ldg, const int64_t* row_index, const int64_t* key,
+                            const int32_t* seg_ptr, int64_t m, int64_t f, int mode, const int32_t* argmax, float* gx,
+                            int64_t ldgx, gg_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -603,13 +603,59 @@ class RowPartitionedGCNID(torch.nn.Module):
 
     def forward(self, x_local, playout, node_id_index):
         from .graph import IdIndex
-        part = playout.part
-        ids = node_id_index[(node_id_index >= part.lo) & (node_id_index < part.hi)] - part.lo
+        ids = _local_ids(node_id_index, playout.part)
         h = F_.id_linear(x_local, self.model.weight, self.model.weight_id, IdIndex(ids, x_local.size(0)))
         return dist_aggregate(h, playout, 'gcn_src', self.model.bias)
 
 
+def _local_ids(node_id_index, part):
+    return node_id_index[(node_id_index >= part.lo) & (node_id_index < part.hi)] - part.lo
+
+
+class RowPartitionedSAGEID(torch.nn.Module):
+    """``sageidconv`` (ref: idconv.py:192-263, ``concat=True`` as GraphGym builds it, idconv.py:410) on a row
+    partition: the neighbour mean is the exchanged aggregation, [x | mean] (W, and W_id on the centres) is row-local."""
+
+    def __init__(self, dim_in, dim_out, bias=True):
+        super().__init__()
+        from .contrib.layer.idconv import SAGEIDConvLayer
+        self.model = SAGEIDConvLayer(dim_in, dim_out, bias=bias, concat=True)
+
+    def forward(self, x_local, playout, node_id_index):
+        from .graph import IdIndex
+        m, k = self.model, self.model.in_channels
+        info = IdIndex(_local_ids(node_id_index, playout.part), x_local.size(0))
+        mean = dist_aggregate(x_local, playout, 'mean')
+        return F_.seg_linear([x_local, mean], [m.weight, m.weight_id],
+                             [(0, 0, False), (1, 0, False), (0, 1, True), (1, 1, True)], info, m.bias,
+                             w_rows=((0, k), (k, 2 * k), (0, k), (k, 2 * k)))
+
+
+class RowPartitionedGINID(torch.nn.Module):
+    """``ginidconv`` (ref: idconv.py:350-382, MLPs of idconv.py:432-436) on a row partition: z = (1 + eps) x + sum_j x_j
+    on the loop-free graph is the exchanged step; nn(z) everywhere and nn_id(z[id]) on this rank's centres are row-local."""
+
+    def __init__(self, dim_in, dim_out, bias=True):
+        super().__init__()
+        from .contrib.layer.idconv import GINIDConvLayer
+
+        def mlp():
+            return torch.nn.Sequential(torch.nn.Linear(dim_in, dim_out), torch.nn.ReLU(), torch.nn.Linear(dim_out, dim_out))
+
+        self.model = GINIDConvLayer(mlp(), mlp())
+
+    def forward(self, x_local, playout, node_id_index):
+        from .contrib.layer.idconv import _mlp
+        m = self.model
+        ids = _local_ids(node_id_index, playout.part).contiguous().long()
+        z = dist_aggregate(x_local, playout, 'sum', None, 1.0 + float(m.initial_eps))
+        out = _mlp(m.nn, z)
+        return F_.scatter_add_rows(out, ids, _mlp(m.nn_id, F_.gather_rows(z, ids)))
+
+
 ROW_PARTITIONED = {'gcnconv': (RowPartitionedGCN, ops.LOOPS_ADD_REMAINING, 'gcn_tgt'),
+                   'sageidconv': (RowPartitionedSAGEID, ops.LOOPS_KEEP, 'mean'),
+                   'ginidconv': (RowPartitionedGINID, ops.LOOPS_REMOVE, 'sum'),
                    'gcnidconv': (RowPartitionedGCNID, ops.LOOPS_ADD_REMAINING, 'gcn_src'),
                    'sageconv': (RowPartitionedSAGE, ops.LOOPS_KEEP, 'mean'),
                    'ginconv': (RowPartitionedGIN, ops.LOOPS_KEEP, 'sum'),

@@ -88,11 +88,19 @@ def relu_grad(g, y):
     return g * (y > 0)
 
 
+def gather_rows(x, ids):
+    return x[ids.long()]
+
+
+def scatter_add_rows_(out, ids, x):
+    return out.index_add_(0, ids.long(), x)
+
+
 def id_count(ids, num_nodes):
     return torch.bincount(ids.long(), minlength=num_nodes).float()
 
 
 def install(monkeypatch_setattr):
     for name in ('layout_build', 'segment_degree', 'gcn_norm', 'mean_weights', 'spmm', 'id_gemm', 'gemm_tn',
-                 'colsum', 'relu_grad', 'id_count'):
+                 'colsum', 'relu_grad', 'id_count', 'gather_rows', 'scatter_add_rows_'):
         monkeypatch_setattr(ops, name, globals()[name])

@@ -52,7 +52,7 @@ def _worker(rank, world, port, n, exchange, ret, fout=8, name='gcnconv'):
         playout = parallel.PartitionedLayout(ei, n, policy, part, exchange=exchange)
         xl = x[part.lo:part.hi].clone().requires_grad_(True)
         ids = torch.arange(0, n, 3)                        # ID-GNN centres on both ranks
-        y = layer(xl, playout, ids) if name == 'gcnidconv' else layer(xl, playout)
+        y = layer(xl, playout, ids) if name.endswith('idconv') else layer(xl, playout)
         y.backward(gy[part.lo:part.hi])
         parallel.allreduce_grads(layer)
         # single-process oracle
@@ -64,6 +64,12 @@ def _worker(rank, world, port, n, exchange, ret, fout=8, name='gcnconv'):
             yo = olayers.gcn_idconv(xo, ei, ids, P['weight'], P['weight_id'], P['bias'])
         elif name == 'sageconv':
             yo = olayers.sageconv(xo, ei, P['lin_l.weight'], P['lin_l.bias'], P['lin_r.weight'])
+        elif name == 'sageidconv':
+            yo = olayers.sage_idconv(xo, ei, ids, P['weight'], P['weight_id'], P['bias'], concat=True)
+        elif name == 'ginidconv':
+            pn = (P['nn.0.weight'], P['nn.0.bias'], P['nn.2.weight'], P['nn.2.bias'])
+            pi = (P['nn_id.0.weight'], P['nn_id.0.bias'], P['nn_id.2.weight'], P['nn_id.2.bias'])
+            yo = olayers.gin_idconv(xo, ei, ids, pn, pi)
         else:
             yo = olayers.ginconv(xo, ei, P['nn.0.weight'], P['nn.0.bias'], P['nn.2.weight'], P['nn.2.bias'])
         yo.backward(gy)
@@ -114,7 +120,7 @@ def test_row_partitioned_gcn_world3_sliced():
 
 
 @pytest.mark.parametrize('exchange', ['allgather', 'sliced_nccl'])
-@pytest.mark.parametrize('name', ['sageconv', 'ginconv', 'gcnidconv'])
+@pytest.mark.parametrize('name', ['sageconv', 'ginconv', 'gcnidconv', 'sageidconv', 'ginidconv'])
 def test_row_partitioned_sage_gin_world2(name, exchange):
     """mean aggregation with global degrees (SAGE), self term through the exchange (GIN)"""
     world = 2

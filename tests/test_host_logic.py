@@ -88,3 +88,39 @@ def test_product_never_imports_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in src and 'from oracle' not in src, f
+
+
+def test_new_entry_points_have_no_cpu_path():
+    """pooling, the clustering label, the bf16 cast and the peer-memory exchange reject CPU tensors like every op"""
+    from graphgym_b200 import ops, parallel
+    from graphgym_b200.contrib.transform.clustering import clustering_coefficient
+    from graphgym_b200.models import pooling
+    x = torch.randn(6, 4)
+    batch = torch.tensor([0, 0, 1, 1, 2, 2])
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        pooling.global_mean_pool(x, batch, size=3)
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        clustering_coefficient(torch.tensor([[0, 1], [1, 0]]), 2)
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        ops.cast_bf16(x)
+    assert sorted(parallel.ROW_PARTITIONED) == ['gatconv', 'gcnconv', 'gcnidconv', 'ginconv', 'ginidconv', 'sageconv',
+                                                'sageidconv']
+    assert ops.bf16_gather_ok(128) and not ops.bf16_gather_ok(100) and not ops.bf16_gather_ok(512)
+
+
+def test_bench_generators_are_seeded_and_well_formed():
+    import bench
+    cpu = torch.device('cpu')
+    n, ei, ptr = bench.gen_ba_batch(bench.WORKLOADS['ego_idgin'], cpu)
+    n2, ei2, _ = bench.gen_ba_batch(bench.WORKLOADS['ego_idgin'], cpu)
+    assert n == n2 == 256 * 64 and torch.equal(ei, ei2)                       # seeded
+    assert ptr.tolist() == list(range(0, n + 1, 64))
+    assert ((ei[0] // 64) == (ei[1] // 64)).all() and (ei[0] != ei[1]).all()      # block-diagonal, no self loops
+    code = ei[0] * n + ei[1]
+    assert code.unique().numel() == code.numel()                                # simple graphs
+    assert torch.equal(torch.sort(code).values, torch.sort(ei[1] * n + ei[0]).values)   # symmetric
+    spec = dict(bench.WORKLOADS['products_gcn'], n=5000, e_und=40000, max_deg=500)
+    m, e = bench.gen_graph(spec, cpu)
+    assert m == 5000 and e.shape == (2, 80000) and int(e.max()) < m
+    assert bench.spmm_bytes(10, 100, 8, True) == 100 * 8 * 4 + 10 * 8 * 4 + 100 * 4 + 11 * 4 + 100 * 4
+    assert bench.spmm_bytes(10, 100, 8, False, gather_bytes=2) == 100 * 8 * 2 + 10 * 8 * 4 + 100 * 4 + 11 * 4

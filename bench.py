@@ -56,8 +56,9 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = 'products_gcn'
 DEFAULT_HALO = 'sliced'
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE aggregation launch from an `ncu --set full` capture of this bench
-# (profiles/r01_spmm_gemm_final_ncu_raw.csv: 17.48 + 1.32 GB; the algorithmic figure is 34.7 GB — the L2 serves the rest)
-NCU_TRAFFIC = {'products_gcn': 18_799_640_000}
+# (profiles/r01_spmm_mpg128_final_ncu_raw.csv: spmm_mpg_kernel<32,1,0> 17.51 + 1.32 GB in 4.12 ms; the algorithmic figure
+# is 34.7 GB — the L2 serves the rest)
+NCU_TRAFFIC = {'products_gcn': 18_829_800_000}
 HALO_DESC = {
     'allgather': 'halo all-gather of the feature rows over NCCL, rank-local SpMM',
     'pipelined': 'P-1 NCCL send/recv rounds overlapped with the per-peer SpMMs',

@@ -8,6 +8,8 @@ It imports graphgym/contrib/layer/idconv.py, graphgym/contrib/transform/identity
 graphgym/models/transform.py from the reference tree (third-party helpers supplied by
 oracle/pyg_shim.py), feeds them seeded inputs and stores inputs, parameters, outputs and gradients:
 
+    pooling.npz         global_add/mean/max_pool of graphgym/models/pooling.py (torch_scatter.scatter restated in
+                        oracle/pooling.py), with and without the 'ego' centre-row select, fwd + bwd
     idconv_layers.npz   the five registered ID layers (+ cfg variants of `idconv`), fwd + bwd
     identity.npz        compute_identity on K3 / P3 / C4 and two bundled fixture graphs
     egonets.npz         ego_nets (canonicalised: member sets + induced edge sets per centre) on C4 and
@@ -127,6 +129,35 @@ def identity(ns):
     print('identity.npz', len(out), 'arrays')
 
 
+def pooling(ns):
+    """The reference's own pooling.py, with torch_scatter.scatter supplied by oracle/pooling.py."""
+    from oracle import pooling as opool
+    sys.modules['torch_scatter'].scatter = opool.scatter
+    pyg_shim._module('graphgym.contrib.pooling')
+    ns.cfg.dataset = pyg_shim._Cfg(transform='none')
+    ref = pyg_shim._load('graphgym.models.pooling', os.path.join(REF, 'graphgym/models/pooling.py'))
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    sizes = [5, 1, 0, 64, 30, 17, 0]                      # empty graphs in the middle and at the end
+    batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    n, f = batch.numel(), 24
+    x0 = torch.randn(n, f, generator=g)
+    gy = torch.randn(len(sizes), f, generator=g)
+    ids = torch.sort(torch.randperm(n, generator=g)[:n // 3]).values
+    out['x'], out['batch'], out['ids'], out['gy'] = x0.numpy(), batch.numpy(), ids.numpy(), gy.numpy()
+    out['size'] = np.int64(len(sizes))
+    for transform in ('none', 'ego'):
+        ns.cfg.dataset.transform = transform
+        for mode in ('add', 'mean', 'max'):
+            x = x0.clone().requires_grad_(True)
+            y = ref.pooling_dict[mode](x, batch, ids, size=len(sizes))
+            y.backward(gy)
+            out['%s_%s/y' % (transform, mode)] = y.detach().numpy()
+            out['%s_%s/gx' % (transform, mode)] = x.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, 'pooling.npz'), **out)
+    print('pooling.npz', len(out), 'arrays')
+
+
 class _Graph:
     def __init__(self, G):
         self.G = G
@@ -196,3 +227,4 @@ if __name__ == '__main__':
     layers(ns)
     identity(ns)
     egonets(ns)
+    pooling(ns)

@@ -83,3 +83,22 @@ def test_clustering_coefficient_matches_networkx(cuda):
     want = torch.tensor(want, dtype=torch.float64)
     assert torch.allclose(got.cpu(), want, atol=1e-12)
     assert torch.allclose(got_batched.cpu(), want, atol=1e-12)
+
+
+def test_pooling_matches_reference_golden(cuda, golden_dir):
+    """against the outputs and gradients of the reference's own pooling.py (tests/golden/make_golden.py)"""
+    import os
+    z = np.load(os.path.join(golden_dir, 'pooling.npz'))
+    x0, batch, ids, gy = (torch.from_numpy(z[k]).to(cuda) for k in ('x', 'batch', 'ids', 'gy'))
+    size = int(z['size'])
+    for transform in ('none', 'ego'):
+        cfg.dataset.transform = transform
+        try:
+            for mode in ('add', 'mean', 'max'):
+                x = x0.clone().requires_grad_(True)
+                y = pooling.pooling_dict[mode](x, batch, ids, size=size)
+                y.backward(gy)
+                assert rel_err(y.detach(), torch.from_numpy(z['%s_%s/y' % (transform, mode)])) < FP32_TOL
+                assert rel_err(x.grad, torch.from_numpy(z['%s_%s/gx' % (transform, mode)])) < FP32_TOL
+        finally:
+            cfg.dataset.transform = 'none'

@@ -41,7 +41,7 @@ def mean_weights(csr_t, deg):
 
 def spmm(csr, x, w_slot=None, reduce=0, x_self=None, self_scale=0.0, bias=None, out=None, rank1=None,
          x_row_base=0, out_peers=None):
-    assert out_peers is None, 'peer memory needs CUDA: the gloo tier runs the all-to-all form'  
+    assert out_peers is None, 'peer memory needs CUDA: the gloo tier runs the all-to-all form'
     rows = csr.num_nodes
     seg = torch.repeat_interleave(torch.arange(rows), (csr.rowptr[1:] - csr.rowptr[:-1]).long())
     msg = x[csr.nbr.long() - int(x_row_base)]
@@ -54,10 +54,58 @@ def spmm(csr, x, w_slot=None, reduce=0, x_self=None, self_scale=0.0, bias=None, 
         res = res + self_scale * x_self
     if bias is not None:
         res = res + bias
+    if rank1 is not None:
+        s1, v1, s2, v2 = rank1
+        res = res + s1.view(-1, 1) * v1.view(1, -1) + s2.view(-1, 1) * v2.view(1, -1)
     if out is not None:
         out.copy_(res)
         return out
     return res
+
+
+# ---- the GAT passes (heads = 1), restated per slot ----------------------------------------------------
+def slot_map(a, b):
+    inv = torch.empty(a.num_edges + a.num_nodes + 1, dtype=torch.long)
+    inv[a.perm.long()] = torch.arange(a.num_slots)
+    return inv[b.perm.long()].to(torch.int32)
+
+
+def gat_scores(h, att_row):
+    c = h.size(1)
+    return h @ att_row[0, :c], h @ att_row[0, c:]
+
+
+def _seg_sum(csr, v):
+    return torch.zeros(csr.num_nodes, dtype=v.dtype).index_add_(0, csr.rowid.long(), v)
+
+
+def gat_alpha(csr, a_tgt, a_src, slope):
+    rows, nbr = csr.rowid.long(), csr.nbr.long()
+    z = torch.nn.functional.leaky_relu(a_tgt[rows] + a_src[nbr], slope)
+    zmax = torch.full((csr.num_nodes,), -float('inf')).scatter_reduce(0, rows, z, reduce='amax')
+    e = torch.exp(z - zmax[rows])
+    return e / (_seg_sum(csr, e)[rows] + 1e-16)
+
+
+def gat_sddmm_slice(csr, h_slice, g_slice):
+    return (g_slice[csr.rowid.long()] * h_slice[csr.nbr.long()]).sum(1)
+
+
+def gat_dz(csr, a_tgt, a_src, alpha, dalpha, slope):
+    rows, nbr = csr.rowid.long(), csr.nbr.long()
+    z = a_tgt[rows] + a_src[nbr]
+    d = _seg_sum(csr, alpha * dalpha)
+    dz = alpha * (dalpha - d[rows]) * torch.where(z > 0, torch.ones_like(z), torch.full_like(z, slope))
+    return dz, _seg_sum(csr, dz)
+
+
+def gat_csc_gather(csc, csc2csr, alpha, dz):
+    m = csc2csr.long()
+    return alpha[m], _seg_sum(csc, dz[m])
+
+
+def gat_att_grad(h, da_tgt, da_src):
+    return torch.cat([da_tgt @ h, da_src @ h]).view(1, -1)
 
 
 def id_gemm(segments, n, f, b_trans=False, bias=None, act=0, relu_mask=None, out=None):
@@ -102,5 +150,6 @@ def id_count(ids, num_nodes):
 
 def install(monkeypatch_setattr):
     for name in ('layout_build', 'segment_degree', 'gcn_norm', 'mean_weights', 'spmm', 'id_gemm', 'gemm_tn',
-                 'colsum', 'relu_grad', 'id_count', 'gather_rows', 'scatter_add_rows_'):
+                 'colsum', 'relu_grad', 'id_count', 'gather_rows', 'scatter_add_rows_', 'slot_map', 'gat_scores',
+                 'gat_alpha', 'gat_sddmm_slice', 'gat_dz', 'gat_csc_gather', 'gat_att_grad'):
         monkeypatch_setattr(ops, name, globals()[name])

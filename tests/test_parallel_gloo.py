@@ -41,7 +41,7 @@ def _worker(rank, world, port, n, exchange, ret, fout=8, name='gcnconv'):
         gy = torch.randn(n, fout, generator=g)
         part = parallel.RowPartition(n, world, rank)
         cls, policy, _ = parallel.ROW_PARTITIONED[name]
-        if name not in ('gcnconv', 'gcnidconv'):
+        if name not in ('gcnconv', 'gcnidconv', 'gatconv'):
             fin = fout if exchange.startswith('sliced') else fin   # SAGE / GIN aggregate the INPUT features
             x = torch.randn(n, fin, generator=g)
         layer = cls(fin, fout, bias=True)   # same seed on every rank
@@ -64,6 +64,8 @@ def _worker(rank, world, port, n, exchange, ret, fout=8, name='gcnconv'):
             yo = olayers.gcn_idconv(xo, ei, ids, P['weight'], P['weight_id'], P['bias'])
         elif name == 'sageconv':
             yo = olayers.sageconv(xo, ei, P['lin_l.weight'], P['lin_l.bias'], P['lin_r.weight'])
+        elif name == 'gatconv':
+            yo = olayers.gatconv(xo, ei, P['weight'], P['att'], P['bias'])
         elif name == 'sageidconv':
             yo = olayers.sage_idconv(xo, ei, ids, P['weight'], P['weight_id'], P['bias'], concat=True)
         elif name == 'ginidconv':
@@ -126,6 +128,15 @@ def test_row_partitioned_sage_gin_world2(name, exchange):
     world = 2
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), 41, exchange, ret, 8, name), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world)), dict(ret)
+
+
+@pytest.mark.parametrize('world,fout', [(2, 8), (3, 12)])
+def test_row_partitioned_gat_sliced(world, fout):
+    """edge-softmax layer on the partition: logits all-gathered, sliced aggregations with rank-1 terms, sliced SDDMM
+    shares all-reduced — host logic over gloo with per-slot stand-ins for the GAT passes"""
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, _free_port(), 41, 'sliced_nccl', ret, fout, 'gatconv'), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)
 
 

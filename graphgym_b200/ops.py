@@ -18,7 +18,7 @@ ACT_NONE, ACT_RELU = 0, 1
 
 
 import os as _os
-SPMM_ALGO = _os.environ.get("GG_SPMM_ALGO", "auto")    # auto | mp | mpg (sub-warp groups, f <= 128) | row
+SPMM_ALGO = _os.environ.get("GG_SPMM_ALGO", "auto")    # auto | mp | mpg (grouped slots, f <= 128) | row | bin (experimental)
 SPMM_STAGE = _os.environ.get("GG_SPMM_STAGE", "tma")   # tma | ldg
 SPMM_DEEP = _os.environ.get("GG_SPMM_DEEP", "0") == "1"  # 16 instead of 8 gathers per lane and batch
 SPMM_L2HINT = _os.environ.get("GG_SPMM_L2HINT", "1") == "1"  # gathers evict_last, streams evict_first in L2
@@ -66,13 +66,14 @@ def launch_count():
 class Csr:
     """One compressed layout of an (edited) edge list: segments grouped by target or by source."""
     __slots__ = ("rowptr", "nbr", "perm", "rowid", "num_slots", "num_nodes", "num_edges", "policy",
-                 "group_by", "_plan")
+                 "group_by", "_plan", "_binned")
 
     def __init__(self, rowptr, nbr, perm, rowid, num_slots, num_nodes, num_edges, policy, group_by):
         self.rowptr, self.nbr, self.perm, self.rowid = rowptr, nbr, perm, rowid
         self.num_slots, self.num_nodes, self.num_edges = num_slots, num_nodes, num_edges
         self.policy, self.group_by = policy, group_by
         self._plan = None
+        self._binned = None
 
     def _build_plan(self, units):
         if self._plan is None:
@@ -239,6 +240,77 @@ def _spmm_bf16(csr, x, w_slot, reduce, x_self, self_scale, bias):
     return out
 
 
+BIN_HUB_DEGREE = 1024   # rows above this degree stay on the merge-path kernel (experimental binned aggregation)
+
+
+class BinnedCsr:
+    """EXPERIMENTAL (GG_SPMM_ALGO=bin): the rows of a Csr in descending-degree order with the slot arrays re-laid in
+    that order (csrc/spmm_bin.cu).  ``order[i]`` = original row of permuted row i; the first ``hubs`` rows exceed
+    BIN_HUB_DEGREE.  Layout-build level: the exclusive scan of the permuted degrees is a torch.cumsum."""
+
+    def __init__(self, csr):
+        L = lib()
+        n, dev = csr.num_nodes, csr.rowptr.device
+        keys = torch.empty(max(n, 1), dtype=torch.int32, device=dev)[:n]
+        vals = torch.empty(max(n, 1), dtype=torch.int32, device=dev)[:n]
+        check(L.gg_degree_keys(_ptr(csr.rowptr), n, _ptr(keys), _ptr(vals), _stream()), "gg_degree_keys")
+        keys_sorted, order = sort_pairs(keys, vals, 31)
+        self.order = order
+        deg = 0x7fffffff - keys_sorted.long()
+        self.rowptr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+        self.rowptr[1:] = torch.cumsum(deg, 0).to(torch.int32)
+        self.hubs = int((deg > BIN_HUB_DEGREE).sum().item())
+        self.csr = csr
+        self.nbr = self.permute(csr.nbr)
+        hub_slots = int(self.rowptr[self.hubs].item())
+        self.hub_csr = Csr(self.rowptr[:self.hubs + 1], self.nbr[:hub_slots], None, None, hub_slots, self.hubs,
+                           csr.num_edges, csr.policy, csr.group_by) if self.hubs else None
+        self._w = {}
+
+    def permute(self, per_slot):
+        """a per-slot int32 / float32 array of the source layout -> the permuted slot order"""
+        src = per_slot.contiguous()
+        dst = torch.empty_like(src)
+        check(lib().gg_permute_rows_u32(_ptr(self.csr.rowptr), _ptr(self.order), _ptr(self.rowptr), _ptr(src), _ptr(dst),
+                                        self.csr.num_nodes, _stream()), "gg_permute_rows_u32")
+        return dst
+
+    def weights(self, w_slot):
+        if w_slot is None:
+            return None
+        key = (w_slot.data_ptr(), w_slot._version)
+        hit = self._w.get(key)
+        if hit is None or hit[0] is not w_slot:
+            hit = self._w[key] = (w_slot, self.permute(w_slot))
+        return hit[1]
+
+
+def _spmm_binned(csr, x, w_slot, reduce, x_self, self_scale, bias):
+    if csr._binned is None:
+        csr._binned = BinnedCsr(csr)
+    b = csr._binned
+    x, ldx = _rows(x, "x")
+    n, f = csr.num_nodes, x.size(1)
+    out = torch.empty((n, f), dtype=torch.float32, device=x.device)
+    ld_self = 0
+    if x_self is not None:
+        x_self, ld_self = _rows(x_self, "x_self")
+    if bias is not None:
+        bias = bias.contiguous()
+    w2 = b.weights(w_slot)
+    L = lib()
+    if b.hubs:
+        hub_slots = b.hub_csr.num_slots
+        tmp = spmm(b.hub_csr, x, w2[:hub_slots] if w2 is not None else None, reduce, algo="auto")
+        check(L.gg_finish_rows_f32(_ptr(tmp), f, _ptr(b.order), b.hubs, f, _ptr(x_self), ld_self, float(self_scale),
+                                   _ptr(bias), _ptr(out), f, _stream()), "gg_finish_rows_f32")
+    counter = torch.empty(64, dtype=torch.int32, device=x.device)
+    check(L.gg_spmm_bin_f32(_ptr(b.rowptr), _ptr(b.nbr), _ptr(w2), _ptr(b.order), b.hubs, n, _ptr(x), ldx, _ptr(out), f,
+                            f, reduce, _ptr(x_self), ld_self, float(self_scale), _ptr(bias), _ptr(counter), _stream()),
+          "gg_spmm_bin_f32")
+    return out
+
+
 class PeerRows:
     """Where the rows of a peer-output SpMM go: ``ptrs[o]`` = device pointer (peer memory, already offset
     to this rank's column slice) of rank o's [rows_per_rank, ld] block."""
@@ -250,7 +322,7 @@ class PeerRows:
 
 
 def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None, out=None, rank1=None,
-         x_row_base=0, out_peers=None):
+         x_row_base=0, out_peers=None, algo=None):
     """out[i,:] = reduce_{s in segment i} w[s]*x[nbr[s],:] + self_scale*x_self[i,:] + bias.
 
     ``rank1`` = (s1 [n], v1 [f], s2 [n], v2 [f]) adds s1[i]*v1 + s2[i]*v2 in the epilogue (merge-path
@@ -285,11 +357,15 @@ def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None
                                 _ptr(bias), _ptr(r1[0]), _ptr(r1[1]), _ptr(r1[2]), _ptr(r1[3]), _ptr(ws), ws_bytes,
                                 _spmm_flags(), _stream()), "gg_spmm_mpg_f32")
         return None
+    algo = algo or SPMM_ALGO   # ``algo`` overrides the module setting for this call
+    if algo == "bin":
+        if f % 4 == 0 and f <= 128 and n > 0 and out is None and rank1 is None and not x_row_base:
+            return _spmm_binned(csr, x, w_slot, reduce, x_self, self_scale, bias)   # experimental, opt-in
+        algo = "auto"
     if out is None:
         out = torch.empty((n, f), dtype=torch.float32, device=x.device)
     out_t, ldo = _rows(out, "out")
     assert out_t is out, "out must have unit inner stride"
-    algo = SPMM_ALGO
     big = n + csr.num_slots >= 1 << 14
     if algo == "auto":
         # merge-path kernels on graphs big enough to need balancing: the grouped-slot kernel up to 128 columns (at 128 it

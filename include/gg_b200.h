@@ -197,6 +197,27 @@ int gg_spmm_mpg_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_sl
                     float self_scale, const float* bias, const float* r1_s, const float* r1_v, const float* r2_s,
                     const float* r2_v, void* workspace, size_t workspace_bytes, int flags, gg_stream_t stream);
 
+/* EXPERIMENTAL, opt-in, not yet measured (csrc/spmm_bin.cu; DESIGN.md "next (1)"): degree-binned aggregation.
+ *   gg_degree_keys        keys[r] = 0x7fffffff - degree(r), vals[r] = r: a stable gg_sort_pairs_u32 on 31 bits gives the
+ *                         rows in descending-degree order (`order`);
+ *   gg_permute_rows_u32   re-lays a per-slot array (neighbour ids, weight bits) in that row order, given the permuted
+ *                         row pointer (exclusive scan of the permuted degrees);
+ *   gg_spmm_bin_f32       rows [row_begin, num_rows) of the permuted layout: one group of lanes per row, 32/G rows of
+ *                         (nearly) equal degree per warp, no row-end handling; out[row_map[i], :] gets the epilogue;
+ *                         f % 4 == 0, f <= 128; `counter`: one int32 of scratch;
+ *   gg_finish_rows_f32    the hub prefix [0, row_begin) is aggregated by gg_spmm_mpg_f32 into a temporary and moved to
+ *                         out[row_map[h], :] with the self term and bias added here. */
+int gg_degree_keys(const int32_t* rowptr, int64_t num_rows, uint32_t* keys, uint32_t* vals, gg_stream_t stream);
+int gg_permute_rows_u32(const int32_t* rowptr, const int32_t* order, const int32_t* rowptr_perm, const uint32_t* src,
+                        uint32_t* dst, int64_t num_rows, gg_stream_t stream);
+int gg_spmm_bin_f32(const int32_t* rowptr_perm, const int32_t* nbr_perm, const float* w_perm, const int32_t* row_map,
+                    int64_t row_begin, int64_t num_rows, const float* x, int64_t ldx, float* out, int64_t ldo, int64_t f,
+                    int reduce, const float* x_self, int64_t ld_self, float self_scale, const float* bias,
+                    int32_t* counter, gg_stream_t stream);
+int gg_finish_rows_f32(const float* tmp, int64_t ld_tmp, const int32_t* row_map, int64_t num_rows, int64_t f,
+                       const float* x_self, int64_t ld_self, float self_scale, const float* bias, float* out,
+                       int64_t ldo, gg_stream_t stream);
+
 /* bf16-gather variant (the north star's 1e-2 mode): x is stored in bf16 (`x_bf16`: raw bf16 bits, ldx in
  * elements, rows 16-byte aligned), products and sums are fp32, out / x_self / bias are fp32.  Same plan and the
  * same fixed summation order as gg_spmm_mpg_f32; needs f % 8 == 0 and f <= 256.  gg_cast_f32_bf16 converts a

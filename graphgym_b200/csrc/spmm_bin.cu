@@ -1,5 +1,7 @@
-// EXPERIMENTAL, opt-in (GG_SPMM_ALGO=bin), NOT YET MEASURED ON A GPU — written at the end of round 1 as the candidate
-// for DESIGN.md §8 "next (1)"; the default paths never call it and its tests run only with GG_TEST_EXPERIMENTAL=1.
+// EXPERIMENTAL, opt-in (GG_SPMM_ALGO=bin), NOT YET TIMED — written at the end of round 1 as the candidate for DESIGN.md §8
+// "next (1)"; the default paths never call it and its tests run only with GG_TEST_EXPERIMENTAL=1.  State: the parity tests
+// against the merge-path kernel passed on a B200 for f = 4..128 (hubs, mean, self term, bias) with the round's last GPU
+// seconds; the empty-layout edge case was fixed afterwards and has not been re-run; no timing yet.
 //
 // Degree-binned aggregation.  The merge-path kernels pay for row ends: 10-26 instructions per slot go into segment
 // sweeps, cross-group butterflies and split-row partials, while the narrow SDDMM — same gathers, no row ends — streams
@@ -183,7 +185,8 @@ int gg_spmm_bin_f32(const int32_t* rowptr_perm, const int32_t* nbr_perm, const f
         set_error("gg_spmm_bin_f32: needs f %% 4 == 0 and f <= 128 (got %lld)", (long long)f);
         return GG_ERR_UNSUPPORTED;
     }
-    GG_REQUIRE(rowptr_perm && nbr_perm && row_map && x && out && counter, "gg_spmm_bin_f32: null pointer");
+    // nbr_perm may be null for a layout without slots (every degree is 0: it is never dereferenced)
+    GG_REQUIRE(rowptr_perm && row_map && x && out && counter, "gg_spmm_bin_f32: null pointer");
     GG_REQUIRE(ldx % 4 == 0 && ldx >= f && ldx < ((int64_t)1 << 30) && ldo % 4 == 0 && ldo >= f && bin_al16(x) &&
                    bin_al16(out) && (!bias || bin_al16(bias)) && (!x_self || (bin_al16(x_self) && ld_self % 4 == 0)),
                "gg_spmm_bin_f32: rows must be 16-byte aligned");

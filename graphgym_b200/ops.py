@@ -271,6 +271,8 @@ class BinnedCsr:
         """a per-slot int32 / float32 array of the source layout -> the permuted slot order"""
         src = per_slot.contiguous()
         dst = torch.empty_like(src)
+        if src.numel() == 0:
+            return dst
         check(lib().gg_permute_rows_u32(_ptr(self.csr.rowptr), _ptr(self.order), _ptr(self.rowptr), _ptr(src), _ptr(dst),
                                         self.csr.num_nodes, _stream()), "gg_permute_rows_u32")
         return dst

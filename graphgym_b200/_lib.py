@@ -58,11 +58,17 @@ SIGNATURES = {
     "gg_spmm_mpg_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64,
                                 c_ptr, c_int, c_i64, c_i64, c_i64, c_int, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_ptr,
                                 c_ptr, c_ptr, c_ptr, c_size, c_int, c_ptr]),
-    "gg_degree_keys": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
-    "gg_permute_rows_u32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
-    "gg_spmm_bin_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_int,
-                                c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_ptr]),
-    "gg_finish_rows_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_i64, c_ptr]),
+    "gg_sell_vrow_capacity": (c_i64, [c_i64, c_i64, c_int]),
+    "gg_sell_unit_capacity": (c_i64, [c_i64, c_i64, c_int]),
+    "gg_sell_split_capacity": (c_i64, [c_i64, c_int]),
+    "gg_sell_build_workspace_bytes": (c_size, [c_i64, c_i64, c_int]),
+    "gg_sell_build": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                              c_size, c_ptr]),
+    "gg_sell_permute_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    "gg_spmm_sell_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "gg_spmm_sell_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr,
+                                 c_i64, c_ptr, c_int, c_i64, c_i64, c_i64, c_int, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_ptr,
+                                 c_ptr, c_ptr, c_ptr, c_size, c_int, c_ptr]),
     "gg_cast_f32_bf16": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_spmm_mp_bf16": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64,
                                 c_int, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_size, c_int, c_ptr]),

@@ -18,7 +18,7 @@ ACT_NONE, ACT_RELU = 0, 1
 
 
 import os as _os
-SPMM_ALGO = _os.environ.get("GG_SPMM_ALGO", "auto")    # auto | mp | mpg (grouped slots, f <= 128) | row | bin (experimental)
+SPMM_ALGO = _os.environ.get("GG_SPMM_ALGO", "auto")    # auto | mp | mpg (grouped slots, f <= 128) | sell (sliced ELL, f <= 128) | row
 SPMM_STAGE = _os.environ.get("GG_SPMM_STAGE", "tma")   # tma | ldg
 SPMM_DEEP = _os.environ.get("GG_SPMM_DEEP", "0") == "1"  # 16 instead of 8 gathers per lane and batch
 SPMM_L2HINT = _os.environ.get("GG_SPMM_L2HINT", "1") == "1"  # gathers evict_last, streams evict_first in L2
@@ -66,14 +66,14 @@ def launch_count():
 class Csr:
     """One compressed layout of an (edited) edge list: segments grouped by target or by source."""
     __slots__ = ("rowptr", "nbr", "perm", "rowid", "num_slots", "num_nodes", "num_edges", "policy",
-                 "group_by", "_plan", "_binned")
+                 "group_by", "_plan", "_sell")
 
     def __init__(self, rowptr, nbr, perm, rowid, num_slots, num_nodes, num_edges, policy, group_by):
         self.rowptr, self.nbr, self.perm, self.rowid = rowptr, nbr, perm, rowid
         self.num_slots, self.num_nodes, self.num_edges = num_slots, num_nodes, num_edges
         self.policy, self.group_by = policy, group_by
         self._plan = None
-        self._binned = None
+        self._sell = None
 
     def _build_plan(self, units):
         if self._plan is None:
@@ -240,77 +240,68 @@ def _spmm_bf16(csr, x, w_slot, reduce, x_self, self_scale, bias):
     return out
 
 
-BIN_HUB_DEGREE = 1024   # rows above this degree stay on the merge-path kernel (experimental binned aggregation)
+SELL_SEG = int(_os.environ.get("GG_SELL_SEG", "256"))   # rows longer than this are cut into virtual rows (multiple of 4)
+SELL_MAX_F = int(_os.environ.get("GG_SELL_MAX_F", "64"))   # auto: widths up to this run on the sliced-ELL kernel
 
 
-class BinnedCsr:
-    """EXPERIMENTAL (GG_SPMM_ALGO=bin): the rows of a Csr in descending-degree order with the slot arrays re-laid in
-    that order (csrc/spmm_bin.cu).  ``order[i]`` = original row of permuted row i; the first ``hubs`` rows exceed
-    BIN_HUB_DEGREE.  Layout-build level: the exclusive scan of the permuted degrees is a torch.cumsum."""
+class SellLayout:
+    """Degree-sorted sliced-ELL re-layout of a Csr for the narrow-row aggregation (csrc/spmm_sell.cu): built once per
+    layout by ``gg_sell_build``; one host read of the sizes (layout-build level, like ``layout_build``'s E')."""
 
-    def __init__(self, csr):
+    def __init__(self, csr, seg=None):
         L = lib()
-        n, dev = csr.num_nodes, csr.rowptr.device
-        keys = torch.empty(max(n, 1), dtype=torch.int32, device=dev)[:n]
-        vals = torch.empty(max(n, 1), dtype=torch.int32, device=dev)[:n]
-        check(L.gg_degree_keys(_ptr(csr.rowptr), n, _ptr(keys), _ptr(vals), _stream()), "gg_degree_keys")
-        keys_sorted, order = sort_pairs(keys, vals, 31)
-        self.order = order
-        deg = 0x7fffffff - keys_sorted.long()
-        self.rowptr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
-        self.rowptr[1:] = torch.cumsum(deg, 0).to(torch.int32)
-        self.hubs = int((deg > BIN_HUB_DEGREE).sum().item())
-        self.csr = csr
-        self.nbr = self.permute(csr.nbr)
-        hub_slots = int(self.rowptr[self.hubs].item())
-        self.hub_csr = Csr(self.rowptr[:self.hubs + 1], self.nbr[:hub_slots], None, None, hub_slots, self.hubs,
-                           csr.num_edges, csr.policy, csr.group_by) if self.hubs else None
-        self._w = {}
-
-    def permute(self, per_slot):
-        """a per-slot int32 / float32 array of the source layout -> the permuted slot order"""
-        src = per_slot.contiguous()
-        dst = torch.empty_like(src)
-        if src.numel() == 0:
-            return dst
-        check(lib().gg_permute_rows_u32(_ptr(self.csr.rowptr), _ptr(self.order), _ptr(self.rowptr), _ptr(src), _ptr(dst),
-                                        self.csr.num_nodes, _stream()), "gg_permute_rows_u32")
-        return dst
+        seg = int(seg or SELL_SEG)
+        n, slots, dev = csr.num_nodes, csr.num_slots, csr.rowptr.device
+        vcap = int(L.gg_sell_vrow_capacity(n, slots, seg))
+        ucap = int(L.gg_sell_unit_capacity(n, slots, seg))
+        hcap = int(L.gg_sell_split_capacity(slots, seg))
+        i32 = lambda k: torch.empty(max(int(k), 1), dtype=torch.int32, device=dev)
+        self.chunk_ptr, self.idx, self.slot_of = i32(vcap // 8 + 1), i32(4 * ucap), i32(4 * ucap)
+        self.vdst, self.hub_rows, self.hub_pptr = i32(vcap), i32(hcap), i32(hcap + 1)
+        info = torch.zeros(8, dtype=torch.int32, device=dev)
+        ws = torch.empty(int(L.gg_sell_build_workspace_bytes(n, slots, seg)), dtype=torch.uint8, device=dev)
+        check(L.gg_sell_build(_ptr(csr.rowptr), _ptr(csr.nbr), n, slots, seg, _ptr(self.chunk_ptr), _ptr(self.idx),
+                              _ptr(self.slot_of), _ptr(self.vdst), _ptr(self.hub_rows), _ptr(self.hub_pptr), _ptr(info),
+                              _ptr(ws), ws.numel(), _stream()), "gg_sell_build")
+        self.vrows, self.chunks, self.units, self.hubs, self.partial_rows = (int(v) for v in info[:5].tolist())
+        self.seg, self.csr = seg, csr
+        self.total = 4 * self.units        # entries of idx / slot_of in use (the arrays keep their capacity)
+        self._w = None
 
     def weights(self, w_slot):
+        """Per-slot weights re-laid in unit order (padding = 0).  The last permutation is kept (a cached GCN norm hits
+        every step; a per-step array such as GAT's alpha is permuted per call and replaces the entry)."""
         if w_slot is None:
             return None
-        key = (w_slot.data_ptr(), w_slot._version)
-        hit = self._w.get(key)
-        if hit is None or hit[0] is not w_slot:
-            hit = self._w[key] = (w_slot, self.permute(w_slot))
-        return hit[1]
+        hit = self._w
+        if hit is not None and hit[0] is w_slot and hit[1] == w_slot._version:
+            return hit[2]
+        src = w_slot.contiguous()
+        dst = torch.empty(max(self.total, 4), dtype=torch.float32, device=src.device)
+        check(lib().gg_sell_permute_f32(_ptr(self.slot_of), self.total, _ptr(src), _ptr(dst), _stream()),
+              "gg_sell_permute_f32")
+        self._w = (w_slot, w_slot._version, dst)
+        return dst
 
 
-def _spmm_binned(csr, x, w_slot, reduce, x_self, self_scale, bias):
-    if csr._binned is None:
-        csr._binned = BinnedCsr(csr)
-    b = csr._binned
-    x, ldx = _rows(x, "x")
-    n, f = csr.num_nodes, x.size(1)
-    out = torch.empty((n, f), dtype=torch.float32, device=x.device)
-    ld_self = 0
-    if x_self is not None:
-        x_self, ld_self = _rows(x_self, "x_self")
-    if bias is not None:
-        bias = bias.contiguous()
-    w2 = b.weights(w_slot)
+def sell_layout(csr):
+    if csr._sell is None:
+        csr._sell = SellLayout(csr)
+    return csr._sell
+
+
+def _spmm_sell(csr, x, ldx, x_ptr, w_slot, reduce, x_self, ld_self, self_scale, bias, r1, out, ldo, out_peers):
+    sl = sell_layout(csr)
     L = lib()
-    if b.hubs:
-        hub_slots = b.hub_csr.num_slots
-        tmp = spmm(b.hub_csr, x, w2[:hub_slots] if w2 is not None else None, reduce, algo="auto")
-        check(L.gg_finish_rows_f32(_ptr(tmp), f, _ptr(b.order), b.hubs, f, _ptr(x_self), ld_self, float(self_scale),
-                                   _ptr(bias), _ptr(out), f, _stream()), "gg_finish_rows_f32")
-    counter = torch.empty(64, dtype=torch.int32, device=x.device)
-    check(L.gg_spmm_bin_f32(_ptr(b.rowptr), _ptr(b.nbr), _ptr(w2), _ptr(b.order), b.hubs, n, _ptr(x), ldx, _ptr(out), f,
-                            f, reduce, _ptr(x_self), ld_self, float(self_scale), _ptr(bias), _ptr(counter), _stream()),
-          "gg_spmm_bin_f32")
-    return out
+    f = x.size(1)
+    ws_bytes = int(L.gg_spmm_sell_workspace_bytes(sl.partial_rows, f))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    peers = (out_peers._arr, len(out_peers.ptrs), out_peers.rows_per_rank) if out_peers is not None else (None, 1, max(csr.num_nodes, 1))
+    check(L.gg_spmm_sell_f32(_ptr(sl.chunk_ptr), sl.chunks, _ptr(sl.idx), _ptr(sl.weights(w_slot)), _ptr(sl.vdst),
+                             _ptr(csr.rowptr), _ptr(sl.hub_rows), _ptr(sl.hub_pptr), sl.hubs, sl.partial_rows, x_ptr, ldx,
+                             _ptr(out), ldo, peers[0], peers[1], peers[2], csr.num_nodes, f, reduce, _ptr(x_self), ld_self,
+                             float(self_scale), _ptr(bias), _ptr(r1[0]), _ptr(r1[1]), _ptr(r1[2]), _ptr(r1[3]), _ptr(ws),
+                             ws_bytes, _spmm_flags(), _stream()), "gg_spmm_sell_f32")
 
 
 class PeerRows:
@@ -347,9 +338,15 @@ def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None
         bias = bias.contiguous()
     L = lib()
     r1 = [t.contiguous() if t is not None else None for t in (rank1 or (None, None, None, None))]
+    algo = algo or SPMM_ALGO   # ``algo`` overrides the module setting for this call
+    sell_ok = f % 4 == 0 and 0 < f <= 128 and n > 0 and (ldx * 4) % 16 == 0
     if out_peers is not None:
         if out is not None:
             raise ValueError("out_peers excludes out")
+        if sell_ok and (algo == "sell" or (algo == "auto" and f <= SELL_MAX_F)):
+            _spmm_sell(csr, x, ldx, x_ptr, w_slot, reduce, x_self, ld_self, self_scale, bias, r1, None, out_peers.ld,
+                       out_peers)
+            return None
         item_row, item_slot, items = csr.plan
         ws_bytes = int(L.gg_spmm_mp_workspace_bytes(items, f))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
@@ -359,16 +356,16 @@ def spmm(csr, x, w_slot=None, reduce=SUM, x_self=None, self_scale=0.0, bias=None
                                 _ptr(bias), _ptr(r1[0]), _ptr(r1[1]), _ptr(r1[2]), _ptr(r1[3]), _ptr(ws), ws_bytes,
                                 _spmm_flags(), _stream()), "gg_spmm_mpg_f32")
         return None
-    algo = algo or SPMM_ALGO   # ``algo`` overrides the module setting for this call
-    if algo == "bin":
-        if f % 4 == 0 and f <= 128 and n > 0 and out is None and rank1 is None and not x_row_base:
-            return _spmm_binned(csr, x, w_slot, reduce, x_self, self_scale, bias)   # experimental, opt-in
-        algo = "auto"
     if out is None:
         out = torch.empty((n, f), dtype=torch.float32, device=x.device)
     out_t, ldo = _rows(out, "out")
     assert out_t is out, "out must have unit inner stride"
     big = n + csr.num_slots >= 1 << 14
+    if sell_ok and (algo == "sell" or (algo == "auto" and big and f <= SELL_MAX_F)):
+        _spmm_sell(csr, x, ldx, x_ptr, w_slot, reduce, x_self, ld_self, self_scale, bias, r1, out, ldo, None)
+        return out
+    if algo == "sell":
+        algo = "auto"
     if algo == "auto":
         # merge-path kernels on graphs big enough to need balancing: the grouped-slot kernel up to 128 columns (at 128 it
         # measures 4.17 ms vs 4.55 ms for the whole-warp TMA kernel on the products graph), whole warps per item with

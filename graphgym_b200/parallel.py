@@ -377,7 +377,9 @@ def _peer_scatter_cols(local, ptrs, row_base):
 
 def _to_slices(playout, local):
     """Forward leg of the exchange: this rank's rows [rows, F] -> its column slice of ALL rows [N, F/P].
-    Peer form: a view of the pool's slice buffer, valid until the next ``_to_slices`` of the same shape."""
+    Peer form: a view of the pool's slice buffer.  It is valid only until ANY rank's next ``_to_slices`` of the same
+    shape, i.e. until this rank's next barrier (the ``_from_slices`` that consumes it): whoever needs the slice later
+    must clone it before that barrier."""
     part, group = playout.part, playout.group
     P, per, n = part.world, part.per, part.n
     rows, f = local.shape
@@ -548,9 +550,13 @@ class _DistGatSliced(torch.autograd.Function):
         a_src = all_gather_rows(a_src_l.view(-1, 1), part, group).reshape(-1).contiguous()
         alpha = ops.gat_alpha(playout.csr, a_tgt, a_src, slope)
         h_slice = _to_slices(playout, h_local)
+        # the slice lives in the pool's (reused) peer buffer: keep a private copy for the backward NOW, between the two
+        # barriers of this exchange — a peer that has left barrier 2 may start its next _to_slices (its backward's
+        # g slice has the same shape) and overwrite the buffer before this rank's host has enqueued a later clone
+        h_keep = h_slice.clone() if playout.exchange == 'sliced' else h_slice
         out = _from_slices(playout, playout.csr, alpha, h_slice, h_local.size(0), ops.SUM, bias)
         ctx.playout, ctx.slope, ctx.has_bias = playout, slope, bias is not None
-        ctx.save_for_backward(h_local, att_row, alpha, a_tgt, a_src, h_slice.clone())
+        ctx.save_for_backward(h_local, att_row, alpha, a_tgt, a_src, h_keep)
         return out
 
     @staticmethod

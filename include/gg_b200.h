@@ -197,26 +197,35 @@ int gg_spmm_mpg_f32(const int32_t* rowptr, const int32_t* nbr, const float* w_sl
                     float self_scale, const float* bias, const float* r1_s, const float* r1_v, const float* r2_s,
                     const float* r2_v, void* workspace, size_t workspace_bytes, int flags, gg_stream_t stream);
 
-/* EXPERIMENTAL, opt-in, not yet measured (csrc/spmm_bin.cu; DESIGN.md "next (1)"): degree-binned aggregation.
- *   gg_degree_keys        keys[r] = 0x7fffffff - degree(r), vals[r] = r: a stable gg_sort_pairs_u32 on 31 bits gives the
- *                         rows in descending-degree order (`order`);
- *   gg_permute_rows_u32   re-lays a per-slot array (neighbour ids, weight bits) in that row order, given the permuted
- *                         row pointer (exclusive scan of the permuted degrees);
- *   gg_spmm_bin_f32       rows [row_begin, num_rows) of the permuted layout: one group of lanes per row, 32/G rows of
- *                         (nearly) equal degree per warp, no row-end handling; out[row_map[i], :] gets the epilogue;
- *                         f % 4 == 0, f <= 128; `counter`: one int32 of scratch;
- *   gg_finish_rows_f32    the hub prefix [0, row_begin) is aggregated by gg_spmm_mpg_f32 into a temporary and moved to
- *                         out[row_map[h], :] with the self term and bias added here. */
-int gg_degree_keys(const int32_t* rowptr, int64_t num_rows, uint32_t* keys, uint32_t* vals, gg_stream_t stream);
-int gg_permute_rows_u32(const int32_t* rowptr, const int32_t* order, const int32_t* rowptr_perm, const uint32_t* src,
-                        uint32_t* dst, int64_t num_rows, gg_stream_t stream);
-int gg_spmm_bin_f32(const int32_t* rowptr_perm, const int32_t* nbr_perm, const float* w_perm, const int32_t* row_map,
-                    int64_t row_begin, int64_t num_rows, const float* x, int64_t ldx, float* out, int64_t ldo, int64_t f,
-                    int reduce, const float* x_self, int64_t ld_self, float self_scale, const float* bias,
-                    int32_t* counter, gg_stream_t stream);
-int gg_finish_rows_f32(const float* tmp, int64_t ld_tmp, const int32_t* row_map, int64_t num_rows, int64_t f,
-                       const float* x_self, int64_t ld_self, float self_scale, const float* bias, float* out,
-                       int64_t ldo, gg_stream_t stream);
+/* Degree-sorted sliced-ELL aggregation for narrow rows (csrc/spmm_sell.cu; f % 4 == 0, f <= 128) — same semantics and
+ * epilogue as gg_spmm_mpg_f32 (incl. peer output), no row-end work in the kernel.  The layout is rebuilt once per CSR:
+ *   rows longer than `seg` slots (multiple of 4, <= 4096) are cut into virtual rows of <= seg slots; virtual rows are
+ *   sorted by descending length (stable) and grouped 8 to a chunk, padded to the chunk's longest row rounded up to 4;
+ *   neighbour ids are stored as int4 units, (4-slot group k4)-major inside a chunk: idx[(chunk_ptr[c] + k4*8 + q)*4 + kk]
+ *   = slot 4*k4+kk of the chunk's row q, -1 for padding; slot_of[] holds the CSR slot of every entry (-1 for padding);
+ *   vdst[8*c + q] = output row (>= 0), -(partial row) - 1 for a piece of a split row, INT32_MIN for capacity padding;
+ *   hub_rows[h] / hub_pptr[h .. h+1] = the split rows and their ranges of partial rows (summed in order by a fix-up).
+ * Capacities (host-side bounds, no sync): vdst gg_sell_vrow_capacity() entries, chunk_ptr that / 8 + 1, idx and slot_of
+ * 4 * gg_sell_unit_capacity(), hub_rows gg_sell_split_capacity(), hub_pptr one more.  info[8] (device) receives
+ * {virtual rows, chunks, int4 units in use, split rows, partial rows}.  gg_sell_permute_f32 re-lays a per-slot array
+ * (weights) in unit order: dst[d] = slot_of[d] >= 0 ? src[slot_of[d]] : 0.  Summation order per row: slot order (one
+ * group of lanes per virtual row; split rows: pieces in order) — fixed, not the order of the merge-path kernels. */
+int64_t gg_sell_vrow_capacity(int64_t num_rows, int64_t num_slots, int seg);
+int64_t gg_sell_unit_capacity(int64_t num_rows, int64_t num_slots, int seg);
+int64_t gg_sell_split_capacity(int64_t num_slots, int seg);
+size_t gg_sell_build_workspace_bytes(int64_t num_rows, int64_t num_slots, int seg);
+int gg_sell_build(const int32_t* rowptr, const int32_t* nbr, int64_t num_rows, int64_t num_slots, int seg,
+                  uint32_t* chunk_ptr, int32_t* idx, int32_t* slot_of, int32_t* vdst, int32_t* hub_rows,
+                  int32_t* hub_pptr, int32_t* info, void* workspace, size_t workspace_bytes, gg_stream_t stream);
+int gg_sell_permute_f32(const int32_t* slot_of, int64_t total, const float* src, float* dst, gg_stream_t stream);
+size_t gg_spmm_sell_workspace_bytes(int64_t partial_rows, int64_t f);
+int gg_spmm_sell_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const float* w_sell,
+                     const int32_t* vdst, const int32_t* rowptr, const int32_t* hub_rows, const int32_t* hub_pptr,
+                     int64_t hubs, int64_t partial_rows, const float* x, int64_t ldx, float* out, int64_t ldo,
+                     float* const* out_peers_host, int world, int64_t rows_per_rank, int64_t num_rows, int64_t f,
+                     int reduce, const float* x_self, int64_t ld_self, float self_scale, const float* bias,
+                     const float* r1_s, const float* r1_v, const float* r2_s, const float* r2_v, void* workspace,
+                     size_t workspace_bytes, int flags, gg_stream_t stream);
 
 /* bf16-gather variant (the north star's 1e-2 mode): x is stored in bf16 (`x_bf16`: raw bf16 bits, ldx in
  * elements, rows 16-byte aligned), products and sums are fp32, out / x_self / bias are fp32.  Same plan and the

@@ -327,6 +327,54 @@ def run_aux(args, spec, dev):
             'roofline': None, 'cpu_baseline': None}
 
 
+def gpu_comparators(name, n, ei, x, gy, fin, fout, lay, policy, ef, dev):
+    """GPU library formulations of the same layer step on the same box and shape (the bar to beat):
+    torch index_select + index_add_ (the reference's own op sequence on the GPU), torch.sparse CSR @ dense (cuSPARSE),
+    and torch.matmul (cuBLAS) for the dense transforms.  Library kernels only; nothing of this runs on the product path."""
+    from graphgym_b200 import ops
+    if name != 'gcnconv':
+        return None
+    out = {}
+    try:
+        torch.manual_seed(0)
+        w = torch.randn(fin, fout, device=dev) * 0.1
+        csr, csc = lay.csr, lay.csc
+        w_csr, w_csc = lay.weights('gcn_tgt')
+        src, tgt = csr.nbr.long(), csr.rowid.long()
+
+        def scatter_step():
+            h = x @ w
+            o = torch.zeros_like(h).index_add_(0, tgt, h.index_select(0, src) * w_csr.view(-1, 1))
+            gh = torch.zeros_like(h).index_add_(0, src, gy.index_select(0, tgt) * w_csr.view(-1, 1))
+            return o, gh @ w.t(), x.t() @ gh
+        ms = _event_ms(scatter_step, 3, 1)
+        out['torch_index_select_index_add'] = {'ms_per_step': round(ms, 3), 'value': round(ef / (ms * 1e-3) / 1e9, 2)}
+        del src, tgt
+        a = torch.sparse_csr_tensor(csr.rowptr.long(), csr.nbr.long(), w_csr, (n, n))
+        at = torch.sparse_csr_tensor(csc.rowptr.long(), csc.nbr.long(), w_csc, (n, n))
+
+        def sparse_step():
+            h = x @ w
+            o = a @ h
+            gh = at @ gy
+            return o, gh @ w.t(), x.t() @ gh
+        ms = _event_ms(sparse_step, 3, 1)
+        h = x @ w
+        ms_spmm = _event_ms(lambda: a @ h, 5, 2)
+        out['torch_sparse_csr_cusparse'] = {'ms_per_step': round(ms, 3), 'value': round(ef / (ms * 1e-3) / 1e9, 2),
+                                            'spmm_ms': round(ms_spmm, 3)}
+        ms_ours = _event_ms(lambda: ops.spmm(csr, h, w_csr), 5, 2)
+        out['ours_spmm_ms'] = round(ms_ours, 3)
+        ms_mm = _event_ms(lambda: x @ w, 10, 3)
+        ms_ours_mm = _event_ms(lambda: ops.id_gemm([(x, w, None)], n, fout), 10, 3)
+        out['torch_matmul_cublas_fp32'] = {'gemm_ms': round(ms_mm, 3), 'ours_tc_gemm_ms': round(ms_ours_mm, 3),
+                                           'allow_tf32': bool(torch.backends.cuda.matmul.allow_tf32)}
+        out['unit'] = 'GEdge-feat/s for `value` (same E\' x F x 2 numerator as the headline)'
+    except Exception as exc:  # noqa: BLE001 - a comparator must never take the bench line down
+        out['error'] = f'{type(exc).__name__}: {exc}'
+    return out
+
+
 def run_ours(args, spec, rank, world, dev):
     import torch.distributed as dist
 
@@ -407,7 +455,7 @@ def run_ours(args, spec, rank, world, dev):
         # (ref: gnn.py:165-168), so the backward includes dX = dH W^T as well as dW, dbias
         x_dev = x_dev.detach().requires_grad_(True)
         if multi:
-            y = layer(x_dev, playout)
+            y = layer(x_dev, playout, ids) if ids is not None else layer(x_dev, playout)
             y.backward(gy_loc)
             parallel.allreduce_grads(layer)
         else:
@@ -459,6 +507,8 @@ def run_ours(args, spec, rank, world, dev):
         step(x_loc, ei, playout)
     sync_all()
     ops.spmm = timed_spmm
+    if multi:
+        parallel.trace_report()   # GG_PEER_TRACE: only the timed steps are reported
     launches0 = ops.launch_count()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
@@ -468,6 +518,7 @@ def run_ours(args, spec, rank, world, dev):
     end.record()
     sync_all()
     ops.spmm = orig_spmm
+    exchange_trace = parallel.trace_report() if (multi and parallel._TRACE) else None
     launches = int(sum_over_ranks(ops.launch_count() - launches0))
     ms = max_over_ranks(start.elapsed_time(end)) / args.steps
     clocks.__exit__(None, None, None)
@@ -482,7 +533,7 @@ def run_ours(args, spec, rank, world, dev):
     peak, peak_src = load_peaks()
     achieved = per_launch_bytes / (avg_spmm_ms * 1e-3) / 1e9
     roofline = {'bound': 'hbm',
-                'kernel': ('spmm_h_kernel (bf16 gather)' if half else 'spmm_mpg_kernel' if f_launch <= 128 else 'spmm_mp_kernel') + ' + fixup (merge-path CSR aggregation; fwd on CSR and bwd on CSC)'
+                'kernel': ('spmm_h_kernel (bf16 gather)' if half else 'spmm_sell_kernel (degree-sorted sliced-ELL)' if f_launch <= ops.SELL_MAX_F and ops.SPMM_ALGO == 'auto' else 'spmm_mpg_kernel (merge-path)' if f_launch <= 128 else 'spmm_mp_kernel (merge-path)') + ' + fixup (CSR aggregation; fwd on CSR and bwd on CSC)'
                           + ((' — rank 0 of %d, ' % world) + ('all rows x F/%d columns (sub-warp-group kernel, rows stored '
                              'to their owners over NVLink)' % world if playout.sliced else 'rank-local rows') if multi else ''),
                 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
@@ -511,7 +562,17 @@ def run_ours(args, spec, rank, world, dev):
 
     # ---- end to end: host buffers in, result out, every step ------------------------------------
     x_host = x_loc.cpu().pin_memory()
-    ei_host = ei.cpu().pin_memory()
+    # N > 1: every rank uploads only ITS 1/N of the edge list (columns [rank*epr, (rank+1)*epr)); the pieces are
+    # all-gathered over NVLink on the device (the layout needs the whole graph in the sliced exchange)
+    e_total = int(ei.size(1))
+    epr = (e_total + world - 1) // world
+    if multi:
+        pad = torch.full((2, epr * world - e_total), -1, dtype=ei.dtype, device=dev)
+        ei_piece = torch.cat([ei, pad], 1)[:, rank * epr:(rank + 1) * epr].contiguous()
+        ei_host = ei_piece.cpu().pin_memory()
+        del pad, ei_piece
+    else:
+        ei_host = ei.cpu().pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
     res_host = torch.empty(fout, dtype=torch.float32).pin_memory()
 
@@ -534,6 +595,9 @@ def run_ours(args, spec, rank, world, dev):
         cur.wait_event(e_ready)
         eid.record_stream(cur)
         if multi:
+            pieces = torch.empty((world, 2, epr), dtype=eid.dtype, device=dev)
+            dist.all_gather_into_tensor(pieces, eid)
+            eid = pieces.permute(1, 0, 2).reshape(2, world * epr)[:, :e_total].contiguous()
             pl = mk_layout(eid)
             warm_weights(pl)
         else:
@@ -567,12 +631,47 @@ def run_ours(args, spec, rank, world, dev):
     e2e = {'value': round(ef / (e2e_ms * 1e-3) / 1e9, 3), 'unit': 'GEdge-feat/s',
            'ms_per_step': round(e2e_ms, 3), 'steps': e2e_steps,
            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(fout * 4 * world),
-           'includes': 'every step: H2D of edge_index then node_feature rows from pinned memory on every rank (copy '
-                       'stream; the copies of step i+1 overlap the compute of step i, as a prefetching loader does), '
+           'includes': 'every step: H2D of this rank\'s 1/N of edge_index, then of its node_feature rows, from pinned memory '
+                       '(copy stream; the copies of step i+1 overlap the compute of step i, as a prefetching loader does), '
+                       + ('NCCL all-gather of the edge list pieces over NVLink, ' if multi else '') +
                        'CSR+CSC layout build, layer fwd+bwd (dX, dW, dbias) via the layer API, D2H of the bias gradient'}
     del x_host, ei_host
 
-    cpu = cpu_baseline(spec, seconds=args.cpu_seconds) if rank == 0 and not args.no_cpu and not multi else None
+    parity = None
+    if multi:
+        # correctness of the driver-run multi-GPU path: this rank's rows of the output and of dX, and the all-reduced
+        # parameter gradients, against the single-GPU layer (same parameters: the partitioned module wraps it) on the
+        # same inputs; max over ranks
+        fwd_m = (lambda t: layer(t, playout, ids)) if ids is not None else (lambda t: layer(t, playout))
+        xg = x_loc.detach().requires_grad_(True)
+        layer.zero_grad(set_to_none=True)
+        y_m = fwd_m(xg)
+        y_m.backward(gy_loc)
+        y_m = y_m.detach()
+        parallel.allreduce_grads(layer)
+        gm = {k: v.grad.detach().clone() for k, v in layer.named_parameters() if v.grad is not None}
+        dx_m = xg.grad.detach().clone()
+        layer.zero_grad(set_to_none=True)
+        x1 = x.detach().requires_grad_(True)
+        y1 = layer.model(x1, ei, ids) if ids is not None else layer.model(x1, ei)
+        y1.backward(gy)
+        rel = lambda a, r: float((a.double() - r.double()).abs().max() / r.double().abs().max().clamp(min=1e-30))
+        errs = {'out': rel(y_m, y1.detach()[part.lo:part.hi]), 'dx': rel(dx_m, x1.grad[part.lo:part.hi])}
+        for k, v in layer.model.named_parameters():
+            if v.grad is not None and ('model.' + k) in gm:
+                errs['d' + k] = rel(gm['model.' + k], v.grad)
+        parity = {k: max_over_ranks(v) for k, v in sorted(errs.items())}
+        parity['tolerance'] = 1e-5
+        parity['ok'] = all(v <= 1e-5 for k, v in parity.items() if k not in ('tolerance', 'ok'))
+        parity['metric'] = 'max|a - b| / max|b| against the single-GPU layer on the same inputs, max over ranks'
+        del y_m, dx_m, x1, y1, gm
+        layer.zero_grad(set_to_none=True)
+    comparators = None
+    if not multi and not args.no_comparators and rank == 0:
+        comparators = gpu_comparators(name, n, ei, x, gy, fin, fout, lay, policy, ef, dev)
+    cpu = None
+    if rank == 0 and not args.no_cpu and not multi:
+        cpu = cpu_baseline(spec, seconds=args.cpu_seconds, warmup=1, graph=(n, ei.cpu(), x.cpu(), gy.cpu()), extras=True)
     out = {
         'metric': 'layer fwd+bwd GEdge-feat/s', 'value': round(value, 3), 'unit': 'GEdge-feat/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms, 4),
@@ -588,12 +687,14 @@ def run_ours(args, spec, rank, world, dev):
                    'layout_cached_across_steps': True},
         'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': int(launches),
         'roofline': roofline, 'cpu_baseline': cpu,
+        'parity_vs_1gpu': parity, 'comparators': comparators,
+        'exchange_trace_ms': exchange_trace,   # GG_PEER_TRACE=1: mean ms between the exchange's phase marks, rank 0, timed steps
+        # the reference re-runs its COO edits + normalisation on every forward (idconv.py:69-87); `value` caches the layout
+        'value_with_layout_build_every_step': round(ef / ((ms + layout_ms) * 1e-3) / 1e9, 3),
         'layout_build_ms': round(layout_ms, 3), 'graph_gen_s': round(gen_s, 2),
         'layout_first_call_s': round(layout_first_s, 3),
     }
     if multi:
-        if parallel._TRACE and rank == 0:
-            print('[bench] exchange phases (ms, count):', json.dumps(parallel.trace_report()), file=sys.stderr)
         if playout.pool is not None:
             playout.pool.close()
         dist.barrier()
@@ -604,74 +705,120 @@ def run_ours(args, spec, rank, world, dev):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle restatement of the reference's op sequence, all host threads
 # ------------------------------------------------------------------------------------------------
-def cpu_layer_step(name, x, ei, params, gy):
-    from oracle import layers as olayers
-    xg = x.requires_grad_(True)
-    for p in params.values():
-        p.grad = None
+CPU_CHUNK = 1 << 22   # edges per chunk of the CPU arm (the [E, F] message tensor of the full graph would be 33 GB)
+
+
+def cpu_params(fin, fout):
+    g = torch.Generator().manual_seed(0)
+    mk = lambda *s: torch.randn(*s, generator=g) * 0.1
+    return {'weight': mk(fin, fout), 'bias': mk(fout), 'w_l': mk(fout, fin), 'w_r': mk(fout, fin),
+            'att': mk(1, 1, 2 * fout)}
+
+
+def cpu_layer_step(name, x, ei, p, gy, chunk=CPU_CHUNK):
+    """One forward+backward of the reference's CPU op sequence (ref: layer.py:135-162 -> pyg.nn.*, idconv.py:89-92):
+    oracle/chunked.py = oracle/layers.py + autograd, evaluated over edge chunks."""
+    from oracle import chunked
     if name == 'gcnconv':
-        y = olayers.gcnconv(xg, ei, params['weight'], params['bias'])
-    elif name == 'sageconv':
-        y = olayers.sageconv(xg, ei, params['w_l'], params['bias'], params['w_r'])
-    elif name == 'gatconv':
-        y = olayers.gatconv(xg, ei, params['weight'], params['att'], params['bias'])
-    else:
-        raise KeyError(name)
-    y.backward(gy)
-    return y
+        return chunked.gcnconv_step(x, ei, p['weight'], p['bias'], gy, chunk)
+    if name == 'sageconv':
+        return chunked.sageconv_step(x, ei, p['w_l'], p['bias'], p['w_r'], gy, chunk)
+    if name == 'gatconv':
+        return chunked.gatconv_step(x, ei, p['weight'], p['att'], p['bias'], gy, chunk=chunk)
+    raise KeyError(name)
 
 
-def cpu_baseline(spec, seconds=15.0, steps=None, warmup=1):
-    """Oracle (kind 'port': PyG is not installable here) on a bounded sample of the same graph
-    family: same generator, nodes and edges scaled down together so one step is ~1-2 s of CPU."""
+def _time_cpu_steps(fn, seconds, steps, warmup):
+    """Median wall time of `steps` calls (or as many as fit `seconds`, at least one) after `warmup` untimed calls."""
+    for _ in range(warmup):
+        fn()
+    times, t_end = [], time.time() + seconds
+    while True:
+        t0 = time.time()
+        fn()
+        times.append(time.time() - t0)
+        if (steps is not None and len(times) >= steps) or (steps is None and (time.time() >= t_end or len(times) >= 50)):
+            break
+    return float(np.median(times)), len(times)
+
+
+def cpu_baseline(spec, seconds=15.0, steps=None, warmup=1, graph=None, extras=False, scale=1.0):
+    """Oracle (kind 'port': PyG is not installable here) on the FULL graph of the workload (`scale` = 1; the per-edge
+    tensors are chunked), all host threads.  `graph` = (n, edge_index, x, gy) CPU tensors to reuse (the bits the GPU arm
+    ran on); otherwise the same generator runs on the CPU.  `extras`: also the reference's default thread count
+    (cfg.num_threads = 6, ref: config.py:57) and a torch.sparse CSR (MKL) formulation of the same layer."""
     name, fin, fout = spec['layer'], spec['fin'], spec['fout']
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    target_edges = 4_000_000
-    full_edges = 2 * (spec.get('e_und') or spec['m'] * spec['n'])
-    scale = min(1.0, target_edges / full_edges)
     cpu = torch.device('cpu')
-    n, ei = gen_graph(spec, cpu, seed=1, scale=scale)
-    x = gen_features(n, fin, cpu)
-    gy = gen_features(n, fout, cpu, seed=7)
-    g = torch.Generator().manual_seed(0)
-    mk = lambda *s: (torch.randn(*s, generator=g) * 0.1).requires_grad_(True)
-    params = {'weight': mk(fin, fout), 'bias': mk(fout), 'w_l': mk(fout, fin), 'w_r': mk(fout, fin),
-              'att': mk(1, 1, 2 * fout)}
-    slots = int(ei.size(1)) + (n if name in ('gcnconv', 'gatconv') else 0)
+    if graph is None:
+        n, ei = gen_graph(spec, cpu, seed=0, scale=scale)
+        x = gen_features(n, fin, cpu)
+        gy = gen_features(n, fout, cpu, seed=7)
+    else:
+        n, ei, x, gy = graph
+    params = cpu_params(fin, fout)
+    slots = int(ei.size(1)) + (n if name in ('gcnconv', 'gatconv') else 0)   # upper bound; exact E' needs the loop count
+    if name in ('gcnconv', 'gatconv'):
+        slots -= int((ei[0] == ei[1]).sum())
     ef, _ = edge_feat_per_step(name, n, slots, fin, fout)
-    for _ in range(warmup):
-        cpu_layer_step(name, x, ei, params, gy)
-    times = []
-    t_end = time.time() + seconds
-    while (steps is None and time.time() < t_end) or (steps is not None and len(times) < steps):
-        t0 = time.time()
-        cpu_layer_step(name, x, ei, params, gy)
-        times.append(time.time() - t0)
-        if steps is None and len(times) >= 50:
-            break
-    t = float(np.median(times))
-    return {'value': round(ef / t / 1e9, 4), 'unit': 'GEdge-feat/s', 'cores': cores, 'kind': 'port',
-            'ms_per_step': round(t * 1e3, 2), 'steps': len(times), 'torch_threads': torch.get_num_threads(),
-            'sample': f'same generator scaled x{scale:.4f}: {n} nodes, {int(ei.size(1))} directed edges, '
-                      f'{name} {fin}->{fout}, fwd+bwd, fp32, oracle restatement of the PyG op sequence '
-                      '(index_select gather, per-edge scale, index_add_ scatter, matmul)'}
+    with torch.no_grad():
+        t, done = _time_cpu_steps(lambda: cpu_layer_step(name, x, ei, params, gy), seconds, steps, warmup)
+        out = {'value': round(ef / t / 1e9, 4), 'unit': 'GEdge-feat/s', 'cores': cores, 'kind': 'port',
+               'ms_per_step': round(t * 1e3, 2), 'steps': done, 'torch_threads': torch.get_num_threads(),
+               'sample': f'the whole workload graph ({n} nodes, {int(ei.size(1))} directed edges, {name} {fin}->{fout}, '
+                         f'fwd+bwd, fp32), {done} step(s) after {warmup} warm-up: oracle restatement of the PyG op sequence '
+                         f'(index_select gather, per-edge scale, index_add_ scatter, matmul) over edge chunks of {CPU_CHUNK}'
+                         + ('' if scale == 1.0 else f' — generator scaled x{scale:.4f}')}
+        if extras:
+            torch.set_num_threads(min(6, cores))
+            t6, d6 = _time_cpu_steps(lambda: cpu_layer_step(name, x, ei, params, gy), 0.0, 1, 0)
+            out['six_threads'] = {'value': round(ef / t6 / 1e9, 4), 'ms_per_step': round(t6 * 1e3, 2), 'steps': d6,
+                                  'torch_threads': torch.get_num_threads(),
+                                  'note': 'the reference default cfg.num_threads = 6 (config.py:57, main_zd.py:284)'}
+            torch.set_num_threads(cores)
+            if name == 'gcnconv':
+                out['torch_sparse_csr'] = cpu_sparse_gcn(n, ei, x, gy, params, ef)
+    return out
+
+
+def cpu_sparse_gcn(n, ei, x, gy, p, ef):
+    """Secondary CPU line: the same GCN layer as A_hat @ (X W) with torch.sparse CSR (MKL), fwd + bwd."""
+    from oracle import layers as olayers
+    t0 = time.time()
+    ei2, norm = olayers.gcn_norm_tgt(ei, n, x.dtype)
+    a = torch.sparse_coo_tensor(torch.stack([ei2[1], ei2[0]]), norm, (n, n)).coalesce()
+    a_csr, at_csr = a.to_sparse_csr(), a.t().coalesce().to_sparse_csr()
+    build = time.time() - t0
+
+    def step():
+        h = x @ p['weight']
+        out = a_csr @ h + p['bias']
+        gh = at_csr @ gy
+        return out, gh @ p['weight'].t(), x.t() @ gh, gy.sum(0)
+    step()
+    t, done = _time_cpu_steps(step, 0.0, 2, 0)
+    return {'value': round(ef / t / 1e9, 4), 'ms_per_step': round(t * 1e3, 2), 'steps': done,
+            'csr_build_s': round(build, 2), 'note': 'torch.sparse CSR @ dense (MKL), adjacency built once outside the step'}
 
 
 def run_reference(args, spec, rank, world):
     if rank != 0:
         return None
-    cpu = cpu_baseline(spec, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    t0 = time.time()
+    # the whole workload graph; K timed steps after one warm-up (a step is ~10 s of CPU at 62 M edges)
+    cpu = cpu_baseline(spec, steps=args.steps, warmup=1 if args.warmup > 0 else 0, scale=args.cpu_scale)
     return {'impl': 'reference', 'metric': 'layer fwd+bwd GEdge-feat/s', 'value': cpu['value'],
             'unit': 'GEdge-feat/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': cpu['ms_per_step'], 'higher_is_better': True, 'scaling': 'strong',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (bounded sample, see cpu_baseline.sample)',
-            'config': {'workload': spec['desc'], 'layer': spec['layer']},
-            'cpu_baseline': cpu,
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (seeded generators in bench.py, run on the CPU)',
+            'config': {'workload': spec['desc'], 'layer': spec['layer'], 'same_graph_family_and_size_as_the_gpu_arm': args.cpu_scale == 1.0,
+                       'warmup_steps_run': 1 if args.warmup > 0 else 0},
+            'cpu_baseline': cpu, 'wall_s': round(time.time() - t0, 1),
             'e2e': {'value': cpu['value'], 'unit': 'GEdge-feat/s', 'h2d_bytes_per_step': 0,
                     'd2h_bytes_per_step': 0},
             'note': 'torch_geometric / torch_scatter are not installable offline: this is the oracle '
-                    'restatement of the reference CPU path (oracle/layers.py), all host threads'}
+                    'restatement of the reference CPU path (oracle/chunked.py == oracle/layers.py + autograd), all host threads'}
 
 
 def main():
@@ -693,6 +840,9 @@ def main():
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--cpu-scale', type=float, default=1.0,
+                    help='--impl reference: shrink the generator (nodes and edges together); 1.0 = the whole workload graph')
+    ap.add_argument('--no-comparators', action='store_true', help='skip the GPU library comparators (N=1)')
     ap.add_argument('--gather-dtype', default='f32', choices=['f32', 'bf16'],
                     help="storage of the aggregation's gathered operand: f32 (reference arithmetic, the default and "
                          "the headline) or bf16 (the north star's 1e-2 mode; single GPU)")

@@ -128,6 +128,12 @@ SIGNATURES = {
                                      c_ptr, c_ptr, c_ptr]),
     "gg_gat_dz_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_ptr]),
     "gg_gat_csc_gather_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    "gg_postops_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "gg_bn_stats_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_ptr, c_size, c_ptr]),
+    "gg_postops_fwd_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32, c_int, c_ptr,
+                                   c_i64, c_ptr, c_ptr]),
+    "gg_postops_bwd_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_int,
+                                   c_int, c_f32, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "gg_gather_rows_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_scatter_add_rows_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_relu_grad_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr]),

@@ -31,7 +31,8 @@ def _defaults():
     c.device = 'auto'
     # not a reference key: storage type of the operand the aggregation gathers.  'f32' = the reference's arithmetic
     # (1e-5 parity); 'bf16' = the north star's 1e-2 mode (rows gathered in bf16, fp32 products and sums)
-    c.b200 = _Node(gather_dtype='f32')
+    # fused_postops: GeneralLayer's BN / activation / L2 as one fused pass (False = the nn modules one by one)
+    c.b200 = _Node(gather_dtype='f32', fused_postops=True)
     return c
 
 

@@ -203,3 +203,47 @@ class _GatAggregate(torch.autograd.Function):
 
 def gat_aggregate(h, att, bias, layout, heads=1, slope=0.2):
     return _GatAggregate.apply(h, att, bias, layout, int(heads), float(slope))
+
+
+class _PostOps(torch.autograd.Function):
+    """out = l2norm( act( BatchNorm1d(y) ) ) in two kernels forward (statistics, apply) and two backward
+    (column sums, apply) — ref: graphgym/models/layer.py:26-46, gnn.py:79-80."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, bn, training, act, slope, l2norm):
+        y = y.contiguous()
+        mean = invstd = None
+        if bn is not None:
+            if training or bn.running_mean is None:
+                mom = 0.0
+                if training and bn.running_mean is not None:
+                    bn.num_batches_tracked += 1
+                    mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                track = training and bn.running_mean is not None
+                mean, invstd = ops.bn_stats(y, bn.eps, bn.running_mean if track else None,
+                                            bn.running_var if track else None, mom)
+                ctx.train = True
+            else:
+                mean = bn.running_mean
+                invstd = torch.rsqrt(bn.running_var + bn.eps)   # [F]-sized, eval mode only
+                ctx.train = False
+        out, rownorm = ops.postops_fwd(y, mean, invstd, gamma, beta, act, slope, l2norm)
+        ctx.act, ctx.slope, ctx.l2norm, ctx.has_bn = act, slope, l2norm, bn is not None
+        ctx.save_for_backward(y, out, mean, invstd, gamma, rownorm)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        y, out, mean, invstd, gamma, rownorm = ctx.saved_tensors
+        dy, dgamma, dbeta = ops.postops_bwd(go.contiguous(), out, y, mean, invstd, gamma, getattr(ctx, 'train', False),
+                                            ctx.act, ctx.slope, ctx.l2norm, rownorm)
+        if gamma is None:
+            dgamma = dbeta = None
+        return dy, dgamma, dbeta, None, None, None, None, None
+
+
+def post_ops(y, bn=None, training=True, act=ops.ACT_NONE, slope=0.0, l2norm=False):
+    """``bn``: an ``nn.BatchNorm1d`` (its parameters / buffers are used and updated as the module would) or None."""
+    gamma = bn.weight if bn is not None else None
+    beta = bn.bias if bn is not None else None
+    return _PostOps.apply(y, gamma, beta, bn, bool(training), int(act), float(slope), bool(l2norm))

@@ -134,11 +134,17 @@ _ACT = {'relu': nn.ReLU, 'selu': nn.SELU, 'prelu': nn.PReLU, 'elu': nn.ELU,
         'lrelu_05': lambda: nn.LeakyReLU(0.5)}
 
 
+_FUSED_ACT = {'relu': (ops.ACT_RELU, 0.0), 'lrelu_01': (ops.ACT_LRELU, 0.1), 'lrelu_025': (ops.ACT_LRELU, 0.25),
+              'lrelu_05': (ops.ACT_LRELU, 0.5)}
+
+
 class GeneralLayer(nn.Module):
     """Caller of the hot path (ref: layer.py:16-47): layer -> BN -> dropout -> act -> optional L2.
 
-    Kept as a thin harness so the layers can be exercised exactly as GraphGym drives them; the
-    post-ops are SURVEY §8(f) item 1 ("next": fuse into the aggregation epilogue)."""
+    The modules of ``post_layer`` are kept as the parameter / buffer holders (same ``state_dict`` keys as the reference);
+    on CUDA tensors the post-ops run as ONE fused pass (``functional.post_ops``: BN statistics, normalise + affine +
+    activation + row L2) whenever the combination is on the fused path — BatchNorm1d and/or ReLU / leaky ReLU and/or L2,
+    no active dropout; anything else (PReLU / ELU / SELU, dropout > 0 while training) runs the modules one by one."""
 
     def __init__(self, name, dim_in, dim_out, has_act=True, has_bn=True, has_l2norm=False, **kwargs):
         super().__init__()
@@ -153,17 +159,28 @@ class GeneralLayer(nn.Module):
         if has_act:
             post.append(_ACT[cfg.gnn.act]())
         self.post_layer = nn.Sequential(*post)
+        self._bn = post[0] if has_bn else None
+        self._drop_p = cfg.gnn.dropout
+        self._act = _FUSED_ACT.get(cfg.gnn.act) if has_act else (ops.ACT_NONE, 0.0)
+
+    def _post(self, h):
+        fused = (h.is_cuda and h.dim() == 2 and h.dtype == torch.float32 and self._act is not None
+                 and not (self._drop_p > 0 and self.training) and cfg.b200.fused_postops)
+        if fused:
+            if self._bn is None and self._act[0] == ops.ACT_NONE and not self.has_l2norm:
+                return h
+            return F_.post_ops(h, self._bn, self.training, self._act[0], self._act[1], self.has_l2norm)
+        h = self.post_layer(h)
+        if self.has_l2norm:
+            h = F.normalize(h, p=2, dim=1)
+        return h
 
     def forward(self, batch):
         batch = self.layer(batch)
         if isinstance(batch, torch.Tensor):
-            batch = self.post_layer(batch)
-            if self.has_l2norm:
-                batch = F.normalize(batch, p=2, dim=1)
+            batch = self._post(batch)
         else:
-            batch.node_feature = self.post_layer(batch.node_feature)
-            if self.has_l2norm:
-                batch.node_feature = F.normalize(batch.node_feature, p=2, dim=1)
+            batch.node_feature = self._post(batch.node_feature)
         return batch
 
 

@@ -14,7 +14,7 @@ from ._lib import GemmSegment, check, lib
 LOOPS_KEEP, LOOPS_ADD_REMAINING, LOOPS_REMOVE_ADD, LOOPS_REMOVE, LOOPS_ADD = range(5)
 BY_TARGET, BY_SOURCE = 0, 1
 SUM, MEAN = 0, 1
-ACT_NONE, ACT_RELU = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
 
 
 import os as _os
@@ -523,6 +523,62 @@ def relu_grad(g, y):
     check(lib().gg_relu_grad_f32(_ptr(g), ldg, _ptr(y), ldy, n, f, _ptr(out), max(f, 1), _stream()),
           "gg_relu_grad_f32")
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# fused layer post-ops (BatchNorm1d -> activation -> row L2 normalise)
+# --------------------------------------------------------------------------------------------
+def bn_stats(y, eps, running_mean=None, running_var=None, momentum=0.0):
+    """-> (mean [f], invstd [f]) of the columns of ``y`` (biased variance); updates the running statistics in place."""
+    _need_cuda(y, running_mean, running_var)
+    y, ld = _rows(y, "y")
+    n, f = y.shape
+    if n < 1:
+        raise ValueError("bn_stats: empty batch")
+    mean = torch.empty(f, dtype=torch.float32, device=y.device)
+    invstd = torch.empty(f, dtype=torch.float32, device=y.device)
+    L = lib()
+    ws_bytes = int(L.gg_postops_workspace_bytes(n, f))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=y.device)
+    check(L.gg_bn_stats_f32(_ptr(y), ld, n, f, float(eps), _ptr(mean), _ptr(invstd), _ptr(running_mean), _ptr(running_var),
+                            float(momentum), _ptr(ws), ws_bytes, _stream()), "gg_bn_stats_f32")
+    return mean, invstd
+
+
+def postops_fwd(y, mean, invstd, gamma, beta, act, slope, l2norm):
+    """-> (out, rownorm or None)"""
+    _need_cuda(y, mean, invstd, gamma, beta)
+    y, ld = _rows(y, "y")
+    n, f = y.shape
+    out = torch.empty((n, f), dtype=torch.float32, device=y.device)
+    rownorm = torch.empty(max(n, 1), dtype=torch.float32, device=y.device)[:n] if l2norm else None
+    check(lib().gg_postops_fwd_f32(_ptr(y), ld, n, f, _ptr(mean), _ptr(invstd), _ptr(gamma), _ptr(beta), int(act),
+                                   float(slope), int(bool(l2norm)), _ptr(out), max(f, 1), _ptr(rownorm), _stream()),
+          "gg_postops_fwd_f32")
+    return out, rownorm
+
+
+def postops_bwd(go, out, y, mean, invstd, gamma, train, act, slope, l2norm, rownorm):
+    """-> (dy, dgamma or None, dbeta or None)"""
+    _need_cuda(go, out, y)
+    go, ld_go = _rows(go, "go")
+    out, ld_o = _rows(out, "out")
+    y, ld_y = _rows(y, "y")
+    n, f = go.shape
+    dev = go.device
+    dy = torch.empty((n, f), dtype=torch.float32, device=dev)
+    dgamma = dbeta = ws = None
+    ws_bytes = 0
+    L = lib()
+    if mean is not None:
+        dgamma = torch.empty(f, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(f, dtype=torch.float32, device=dev)
+        ws_bytes = int(L.gg_postops_workspace_bytes(n, f))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(L.gg_postops_bwd_f32(_ptr(go), ld_go, _ptr(out), ld_o, _ptr(y), ld_y, n, f, _ptr(mean), _ptr(invstd), _ptr(gamma),
+                               int(bool(train)), int(act), float(slope), int(bool(l2norm)), _ptr(rownorm), _ptr(dy),
+                               max(f, 1), _ptr(dgamma), _ptr(dbeta), _ptr(ws), ws_bytes, _stream()), "gg_postops_bwd_f32")
+    return dy, dgamma, dbeta
 
 
 # --------------------------------------------------------------------------------------------

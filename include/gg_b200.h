@@ -257,7 +257,7 @@ typedef struct gg_gemm_segment {
     const float* scale; /* [n] row multipliers, nullable */
     int64_t k;
 } gg_gemm_segment;
-enum gg_act { GG_ACT_NONE = 0, GG_ACT_RELU = 1 };
+enum gg_act { GG_ACT_NONE = 0, GG_ACT_RELU = 1, GG_ACT_LRELU = 2 /* post-ops only */ };
 int gg_id_gemm_f32(const gg_gemm_segment* segments_host, int num_segments, int b_trans, int64_t n,
                    int64_t f, const float* bias, int act, const float* relu_mask, int64_t ld_mask,
                    float* out, int64_t ldo, gg_stream_t stream);
@@ -407,6 +407,30 @@ int gg_gat_dz_f32(const int32_t* rowptr, const int32_t* nbr, const float* a_tgt,
                   gg_stream_t stream);
 int gg_gat_csc_gather_f32(const int32_t* rowptr_t, const int32_t* slot_map, const float* alpha, const float* dz,
                           int64_t n, float* alpha_t, float* da_src, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused layer post-ops (csrc/postops.cu) — what GeneralLayer / GNNStackStage apply after the
+ * message-passing layer (ref: graphgym/models/layer.py:26-46, graphgym/models/gnn.py:76-81):
+ *   a = BatchNorm1d(y)   (mean / invstd null: no BN; gamma / beta null: no affine)
+ *   r = act(a)           GG_ACT_NONE | GG_ACT_RELU | GG_ACT_LRELU (slope > 0)
+ *   out = l2norm ? r / max(||r||_2, 1e-12) : r          (torch.nn.functional.normalize over dim 1)
+ * gg_bn_stats_f32: per-column mean and 1/sqrt(biased var + eps) of y in one pass (deterministic), and, when the pointers
+ *   are given, BatchNorm1d's running-statistics update running = (1 - momentum) running + momentum * stat (unbiased var).
+ * gg_postops_fwd_f32: one pass; rownorm[n] receives max(||r||, 1e-12) when l2norm (kept for the backward).
+ * gg_postops_bwd_f32: dy from go, the SAVED out (activation gates = sign of out), y, mean / invstd, rownorm; train != 0:
+ *   batch-statistics BN (dy includes the mean / variance terms); dgamma / dbeta are written whenever mean is given.
+ * Workspace: gg_postops_workspace_bytes(n, f) for the statistics and for the backward. */
+size_t gg_postops_workspace_bytes(int64_t n, int64_t f);
+int gg_bn_stats_f32(const float* y, int64_t ld, int64_t n, int64_t f, float eps, float* mean, float* invstd,
+                    float* running_mean, float* running_var, float momentum, void* workspace, size_t workspace_bytes,
+                    gg_stream_t stream);
+int gg_postops_fwd_f32(const float* y, int64_t ld_y, int64_t n, int64_t f, const float* mean, const float* invstd,
+                       const float* gamma, const float* beta, int act, float slope, int l2norm, float* out,
+                       int64_t ld_out, float* rownorm, gg_stream_t stream);
+int gg_postops_bwd_f32(const float* go, int64_t ld_go, const float* out, int64_t ld_out, const float* y, int64_t ld_y,
+                       int64_t n, int64_t f, const float* mean, const float* invstd, const float* gamma, int train,
+                       int act, float slope, int l2norm, const float* rownorm, float* dy, int64_t ld_dy, float* dgamma,
+                       float* dbeta, void* workspace, size_t workspace_bytes, gg_stream_t stream);
 
 /* Row gather / scatter-add / ReLU gradient used by the GIN-ID branch (ref: idconv.py:372-375):
  *   gather:      out[r,:]      = x[id[r],:]

@@ -60,67 +60,84 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---- statistics ----------------------------------------------------------------------------------------------------
-// CTA b owns rows [b * chunk, (b+1) * chunk): per column the shifted sums s1 = sum(x - K), s2 = sum((x - K)^2) with
-// K = the chunk's first row (keeps s2 - s1^2/n well conditioned when |mean| >> std).  part[b] = {K[f], s1[f], s2[f]}.
+// Shifted sums per column, s1 = sum(x - K), s2 = sum((x - K)^2) with K = row 0 of y (one shift for the whole matrix, so
+// the CTAs' partials simply add; keeps s2 - s1^2/n well conditioned when |mean| >> std).  A warp walks rows — one
+// coalesced row segment per load, 4 rows in flight — and keeps its columns' sums in registers; the CTA's 8 warps are
+// combined through shared memory in a fixed order.  part[b] = {s1[f], s2[f]}.
+template <int V>
 __global__ void __launch_bounds__(kPoThreads) bn_stats_partial_kernel(const float* __restrict__ y, int64_t ld, int64_t n,
                                                                       int f, int64_t chunk, float* __restrict__ part) {
-    __shared__ float sh1[kPoThreads], sh2[kPoThreads];
+    extern __shared__ float sh[];   // [kPoWarps][2][f]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * chunk;
     const int64_t r1 = r0 + chunk < n ? r0 + chunk : n;
-    float* pb = part + (int64_t)blockIdx.x * 3 * f;
-    for (int c0 = 0; c0 < f; c0 += kPoThreads) {
-        const int cols = f - c0 < kPoThreads ? f - c0 : kPoThreads;   // columns of this tile
-        const int rpp = kPoThreads / cols;                           // rows per pass
-        const int t = threadIdx.x;
-        const int c = t % cols, ry = t / cols;
-        float s1 = 0.f, s2 = 0.f, K = 0.f;
-        if (ry < rpp && r0 < n) {
-            K = y[r0 * ld + c0 + c];
-            for (int64_t r = r0 + ry; r < r1; r += rpp) {
-                const float d = y[r * ld + c0 + c] - K;
-                s1 += d;
-                s2 = fmaf(d, d, s2);
+    float* mine = sh + (int64_t)wid * 2 * f;
+    for (int c0 = lane * V; c0 < f; c0 += 32 * V) {   // column groups this lane owns
+        float K[V], s1[V], s2[V];
+#pragma unroll
+        for (int q = 0; q < V; ++q) { K[q] = __ldg(y + c0 + q); s1[q] = 0.f; s2[q] = 0.f; }
+        int64_t r = r0 + wid;
+        for (; r + 3 * kPoWarps < r1; r += 4 * kPoWarps) {
+            float v[4][V];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float* p = y + (r + (int64_t)u * kPoWarps) * ld + c0;
+                if (V == 4) *reinterpret_cast<float4*>(v[u]) = *reinterpret_cast<const float4*>(p);
+                else v[u][0] = *p;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < V; ++q) {
+                    const float d = v[u][q] - K[q];
+                    s1[q] += d;
+                    s2[q] = fmaf(d, d, s2[q]);
+                }
+        }
+        for (; r < r1; r += kPoWarps) {
+            float v[V];
+            const float* p = y + r * ld + c0;
+            if (V == 4) *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(p);
+            else v[0] = *p;
+#pragma unroll
+            for (int q = 0; q < V; ++q) {
+                const float d = v[q] - K[q];
+                s1[q] += d;
+                s2[q] = fmaf(d, d, s2[q]);
             }
         }
-        sh1[t] = s1;
-        sh2[t] = s2;
-        __syncthreads();
-        if (t < cols) {
-            for (int q = 1; q < rpp; ++q) {   // fixed order
-                s1 += sh1[q * cols + t];
-                s2 += sh2[q * cols + t];
-            }
-            pb[c0 + t] = K;
-            pb[f + c0 + t] = s1;
-            pb[2 * f + c0 + t] = s2;
-        }
-        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < V; ++q) { mine[c0 + q] = s1[q]; mine[f + c0 + q] = s2[q]; }
+    }
+    __syncthreads();
+    float* pb = part + (int64_t)blockIdx.x * 2 * f;
+    for (int c = threadIdx.x; c < 2 * f; c += kPoThreads) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < kPoWarps; ++w) acc += sh[(int64_t)w * 2 * f + c];   // fixed order
+        pb[c] = acc;
     }
 }
 
-// Chan's pairwise merge over the CTAs in order, fp64; also the running-statistics update of BatchNorm1d
+// the CTAs' partials add up in fp64 in CTA order; also the running-statistics update of BatchNorm1d
 // (running = (1 - m) running + m stat, the variance unbiased).
-__global__ void __launch_bounds__(256) bn_stats_final_kernel(const float* __restrict__ part, int blocks, int64_t chunk,
-                                                             int64_t n, int f, float eps, float* __restrict__ mean,
-                                                             float* __restrict__ invstd, float* __restrict__ running_mean,
+__global__ void __launch_bounds__(256) bn_stats_final_kernel(const float* __restrict__ part, const float* __restrict__ y,
+                                                             int blocks, int64_t n, int f, float eps,
+                                                             float* __restrict__ mean, float* __restrict__ invstd,
+                                                             float* __restrict__ running_mean,
                                                              float* __restrict__ running_var, float momentum) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= f) return;
-    double cnt = 0.0, mu = 0.0, m2 = 0.0;
+    double s1 = 0.0, s2 = 0.0;
     for (int b = 0; b < blocks; ++b) {
-        const int64_t r0 = (int64_t)b * chunk;
-        if (r0 >= n) break;
-        const double nb = (double)((r0 + chunk < n ? r0 + chunk : n) - r0);
-        const float* pb = part + (int64_t)b * 3 * f;
-        const double s1 = pb[f + c], s2 = pb[2 * f + c];
-        const double mb = (double)pb[c] + s1 / nb;
-        const double m2b = s2 - s1 * s1 / nb;
-        const double tot = cnt + nb, delta = mb - mu;
-        mu += delta * nb / tot;
-        m2 += m2b + delta * delta * cnt * nb / tot;
-        cnt = tot;
+        s1 += (double)part[(int64_t)b * 2 * f + c];
+        s2 += (double)part[(int64_t)b * 2 * f + f + c];
     }
-    const double var = cnt > 0 ? (m2 > 0 ? m2 / cnt : 0.0) : 0.0;
+    const double cnt = (double)n;
+    const double mu = (double)y[c] + s1 / cnt;
+    double m2 = s2 - s1 * s1 / cnt;
+    if (m2 < 0.0) m2 = 0.0;
+    const double var = m2 / cnt;
     mean[c] = (float)mu;
     invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
     if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
@@ -131,45 +148,74 @@ __global__ void __launch_bounds__(256) bn_stats_final_kernel(const float* __rest
 }
 
 // ---- forward -----------------------------------------------------------------------------------------------------
-// one warp per row; lanes stride the columns
-__device__ __forceinline__ float po_pre(const PostArgs& a, float v, int c) {
-    if (a.mean) {
-        v = (v - __ldg(a.mean + c)) * __ldg(a.invstd + c);
-        if (a.gamma) v = fmaf(v, __ldg(a.gamma + c), __ldg(a.beta + c));
+// one warp per row; lanes stride the columns.  The per-column constants (mean, invstd * gamma, beta) are staged in shared
+// memory once per CTA — reading them with four __ldg per element made the first version instruction-bound (603 M
+// instructions, 1.75 TB/s at F = 128, profiles/r02_sell_postops_ncu_raw.csv).
+struct PoCols {
+    const float* mu;    // shared-memory arrays [f]
+    const float* isg;
+    const float* beta;
+};
+__device__ __forceinline__ PoCols po_stage_cols(const PostArgs& a, float* sh) {
+    float* mu = sh;
+    float* isg = sh + a.f;
+    float* be = sh + 2 * a.f;
+    for (int c = threadIdx.x; c < a.f; c += blockDim.x) {
+        mu[c] = a.mean ? a.mean[c] : 0.f;
+        isg[c] = a.mean ? a.invstd[c] * (a.gamma ? a.gamma[c] : 1.f) : 1.f;
+        be[c] = (a.mean && a.gamma) ? a.beta[c] : 0.f;
     }
-    return v;
+    __syncthreads();
+    return PoCols{mu, isg, be};
 }
 
 template <int V>
 __global__ void __launch_bounds__(kPoThreads) postops_fwd_kernel(const __grid_constant__ PostArgs a) {
+    extern __shared__ float sh[];
+    const PoCols pc = po_stage_cols(a, sh);
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * kPoWarps;
+    constexpr int kKeep = 4;   // column groups of a row a lane keeps in registers (f <= 512 with V = 4)
     for (int64_t r = (int64_t)blockIdx.x * kPoWarps + (threadIdx.x >> 5); r < a.n; r += warps) {
         const float* yr = a.y + r * a.ld_y;
         float* orow = a.dst + r * a.ld_dst;
-        float scale = 1.f;
-        if (a.l2) {
-            float ss = 0.f;
-            for (int c = lane * V; c < a.f; c += 32 * V) {
-                float v[V];
-                if (V == 4) *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(yr + c);
-                else v[0] = yr[c];
-#pragma unroll
-                for (int q = 0; q < V; ++q) {
-                    const float t = po_act(po_pre(a, v[q], c + q), a.act, a.slope);
-                    ss = fmaf(t, t, ss);
-                }
-            }
-            const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);   // F.normalize: x / max(||x||, eps)
-            if (lane == 0) a.rownorm[r] = nrm;
-            scale = 1.f / nrm;
-        }
-        for (int c = lane * V; c < a.f; c += 32 * V) {
+        float keep[kKeep][V];
+        float ss = 0.f;
+        int k = 0;
+        for (int c = lane * V; c < a.f; c += 32 * V, ++k) {
             float v[V];
             if (V == 4) *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(yr + c);
             else v[0] = yr[c];
 #pragma unroll
-            for (int q = 0; q < V; ++q) v[q] = po_act(po_pre(a, v[q], c + q), a.act, a.slope) * scale;
+            for (int q = 0; q < V; ++q) {
+                v[q] = po_act(fmaf(v[q] - pc.mu[c + q], pc.isg[c + q], pc.beta[c + q]), a.act, a.slope);
+                ss = fmaf(v[q], v[q], ss);
+            }
+            if (!a.l2) {
+                if (V == 4) *reinterpret_cast<float4*>(orow + c) = *reinterpret_cast<float4*>(v);
+                else orow[c] = v[0];
+            } else if (k < kKeep) {
+#pragma unroll
+                for (int q = 0; q < V; ++q) keep[k][q] = v[q];
+            }
+        }
+        if (!a.l2) continue;
+        const float nrm = fmaxf(sqrtf(warp_sum(ss)), 1e-12f);   // F.normalize: x / max(||x||, eps)
+        if (lane == 0) a.rownorm[r] = nrm;
+        const float scale = 1.f / nrm;
+        k = 0;
+        for (int c = lane * V; c < a.f; c += 32 * V, ++k) {
+            float v[V];
+            if (k < kKeep) {
+#pragma unroll
+                for (int q = 0; q < V; ++q) v[q] = keep[k][q] * scale;
+            } else {   // very wide rows: recompute from the (L1-resident) row
+                if (V == 4) *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(yr + c);
+                else v[0] = yr[c];
+#pragma unroll
+                for (int q = 0; q < V; ++q)
+                    v[q] = po_act(fmaf(v[q] - pc.mu[c + q], pc.isg[c + q], pc.beta[c + q]), a.act, a.slope) * scale;
+            }
             if (V == 4) *reinterpret_cast<float4*>(orow + c) = *reinterpret_cast<float4*>(v);
             else orow[c] = v[0];
         }
@@ -202,11 +248,14 @@ __device__ __forceinline__ float po_da(const PostArgs& a, float g, float o, floa
 // column sums of dA and dA * xhat over the CTA's rows -> partial[blockIdx][{0,1}][f]
 template <int V>
 __global__ void __launch_bounds__(kPoThreads) postops_bwd_reduce_kernel(const __grid_constant__ PostArgs a, int64_t chunk) {
-    extern __shared__ float sh[];   // [kPoWarps][2][f]
+    extern __shared__ float sh[];   // [kPoWarps][2][f] sums, then mean[f], invstd[f]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* mine = sh + (int64_t)wid * 2 * a.f;
+    float* s_mu = sh + (int64_t)kPoWarps * 2 * a.f;
+    float* s_is = s_mu + a.f;
+    for (int c = threadIdx.x; c < a.f; c += kPoThreads) { s_mu[c] = a.mean[c]; s_is[c] = a.invstd[c]; }
     for (int c = lane; c < 2 * a.f; c += 32) mine[c] = 0.f;
-    __syncwarp();
+    __syncthreads();
     const int64_t r0 = (int64_t)blockIdx.x * chunk;
     const int64_t r1 = r0 + chunk < a.n ? r0 + chunk : a.n;
     for (int64_t r = r0 + wid; r < r1; r += kPoWarps) {
@@ -227,7 +276,7 @@ __global__ void __launch_bounds__(kPoThreads) postops_bwd_reduce_kernel(const __
 #pragma unroll
             for (int q = 0; q < V; ++q) {
                 const float da = po_da(a, g[q], o[q], dot, inv_norm);
-                const float xhat = (yv[q] - __ldg(a.mean + c + q)) * __ldg(a.invstd + c + q);
+                const float xhat = (yv[q] - s_mu[c + q]) * s_is[c + q];
                 mine[c + q] += da;                       // a lane owns its columns: no conflicts inside the warp
                 mine[a.f + c + q] = fmaf(da, xhat, mine[a.f + c + q]);
             }
@@ -258,9 +307,25 @@ __global__ void __launch_bounds__(256) postops_bwd_final_kernel(const float* __r
 
 template <int V>
 __global__ void __launch_bounds__(kPoThreads) postops_bwd_apply_kernel(const __grid_constant__ PostArgs a) {
+    extern __shared__ float sh[];   // mean, invstd * gamma, invstd, dbeta / n, dgamma / n   [5][f]
+    float* s_mu = sh;
+    float* s_isg = sh + a.f;
+    float* s_is = sh + 2 * a.f;
+    float* s_db = sh + 3 * a.f;
+    float* s_dg = sh + 4 * a.f;
+    if (a.mean) {
+        const float inv_cnt = 1.f / (float)a.n;
+        for (int c = threadIdx.x; c < a.f; c += kPoThreads) {
+            s_mu[c] = a.mean[c];
+            s_is[c] = a.invstd[c];
+            s_isg[c] = a.invstd[c] * (a.gamma ? a.gamma[c] : 1.f);
+            s_db[c] = a.train ? a.dbeta[c] * inv_cnt : 0.f;
+            s_dg[c] = a.train ? a.dgamma[c] * inv_cnt : 0.f;
+        }
+        __syncthreads();
+    }
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * kPoWarps;
-    const float inv_n = 1.f / (float)a.n;
     for (int64_t r = (int64_t)blockIdx.x * kPoWarps + (threadIdx.x >> 5); r < a.n; r += warps) {
         const float dot = po_row_dot<V>(a, r, lane);
         const float inv_norm = a.l2 ? 1.f / a.rownorm[r] : 1.f;
@@ -282,13 +347,11 @@ __global__ void __launch_bounds__(kPoThreads) postops_bwd_apply_kernel(const __g
             for (int q = 0; q < V; ++q) {
                 float d = po_da(a, g[q], o[q], dot, inv_norm);
                 if (a.mean) {
-                    const float is = __ldg(a.invstd + c + q);
-                    const float gm = a.gamma ? __ldg(a.gamma + c + q) : 1.f;
                     if (a.train) {
-                        const float xhat = (yv[q] - __ldg(a.mean + c + q)) * is;
-                        d = d - __ldg(a.dbeta + c + q) * inv_n - xhat * __ldg(a.dgamma + c + q) * inv_n;
+                        const float xhat = (yv[q] - s_mu[c + q]) * s_is[c + q];
+                        d = d - s_db[c + q] - xhat * s_dg[c + q];
                     }
-                    d *= gm * is;
+                    d *= s_isg[c + q];
                 }
                 g[q] = d;
             }
@@ -339,9 +402,17 @@ int gg_bn_stats_f32(const float* y, int64_t ld, int64_t n, int64_t f, float eps,
     int64_t chunk;
     const int blocks = po_chunks(n, &chunk);
     float* part = static_cast<float*>(workspace);
-    bn_stats_partial_kernel<<<blocks, kPoThreads, 0, st>>>(y, ld, n, (int)f, chunk, part);
+    const size_t smem = (size_t)kPoWarps * 2 * f * sizeof(float);
+    GG_REQUIRE(smem <= 200 * 1024, "gg_bn_stats_f32: f=%lld too wide for the column reduction", (long long)f);
+    if (f % 4 == 0 && po_vec_ok(y, ld)) {
+        GG_CUDA(cudaFuncSetAttribute(bn_stats_partial_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bn_stats_partial_kernel<4><<<blocks, kPoThreads, smem, st>>>(y, ld, n, (int)f, chunk, part);
+    } else {
+        GG_CUDA(cudaFuncSetAttribute(bn_stats_partial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        bn_stats_partial_kernel<1><<<blocks, kPoThreads, smem, st>>>(y, ld, n, (int)f, chunk, part);
+    }
     GG_LAUNCHED();
-    bn_stats_final_kernel<<<(int)ceil_div(f, 256), 256, 0, st>>>(part, blocks, chunk, n, (int)f, eps, mean, invstd,
+    bn_stats_final_kernel<<<(int)ceil_div(f, 256), 256, 0, st>>>(part, y, blocks, n, (int)f, eps, mean, invstd,
                                                                 running_mean, running_var, momentum);
     GG_LAUNCHED();
     return GG_OK;
@@ -365,8 +436,15 @@ int gg_postops_fwd_f32(const float* y, int64_t ld_y, int64_t n, int64_t f, const
     a.y = y; a.ld_y = ld_y; a.dst = out; a.ld_dst = ld_out; a.n = n; a.f = (int)f; a.mean = mean; a.invstd = invstd;
     a.gamma = gamma; a.beta = beta; a.act = act; a.slope = slope; a.l2 = l2norm; a.rownorm = rownorm;
     const bool vec = f % 4 == 0 && po_vec_ok(y, ld_y) && po_vec_ok(out, ld_out);
-    if (vec) postops_fwd_kernel<4><<<po_row_grid(n), kPoThreads, 0, as_stream(stream)>>>(a);
-    else postops_fwd_kernel<1><<<po_row_grid(n), kPoThreads, 0, as_stream(stream)>>>(a);
+    const size_t smem = (size_t)3 * f * sizeof(float);
+    GG_REQUIRE(smem <= 200 * 1024, "gg_postops_fwd_f32: f=%lld too wide", (long long)f);
+    if (vec) {
+        GG_CUDA(cudaFuncSetAttribute(postops_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        postops_fwd_kernel<4><<<po_row_grid(n), kPoThreads, smem, as_stream(stream)>>>(a);
+    } else {
+        GG_CUDA(cudaFuncSetAttribute(postops_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        postops_fwd_kernel<1><<<po_row_grid(n), kPoThreads, smem, as_stream(stream)>>>(a);
+    }
     GG_LAUNCHED();
     return GG_OK;
 }
@@ -395,7 +473,7 @@ int gg_postops_bwd_f32(const float* go, int64_t ld_go, const float* out, int64_t
     if (mean) {   // dgamma / dbeta (also in eval mode: the affine parameters still get gradients)
         int64_t chunk;
         const int blocks = po_chunks(n, &chunk);
-        const size_t smem = (size_t)kPoWarps * 2 * f * sizeof(float);
+        const size_t smem = (size_t)(kPoWarps * 2 + 2) * f * sizeof(float);
         GG_REQUIRE(smem <= 200 * 1024, "gg_postops_bwd_f32: f=%lld too wide for the column reduction", (long long)f);
         if (vec) {
             GG_CUDA(cudaFuncSetAttribute(postops_bwd_reduce_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -408,8 +486,15 @@ int gg_postops_bwd_f32(const float* go, int64_t ld_go, const float* out, int64_t
         postops_bwd_final_kernel<<<(int)ceil_div(f, 256), 256, 0, st>>>(a.partial, blocks, (int)f, dgamma, dbeta);
         GG_LAUNCHED();
     }
-    if (vec) postops_bwd_apply_kernel<4><<<po_row_grid(n), kPoThreads, 0, st>>>(a);
-    else postops_bwd_apply_kernel<1><<<po_row_grid(n), kPoThreads, 0, st>>>(a);
+    const size_t smem_apply = (size_t)5 * f * sizeof(float);
+    GG_REQUIRE(smem_apply <= 200 * 1024, "gg_postops_bwd_f32: f=%lld too wide", (long long)f);
+    if (vec) {
+        GG_CUDA(cudaFuncSetAttribute(postops_bwd_apply_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_apply));
+        postops_bwd_apply_kernel<4><<<po_row_grid(n), kPoThreads, smem_apply, st>>>(a);
+    } else {
+        GG_CUDA(cudaFuncSetAttribute(postops_bwd_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_apply));
+        postops_bwd_apply_kernel<1><<<po_row_grid(n), kPoThreads, smem_apply, st>>>(a);
+    }
     GG_LAUNCHED();
     return GG_OK;
 }

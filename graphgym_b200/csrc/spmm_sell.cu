@@ -230,7 +230,10 @@ __global__ void __launch_bounds__(kSellThreads, G >= 16 ? 3 : 4)
     const bool act = gl < nvec;
     // lanes past the row's last vector (f/4 < G) gather a duplicate of it and never store: no predicates
     const char* __restrict__ xg = reinterpret_cast<const char*>(a.x) + (act ? gl : nvec - 1) * 16;
-    const uint32_t row_bytes = (uint32_t)a.ldx * 4u;
+    uint32_t row_bytes = (uint32_t)a.ldx * 4u;
+    // opaque to the compiler: under the 64-register cap it otherwise RE-DERIVES both values (tid, f, ldx, a.x from the
+    // constant bank: ~15 instructions) in front of every gather instead of keeping three registers live
+    asm volatile("" : "+l"(xg), "+r"(row_bytes));
     const uint64_t pol_keep = l2_policy(a.l2_hint ? 1 : 0), pol_stream = l2_policy(a.l2_hint ? 2 : 0);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int4 none4 = make_int4(-1, -1, -1, -1);
@@ -259,14 +262,9 @@ __global__ void __launch_bounds__(kSellThreads, G >= 16 ? 3 : 4)
         for (int p = 0; p < P; ++p) acc[p] = zero4;
 
         int4 ia = none4, ib = none4;
-        float4 wa = zero4, wb = zero4;
         if (nun > 0) {
             ia = ldg_nc_i4_hint(ip, pol_stream);
-            if (WEIGHTED) wa = ldg_nc_f4_hint(wp, pol_stream);
-            if (P >= 2 || nun > 1) {
-                ib = ldg_nc_i4_hint(ip + S, pol_stream);
-                if (WEIGHTED) wb = ldg_nc_f4_hint(wp + S, pol_stream);
-            }
+            if (P >= 2 || nun > 1) ib = ldg_nc_i4_hint(ip + S, pol_stream);
         }
         for (int t0 = 0; t0 < npairs; t0 += PAIRS) {
 #pragma unroll
@@ -274,15 +272,16 @@ __global__ void __launch_bounds__(kSellThreads, G >= 16 ? 3 : 4)
                 const int t = t0 + jj;
                 // the next pair's index units are requested before this pair's gathers
                 int4 na = none4, nb = none4;
-                float4 nwa = zero4, nwb = zero4;
                 if (t + 1 < npairs) {
                     const int u = 2 * (t + 1);
                     na = ldg_nc_i4_hint(ip + (int64_t)u * S, pol_stream);
-                    if (WEIGHTED) nwa = ldg_nc_f4_hint(wp + (int64_t)u * S, pol_stream);
-                    if (P >= 2 || u + 1 < nun) {
-                        nb = ldg_nc_i4_hint(ip + (int64_t)(u + 1) * S, pol_stream);
-                        if (WEIGHTED) nwb = ldg_nc_f4_hint(wp + (int64_t)(u + 1) * S, pol_stream);
-                    }
+                    if (P >= 2 || u + 1 < nun) nb = ldg_nc_i4_hint(ip + (int64_t)(u + 1) * S, pol_stream);
+                }
+                // this pair's weights travel with its gathers (padding entries: idx = -1 gathers nothing, v = 0)
+                float4 wa = zero4, wb = zero4;
+                if (WEIGHTED) {
+                    wa = ldg_nc_f4_hint(wp + (int64_t)(2 * t) * S, pol_stream);
+                    if (P >= 2 || 2 * t + 1 < nun) wb = ldg_nc_f4_hint(wp + (int64_t)(2 * t + 1) * S, pol_stream);
                 }
                 const float4 v0 = gather(ia.x), v1 = gather(ia.y), v2 = gather(ia.z), v3 = gather(ia.w);
                 const float4 v4 = gather(ib.x), v5 = gather(ib.y), v6 = gather(ib.z), v7 = gather(ib.w);
@@ -295,7 +294,7 @@ __global__ void __launch_bounds__(kSellThreads, G >= 16 ? 3 : 4)
                     add4(A, v0); add4(A, v1); add4(A, v2); add4(A, v3);
                     add4(B, v4); add4(B, v5); add4(B, v6); add4(B, v7);
                 }
-                ia = na; ib = nb; wa = nwa; wb = nwb;
+                ia = na; ib = nb;
             }
         }
         if (act) {

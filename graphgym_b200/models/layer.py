@@ -159,7 +159,7 @@ class GeneralLayer(nn.Module):
         if has_act:
             post.append(_ACT[cfg.gnn.act]())
         self.post_layer = nn.Sequential(*post)
-        self._bn = post[0] if has_bn else None
+        self._has_bn = bool(has_bn)        # post_layer[0] is the BatchNorm1d (not re-registered under a second name)
         self._drop_p = cfg.gnn.dropout
         self._act = _FUSED_ACT.get(cfg.gnn.act) if has_act else (ops.ACT_NONE, 0.0)
 
@@ -167,9 +167,10 @@ class GeneralLayer(nn.Module):
         fused = (h.is_cuda and h.dim() == 2 and h.dtype == torch.float32 and self._act is not None
                  and not (self._drop_p > 0 and self.training) and cfg.b200.fused_postops)
         if fused:
-            if self._bn is None and self._act[0] == ops.ACT_NONE and not self.has_l2norm:
+            bn = self.post_layer[0] if self._has_bn else None
+            if bn is None and self._act[0] == ops.ACT_NONE and not self.has_l2norm:
                 return h
-            return F_.post_ops(h, self._bn, self.training, self._act[0], self._act[1], self.has_l2norm)
+            return F_.post_ops(h, bn, self.training, self._act[0], self._act[1], self.has_l2norm)
         h = self.post_layer(h)
         if self.has_l2norm:
             h = F.normalize(h, p=2, dim=1)

@@ -241,7 +241,7 @@ def _spmm_bf16(csr, x, w_slot, reduce, x_self, self_scale, bias):
 
 
 SELL_SEG = int(_os.environ.get("GG_SELL_SEG", "256"))   # rows longer than this are cut into virtual rows (multiple of 4)
-SELL_MAX_F = int(_os.environ.get("GG_SELL_MAX_F", "64"))   # auto: widths up to this run on the sliced-ELL kernel
+SELL_MAX_F = int(_os.environ.get("GG_SELL_MAX_F", "128"))   # auto: widths up to this run on the sliced-ELL kernel
 
 
 class SellLayout:

@@ -409,6 +409,36 @@ int gg_gat_csc_gather_f32(const int32_t* rowptr_t, const int32_t* slot_map, cons
                           int64_t n, float* alpha_t, float* da_src, gg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * On-device batch collation (csrc/collate.cu): the block-diagonal concatenation DeepSNAP's
+ * Batch.collate() does on the host every iteration (ref: graphgym/loader.py:245-250, graphgym/train.py:21) and the
+ * column-wise feature concat of Preprocess (ref: graphgym/models/feature_augment.py:329-333) as segmented copies, one
+ * launch per output array.  The segment tables are DEVICE arrays (the caller uploads them, a few hundred bytes).
+ *   gg_collate_index_i64: out[dst_offset + k] = (src ? src[k] : 0) + add, k < count  — edge_index rows and
+ *     node_id_index with the graph's node offset added, the `batch` vector (src null, add = graph number), labels.
+ *   gg_collate_rows_f32:  out[(dst_row + i) * ldo + col_offset + c] = (float) src[i * ld + c], i < rows, c < f — feature
+ *     blocks stacked by graph; call once per feature key with that key's column offset.  src_dtype: GG_DTYPE_*.
+ * `scratch_ends_dev`: num_segments int64 of device scratch. */
+typedef struct gg_index_segment {
+    const int64_t* src; /* nullable */
+    int64_t count;
+    int64_t dst_offset;
+    int64_t add;
+    int64_t reserved; /* keeps both segment records at 40 bytes: one table can hold either kind */
+} gg_index_segment;
+typedef struct gg_rows_segment {
+    const void* src;
+    int64_t ld;   /* elements between consecutive source rows */
+    int64_t rows;
+    int64_t f;
+    int64_t dst_row;
+} gg_rows_segment;
+enum gg_dtype { GG_DTYPE_F32 = 0, GG_DTYPE_I64 = 1, GG_DTYPE_U8 = 2 };
+int gg_collate_index_i64(const gg_index_segment* segments_dev, int num_segments, int64_t total, int64_t* out,
+                         int64_t* scratch_ends_dev, gg_stream_t stream);
+int gg_collate_rows_f32(const gg_rows_segment* segments_dev, int num_segments, int64_t total_elements, int src_dtype,
+                        float* out, int64_t ldo, int64_t col_offset, int64_t* scratch_ends_dev, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused layer post-ops (csrc/postops.cu) — what GeneralLayer / GNNStackStage apply after the
  * message-passing layer (ref: graphgym/models/layer.py:26-46, graphgym/models/gnn.py:76-81):
  *   a = BatchNorm1d(y)   (mean / invstd null: no BN; gamma / beta null: no affine)

@@ -573,7 +573,7 @@ def run_ours(args, spec, rank, world, dev):
         del pad, ei_piece
     else:
         ei_host = ei.cpu().pin_memory()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(5, min(args.steps, 10))
     res_host = torch.empty(fout, dtype=torch.float32).pin_memory()
 
     side = torch.cuda.Stream(device=dev)
@@ -619,18 +619,22 @@ def run_ours(args, spec, rank, world, dev):
                 nxt = issue_copies()
             compute(*cur_in)
 
-    e2e_run(2)
+    e2e_run(4)   # the prefetch pipeline keeps two steps' buffers alive: let the caching allocator reach its steady state
     sync_all()
     clear_cache()
+    stats0 = torch.cuda.memory_stats(dev)
     s.record()
     e2e_run(e2e_steps)
     e.record()
     sync_all()
+    stats1 = torch.cuda.memory_stats(dev)
     e2e_ms = max_over_ranks(s.elapsed_time(e)) / e2e_steps
     h2d = int(sum_over_ranks(x_host.numel() * 4 + ei_host.numel() * 8))
     e2e = {'value': round(ef / (e2e_ms * 1e-3) / 1e9, 3), 'unit': 'GEdge-feat/s',
            'ms_per_step': round(e2e_ms, 3), 'steps': e2e_steps,
            'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': int(fout * 4 * world),
+           'stats': {k: stats1.get(k, 0) - stats0.get(k, 0) for k in ('num_device_alloc', 'num_device_free', 'num_alloc_retries')}
+           if os.environ.get('GG_E2E_STATS') else None,
            'includes': 'every step: H2D of this rank\'s 1/N of edge_index, then of its node_feature rows, from pinned memory '
                        '(copy stream; the copies of step i+1 overlap the compute of step i, as a prefetching loader does), '
                        + ('NCCL all-gather of the edge list pieces over NVLink, ' if multi else '') +

@@ -14,6 +14,11 @@ oracle/pyg_shim.py), feeds them seeded inputs and stores inputs, parameters, out
     identity.npz        compute_identity on K3 / P3 / C4 and two bundled fixture graphs
     egonets.npz         ego_nets (canonicalised: member sets + induced edge sets per centre) on C4 and
                         on bundled fixture graphs, radius 1..3
+    scalefree16.npz     the Cfg-A workload: graphs [0:16] of datasets/scalefree.pkl as one block-diagonal
+                        batch (edge lists, node offsets), the reference label of the node task — nx.clustering
+                        (feature_augment.py:81-82) — its 10-way balanced binning restated from feature_augment.py:208-231
+                        and :134-143 over the 16 graphs, and the size of every graph's radius-3 ego expansion as the
+                        reference's own transform.py produces it
 The committed .npz files are what the tests read; /root/reference is never touched at test time.
 """
 import os
@@ -222,9 +227,43 @@ def egonets(ns):
     print('egonets.npz', len(out), 'arrays')
 
 
+def scalefree16(ns):
+    graphs = fixture_graphs('scalefree', range(16))
+    out, eis, ptr, clus, ego_nodes, ego_edges = {}, [], [0], [], [], []
+    for G in graphs:
+        G = nx.convert_node_labels_to_integers(nx.Graph(G.edges()), ordering='sorted')
+        n = G.number_of_nodes()
+        eis.append(nx_to_edge_index(G) + ptr[-1])
+        ptr.append(ptr[-1] + n)
+        c = nx.clustering(G)
+        clus += [c[v] for v in range(n)]                      # feature_augment.py:81-82: list(nx.clustering(G).values())
+        g = _Graph(G.copy())
+        ns.transform.ego_nets(g, radius=3)                    # the reference's own transform (cfg.gnn.layers_mp = 3)
+        ego_nodes.append(g.G.number_of_nodes())
+        ego_edges.append(g.G.number_of_edges())
+    arr = np.array(clus)
+    # balanced binning, feature_dim = 10 (feature_augment.py:219-231), then np.digitize(arr, bins) - 1 (:139-140)
+    sorted_arr = np.sort(arr)
+    bin_indices = np.linspace(0, len(arr), num=10, endpoint=False).astype(int)
+    bins = np.unique(sorted_arr[bin_indices])
+    out['edge_index'] = np.concatenate(eis, axis=1)
+    out['graph_ptr'] = np.array(ptr, dtype=np.int64)
+    out['clustering'] = arr
+    out['bin_edges'] = bins
+    out['label'] = (np.digitize(arr, bins) - 1).astype(np.int64)
+    out['ego_nodes'] = np.array(ego_nodes, dtype=np.int64)
+    out['ego_undirected_edges'] = np.array(ego_edges, dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, 'scalefree16.npz'), **out)
+    print('scalefree16.npz', {k: v.shape for k, v in out.items()}, 'ego nodes', sum(ego_nodes))
+
+
 if __name__ == '__main__':
     ns = pyg_shim.install(REF)
+    if len(sys.argv) > 1 and sys.argv[1] == 'scalefree16':
+        scalefree16(ns)
+        sys.exit(0)
     layers(ns)
     identity(ns)
     egonets(ns)
     pooling(ns)
+    scalefree16(ns)

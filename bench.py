@@ -52,6 +52,12 @@ WORKLOADS = {
     'ego_idgin': dict(aux='ego', graph='ba_batch', graphs=256, nodes_per_graph=64, m=4, radius=3, hidden=256,
                       layers=3, desc='ID-GNN Full: 3-hop ego-nets of every node of 256 BA graphs x 64 nodes '
                                      '(reference dataset shape), then 3 ginidconv layers 256->256 fwd+bwd'),
+    # configs[0] (Cfg-A): idgcn_tf on the bundled ScaleFree graphs [0:16] (committed fixture
+    # tests/golden/scalefree16.npz, made from /root/reference/datasets/scalefree.pkl), 3-hop ego-nets, X = ones [N,1],
+    # pre_mp-free stack of 3 gcnidconv GeneralLayers 1 -> 128 -> 128 -> 128 (BN + ReLU, stage L2 norm), fwd + bwd
+    'scalefree_idgcn': dict(aux='cfg_a', fixture='tests/golden/scalefree16.npz', radius=3, hidden=128, layers=3,
+                            desc='idgcn_tf (ID-GNN Full GCN): 16 bundled ScaleFree graphs x 64 nodes, 3-hop ego-nets, '
+                                 '3 gcnidconv GeneralLayers 1->128->128->128 (BN, ReLU, L2), fwd+bwd'),
 }
 DEFAULT_WORKLOAD = 'products_gcn'
 DEFAULT_HALO = 'sliced'
@@ -232,14 +238,126 @@ def gen_ba_batch(spec, device, seed=0):
     return G * nn_, ei, torch.arange(G + 1, device=device, dtype=torch.int32) * nn_
 
 
-def run_aux(args, spec, dev):
-    """Secondary hot-path rows: their own units, same JSON shape."""
-    from graphgym_b200 import ops
+def _aux_dist(world, dev):
+    """Secondary workloads shard by independent units: no data-path collective; the process group only
+    carries the timing barrier, the max-over-ranks reduction and, for the trained stack, the dW all-reduce."""
+    import torch.distributed as dist
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+    return sync_all, (lambda v: reduce(v, dist.ReduceOp.MAX)), (lambda v: reduce(v, dist.ReduceOp.SUM))
+
+
+def _timed_steps(fn, steps, warmup, sync_all, max_over_ranks):
+    for _ in range(warmup):
+        fn()
+    sync_all()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        fn()
+    e.record()
+    sync_all()
+    return max_over_ranks(s.elapsed_time(e)) / steps
+
+
+def cpu_cycles_baseline(seconds):
+    """The reference algorithm itself (identity.py:25-35: dense A_hat, k-1 dense matmuls) on BA graphs of growing size; at
+    1M nodes it is infeasible (n^2 floats = 4 TB)."""
+    from oracle import identity as oid
+    torch.set_num_threads(os.cpu_count() or 1)
+    out, t_all = [], time.time()
+    for n in (64, 2708, 8192, 16384):
+        if n > 8192 and seconds < 120:
+            out.append({'nodes': n, 'skipped': 'about 60 s of dense matmul on 16 cores: run with --cpu-seconds >= 120'})
+            continue
+        _, ei = gen_graph(dict(graph='ba', n=n, m=5), torch.device('cpu'), seed=0)
+        t0 = time.time()
+        oid.compute_identity(ei, n, 10)
+        dt = time.time() - t0
+        out.append({'nodes': n, 'seconds': round(dt, 4), 'nodes_per_s': round(n / dt, 1)})
+    return {'kind': 'port', 'cores': os.cpu_count() or 1, 'unit': 'nodes/s', 'value': out[2].get('nodes_per_s'),
+            'sample': 'oracle/identity.py = dense compute_identity of the reference (k = 10) on BA graphs (m = 5) of '
+                      '64 / 2708 / 8192 / 16384 nodes; the 1M-node workload graph is out of reach for it (O(n^3), 4 TB)',
+            'sizes': out, 'wall_s': round(time.time() - t_all, 1)}
+
+
+def cpu_ego_baseline(ei_cpu, n, radius, graph_ptr=None, max_centres=512):
+    """nx.ego_graph per centre + induced-subgraph copy, as the reference's ego_nets does (transform.py:11-38), on the
+    workload's own graphs (a bounded number of centres)."""
+    import networkx as nx
+    G = nx.Graph()
+    G.add_nodes_from(range(n))
+    G.add_edges_from(ei_cpu.t().tolist())
+    centres = list(range(0, n, max(1, n // max_centres)))[:max_centres]
+    t0 = time.time()
+    nodes = edges = 0
+    for c in centres:
+        ego = nx.ego_graph(G, c, radius=radius)
+        sub = nx.Graph(ego)       # the reference copies every ego into the output graph with fresh ids
+        nodes += sub.number_of_nodes()
+        edges += sub.number_of_edges()
+    dt = time.time() - t0
+    return {'kind': 'reference-algorithm (networkx)', 'cores': 1, 'unit': 'centres/s', 'value': round(len(centres) / dt, 1),
+            'ms_per_centre': round(1e3 * dt / len(centres), 3), 'output_edges_per_s': round(edges / dt, 1),
+            'sample': f'{len(centres)} of {n} centres, radius {radius}, nx.ego_graph + subgraph copy (transform.py:20-36)'}
+
+
+def cpu_stack_baseline(spec, x_cpu, ei_cpu, ids_cpu, dims, layer_name, seconds):
+    """fwd+bwd of the layer stack with the oracle layers + torch BN / ReLU / normalize on the host (the reference's own
+    module sequence, layer.py:26-46), all host threads."""
+    import torch.nn.functional as Fn
+    from oracle import layers as olayers
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    params = []
+    for din, dout in zip(dims[:-1], dims[1:]):
+        mk = lambda *s: (torch.randn(*s, generator=g) * 0.1).requires_grad_(True)
+        if layer_name == 'gcnidconv':
+            params.append((mk(din, dout), mk(din, dout)))
+        else:   # ginidconv: nn / nn_id = Linear, ReLU, Linear
+            params.append(tuple(mk(*s) for s in ((dout, din), (dout,), (dout, dout), (dout,)) * 2))
+    bns = [torch.nn.BatchNorm1d(d) for d in dims[1:]]
+    gy = torch.randn(x_cpu.size(0), dims[-1], generator=g)
+
+    def step():
+        h = x_cpu
+        for i, p in enumerate(params):
+            if layer_name == 'gcnidconv':
+                h = olayers.gcn_idconv(h, ei_cpu, ids_cpu, p[0], p[1], None)
+                h = torch.relu(bns[i](h))
+            else:
+                h = torch.relu(olayers.gin_idconv(h, ei_cpu, ids_cpu, p[:4], p[4:]))
+        if layer_name == 'gcnidconv':
+            h = Fn.normalize(h, p=2, dim=1)
+        h.backward(gy)
+    t, done = _time_cpu_steps(step, seconds, None, 1)
+    return t, done
+
+
+def run_aux(args, spec, dev, rank=0, world=1):
+    """Secondary hot-path rows (Cfg-A / Cfg-C / Cfg-E): their own units, same JSON shape.  With
+    --gpus N every rank works on its own units (source blocks / graphs): weak scaling, no data-path collective."""
+    from graphgym_b200 import ops, parallel
     from graphgym_b200.contrib.transform import identity as gid
     from graphgym_b200.models import transform as gtr
     from graphgym_b200.models.layer import Batch, layer_dict
     peak, peak_src = load_peaks()
     clocks = ClockSampler(dev.index or 0)
+    sync_all, max_over_ranks, sum_over_ranks = _aux_dist(world, dev)
+    par = 'single GPU' if world == 1 else f'{world} GPUs, independent units per rank (no data-path collective)'
     if spec['aux'] == 'cycles':
         n, ei = gen_graph(spec, dev, seed=0)
         k = spec['k']
@@ -251,11 +369,11 @@ def run_aux(args, spec, dev):
         use_mp = gid.MP_STEP
         ws = torch.empty(int(L.gg_cycle_diag_mp_workspace_bytes(n, items)), dtype=torch.uint8, device=dev)
         out = torch.empty((128, k), dtype=torch.float32, device=dev)
-        blk = [0]
+        blk = [rank]
 
-        def one_block():   # 128 consecutive sources: 5 hops over the whole graph + 10 dot products
+        def one_block():   # 128 consecutive sources: 5 hops over the whole graph + 10 dot products; rank r takes blocks r, r+P, ...
             sb = (blk[0] * 128) % (n - 128)
-            blk[0] += 1
+            blk[0] += world
             if use_mp:
                 ops.check(L.gg_cycle_diag_mp_f32(ops._ptr(csr.rowptr), ops._ptr(csr.nbr), ops._ptr(w), ops._ptr(item_row),
                                                  ops._ptr(item_slot), items, n, k, 1, sb, 128, ops._ptr(out), k,
@@ -265,66 +383,119 @@ def run_aux(args, spec, dev):
                                               ops._ptr(out), k, ops._ptr(ws), ws.numel(), ops._stream()), 'gg_cycle_diag_f32')
         launches0 = ops.launch_count()
         with clocks:
-            ms = _event_ms(one_block, args.steps, args.warmup)
-        launches = (ops.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+            ms = _timed_steps(one_block, args.steps, args.warmup, sync_all, max_over_ranks)
+        launches = int(sum_over_ranks((ops.launch_count() - launches0) * args.steps // (args.steps + args.warmup)))
         hops = (k + 1) // 2
         slots = csr.num_slots
-        visits = slots * 128 * hops
+        visits = slots * 128 * hops * world
         step_bytes = hops * (slots * 512 + n * 512 + slots * 8 + (n + 1) * 4) + k * 2 * n * 512
         ach = step_bytes / (ms * 1e-3) / 1e9
+        cpu = cpu_cycles_baseline(args.cpu_seconds) if (rank == 0 and not args.no_cpu and world == 1) else None
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
         return {'metric': 'cycle-feature edge-visits/s (one visit = one slot x one source column x one hop)',
-                'value': round(visits / (ms * 1e-3) / 1e9, 3), 'unit': 'G edge-visits/s', 'n_gpus': 1,
+                'value': round(visits / (ms * 1e-3) / 1e9, 3), 'unit': 'G edge-visits/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms, 4), 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (seeded BA generator in bench.py)',
-                'config': {'workload': spec['desc'], 'nodes': n, 'slots': slots, 'k': k, 'sources_per_step': 128,
-                           'whole_graph_seconds_1gpu': round(ms * 1e-3 * (n / 128), 1),
+                'config': {'workload': spec['desc'], 'nodes': n, 'slots': slots, 'k': k, 'sources_per_step_per_gpu': 128,
+                           'parallelism': par,
+                           'whole_graph_seconds': round(ms * 1e-3 * (n / 128) / world, 1),
                            'l2_policy': 'inputs larger than L2 (two 512 MB walk matrices)'},
-                'clocks': clocks.summary(), 'e2e': None, 'gpu_launches': int(launches),
-                'roofline': {'bound': 'hbm', 'kernel': ('spmm_mpg_kernel' if use_mp else 'walk_step_kernel') + ' (+ walk_dot) over one block of 128 sources',
+                'clocks': clocks.summary(), 'e2e': None, 'gpu_launches': launches,
+                'roofline': {'bound': 'hbm', 'kernel': ('spmm_mpg_kernel' if use_mp else 'walk_step_kernel') + ' (+ walk_dot) over one block of 128 sources (per GPU)',
                              'achieved': round(ach, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4),
                              'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_step': step_bytes},
-                'cpu_baseline': None}
-    # ---- ID-GNN Full ----
-    n, ei, gptr = gen_ba_batch(spec, dev)
-    radius, hid, nl = spec['radius'], spec['hidden'], spec['layers']
+                'cpu_baseline': cpu}
+    # ---- ID-GNN Full: ego-net extraction + a stack of ID layers (Cfg-E: synthetic BA batch + ginidconv; Cfg-A: fixture + gcnidconv)
+    cfg_a = spec['aux'] == 'cfg_a'
+    if cfg_a:
+        d = np.load(os.path.join(ROOT, spec['fixture']))
+        ei = torch.from_numpy(d['edge_index']).to(dev)
+        gptr = torch.from_numpy(d['graph_ptr']).to(dev).int()
+        n = int(d['graph_ptr'][-1])
+        layer_name, dims = 'gcnidconv', [1] + [spec['hidden']] * spec['layers']
+    else:
+        n, ei, gptr = gen_ba_batch(spec, dev, seed=rank)      # every rank its own graphs (data parallel over graphs)
+        layer_name, dims = 'ginidconv', [spec['hidden']] * (spec['layers'] + 1)
+    radius, nl = spec['radius'], spec['layers']
     res = gtr.ego_nets_batch(ei, n, radius, gptr)     # warm + sizes
     torch.cuda.synchronize()
+    n_out, e_out = res['num_nodes'], int(res['edge_index'].size(1))
+    checks = None
+    if cfg_a:   # sizes of the reference's own ego expansion (transform.py run by tests/golden/make_golden.py)
+        per_graph = (res['out_node_ptr'][1:] - res['out_node_ptr'][:-1]).cpu().numpy()
+        checks = {'ego_nodes_equal_reference': bool(np.array_equal(per_graph, d['ego_nodes'])),
+                  'ego_edges_equal_reference': bool(e_out == 2 * int(d['ego_undirected_edges'].sum()))}
+    from graphgym_b200.config import cfg as gg_cfg, reset_cfg
+    from graphgym_b200.models.gnn import GNNStackStage
+    reset_cfg()
     with clocks:
-        ego_ms = _event_ms(lambda: gtr.ego_nets_batch(ei, n, radius, gptr), max(3, args.steps // 2), 2)
-        n_out, e_out = res['num_nodes'], int(res['edge_index'].size(1))
+        ego_ms = _timed_steps(lambda: gtr.ego_nets_batch(ei, n, radius, gptr), max(3, args.steps // 2), 2, sync_all,
+                              max_over_ranks)
         torch.manual_seed(0)
-        layers = [layer_dict['ginidconv'](hid, hid, bias=True).to(dev) for _ in range(nl)]
-        x = gen_features(n_out, hid, dev)
-        gy = gen_features(n_out, hid, dev, seed=7)
         eo, ids = res['edge_index'], res['node_id_index']
+        if cfg_a:
+            stages = [GNNStackStage(1, spec['hidden'], nl, 'gcnidconv').to(dev)]
+            x = torch.ones(n_out, 1, device=dev)                                  # node_feature = tensor([1.]) per node
+        else:
+            stages = [layer_dict['ginidconv'](dims[i], dims[i + 1], bias=True).to(dev) for i in range(nl)]
+            x = gen_features(n_out, dims[0], dev, seed=rank)
+        gy = gen_features(n_out, dims[-1], dev, seed=7 + rank)
 
         def step():
-            for l in layers:
+            for l in stages:
                 l.zero_grad(set_to_none=True)
             h = x.detach().requires_grad_(True)
             b = Batch(h, eo, ids)
-            for l in layers:
+            for l in stages:
                 b = l(b)
-                b.node_feature = torch.relu(b.node_feature)   # GeneralLayer's activation (ref: layer.py:31-33)
+                if not cfg_a:
+                    b.node_feature = torch.relu(b.node_feature)   # GeneralLayer's activation (ref: layer.py:31-33)
             b.node_feature.backward(gy)
+            if world > 1:
+                for l in stages:
+                    parallel.allreduce_grads(l)
         launches0 = ops.launch_count()
-        ms = _event_ms(step, args.steps, args.warmup)
-    launches = (ops.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
-    ef = e_out * hid * 2 * nl
+        ms = _timed_steps(step, args.steps, args.warmup, sync_all, max_over_ranks)
+    launches = int(sum_over_ranks((ops.launch_count() - launches0) * args.steps // (args.steps + args.warmup)))
+    slots_per_layer = e_out + (n_out if cfg_a else 0)      # gcnidconv adds the remaining self loops
+    ef_rank = sum(slots_per_layer * (dims[i + 1] if cfg_a else dims[i]) * 2 for i in range(nl))
+    ef = sum_over_ranks(ef_rank)
     ego_bytes = e_out * 8 + n_out * 8 + int(ei.size(1)) * 4   # output edges (2 x int64 written) + ids + adjacency read
-    return {'metric': 'layer fwd+bwd GEdge-feat/s', 'value': round(ef / (ms * 1e-3) / 1e9, 3), 'unit': 'GEdge-feat/s',
-            'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms, 4),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic (seeded BA-batch generator in bench.py; random-init weights)',
-            'config': {'workload': spec['desc'], 'centres': n, 'ego_batch_nodes': n_out, 'ego_batch_edges_directed': e_out,
-                       'hidden': hid, 'layers': nl,
-                       'l2_policy': 'inputs larger than L2 (feature matrix %.0f MB)' % (n_out * hid * 4 / 1e6)},
-            'clocks': clocks.summary(), 'e2e': None, 'gpu_launches': int(launches),
-            'ego_extraction': {'ms': round(ego_ms, 3), 'centres_per_s': round(n / (ego_ms * 1e-3), 1),
-                               'output_edges_per_s': round(e_out / (ego_ms * 1e-3), 1),
-                               'output_GBps': round(ego_bytes / (ego_ms * 1e-3) / 1e9, 2),
-                               'includes': 'adjacency layout build, sizes pass, fill pass (two kernel launches + scans)'},
-            'roofline': None, 'cpu_baseline': None}
+    cpu = None
+    if rank == 0 and not args.no_cpu and world == 1:
+        ei_cpu = ei.cpu()
+        cpu_ego = cpu_ego_baseline(ei_cpu, n, radius)
+        t_cpu, done = cpu_stack_baseline(spec, x.cpu(), eo.cpu(), ids.cpu(), dims, layer_name, min(args.cpu_seconds, 20.0))
+        cpu = {'value': round(ef_rank / t_cpu / 1e9, 4), 'unit': 'GEdge-feat/s', 'cores': os.cpu_count() or 1, 'kind': 'port',
+               'ms_per_step': round(t_cpu * 1e3, 2), 'steps': done,
+               'sample': f'the same ego batch ({n_out} nodes, {e_out} directed edges), {nl} x {layer_name} fwd+bwd with the '
+                         'oracle layers + torch BN / ReLU / normalize on the host, all threads',
+               'ego_extraction': cpu_ego}
+    out = {'metric': 'layer fwd+bwd GEdge-feat/s', 'value': round(ef / (ms * 1e-3) / 1e9, 3), 'unit': 'GEdge-feat/s',
+           'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms, 4),
+           'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+           'data': ('bundled reference fixture (datasets/scalefree.pkl graphs [0:16], committed as tests/golden/scalefree16.npz)'
+                    if cfg_a else 'synthetic (seeded BA-batch generator in bench.py)') + '; random-init weights',
+           'config': {'workload': spec['desc'], 'centres_per_gpu': n, 'ego_batch_nodes_per_gpu': n_out,
+                      'ego_batch_edges_directed_per_gpu': e_out, 'dims': dims, 'layers': nl, 'layer': layer_name,
+                      'parallelism': par + ('' if world == 1 else '; dW all-reduced every step (data parallel over graphs)'),
+                      'l2_policy': ('inputs larger than L2 (feature matrix %.0f MB)' % (n_out * dims[-1] * 4 / 1e6))
+                      if n_out * dims[-1] * 4 > 126e6 else 'working set fits L2 (%.0f MB): launch / latency bound' % (n_out * dims[-1] * 4 / 1e6)},
+           'clocks': clocks.summary(), 'e2e': None, 'gpu_launches': launches,
+           'ego_extraction': {'ms': round(ego_ms, 3), 'centres_per_s': round(n * world / (ego_ms * 1e-3), 1),
+                              'output_edges_per_s': round(e_out * world / (ego_ms * 1e-3), 1),
+                              'output_GBps_per_gpu': round(ego_bytes / (ego_ms * 1e-3) / 1e9, 2),
+                              'includes': 'adjacency layout build, sizes pass, fill pass (two kernel launches + scans)'},
+           'roofline': None, 'cpu_baseline': cpu, 'reference_checks': checks}
+    reset_cfg()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
 
 
 def gpu_comparators(name, n, ei, x, gy, fin, fout, lay, policy, ef, dev):
@@ -868,9 +1039,7 @@ def main():
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     if spec.get('aux'):
-        if world > 1:
-            raise SystemExit('the secondary workloads shard by independent units: run them with --gpus 1')
-        out = run_aux(args, spec, dev)
+        out = run_aux(args, spec, dev, rank, world)
     else:
         out = run_ours(args, spec, rank, world, dev)
     if rank == 0:

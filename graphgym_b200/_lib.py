@@ -130,6 +130,9 @@ SIGNATURES = {
     "gg_gat_csc_gather_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "gg_collate_index_i64": (c_int, [c_ptr, c_int, c_i64, c_ptr, c_ptr, c_ptr]),
     "gg_collate_rows_f32": (c_int, [c_ptr, c_int, c_i64, c_int, c_ptr, c_i64, c_i64, c_ptr, c_ptr]),
+    "gg_f64_sort_keys": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "gg_gather_u32": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr]),
+    "gg_digitize_f64": (c_int, [c_ptr, c_i64, c_ptr, c_int, c_ptr, c_ptr]),
     "gg_postops_workspace_bytes": (c_size, [c_i64, c_i64]),
     "gg_bn_stats_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_f32, c_ptr, c_size, c_ptr]),
     "gg_postops_fwd_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_f32, c_int, c_ptr,

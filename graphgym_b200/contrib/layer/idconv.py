@@ -81,7 +81,8 @@ class _NormalisedIDConv(_IDBase):
         h = F_.id_linear(x, self.weight, self.weight_id, get_id_index(id, n))
         if self.normalize:
             # add_remaining_self_loops + deg over edge_index[0] (ref: idconv.py:139-148)
-            layout, kind = get_layout(edge_index, n, ops.LOOPS_ADD_REMAINING), 'gcn_src'
+            layout = get_layout(edge_index, n, ops.LOOPS_ADD_REMAINING)
+            kind = 'gcn_src_mean' if self.aggr == 'mean' else 'gcn_src'
         else:
             layout, kind = get_layout(edge_index, n, ops.LOOPS_KEEP), \
                 ('mean' if self.aggr == 'mean' else 'sum')

@@ -70,12 +70,23 @@ def _run(layout_csr, w_slot, n, k, symmetric, graph_ptr, integer):
     return out, overflow
 
 
-def compute_identity(edge_index, n, k, symmetric=True, graph_ptr=None):
-    """[n, k] fp32, column p-1 = diag(A_hat^p).  ``symmetric=True`` (undirected graphs, as every
-    reference dataset is) enables the half-power trick; pass False for a directed edge list.
+def is_symmetric(edge_index, n):
+    """True iff the multiset of (src, tgt) pairs equals the multiset of (tgt, src) pairs.  A one-off check at
+    feature-augmentation time (two int64 sorts, off the per-step path): the half-power trick diag(A^2t) = <V_t, V_t> is
+    only valid on a symmetric edge list, and the reference's ``compute_identity`` is correct for any."""
+    a = torch.sort(edge_index[0] * int(n) + edge_index[1]).values
+    b = torch.sort(edge_index[1] * int(n) + edge_index[0]).values
+    return bool(torch.equal(a, b))
+
+
+def compute_identity(edge_index, n, k, symmetric=None, graph_ptr=None):
+    """[n, k] fp32, column p-1 = diag(A_hat^p).  ``symmetric=None`` (default) checks the edge list once and enables the
+    half-power trick only for undirected graphs (as every reference dataset is); True / False skip the check.
     ``graph_ptr`` ([G+1] node offsets of a block-diagonal batch) restricts every source block to its
     own graphs."""
     ops._need_cuda(edge_index)
+    if symmetric is None:
+        symmetric = is_symmetric(edge_index, n)
     csr = ops.layout_build(edge_index, n, ops.LOOPS_ADD_REMAINING, ops.BY_TARGET)
     csc = ops.layout_build(edge_index, n, ops.LOOPS_ADD_REMAINING, ops.BY_SOURCE)
     deg = ops.segment_degree(csc)                 # degree over edge_index[0] (identity.py:17-18)
@@ -84,9 +95,11 @@ def compute_identity(edge_index, n, k, symmetric=True, graph_ptr=None):
     return out
 
 
-def closed_walk_counts(edge_index, n, k, symmetric=True, graph_ptr=None):
-    """([n, k] int64 exact closed-walk counts diag(A^p), number of overflowed entries)."""
+def closed_walk_counts(edge_index, n, k, symmetric=None, graph_ptr=None):
+    """([n, k] int64 exact closed-walk counts diag(A^p), number of overflowed entries).  ``symmetric`` as above."""
     ops._need_cuda(edge_index)
+    if symmetric is None:
+        symmetric = is_symmetric(edge_index, n)
     csr = ops.layout_build(edge_index, n, ops.LOOPS_KEEP, ops.BY_TARGET)
     out, overflow = _run(csr, None, n, k, symmetric, graph_ptr, integer=True)
     return out, int(overflow.item())

@@ -12,14 +12,19 @@ from . import ops
 
 class _Aggregate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, layout, kind, self_scale, bias, half):
+    def forward(ctx, x, layout, kind, self_scale, bias, half, residual=None):
         w_fwd, _ = layout.weights(kind)
-        reduce = ops.MEAN if kind == "mean" else ops.SUM
+        reduce = ops.MEAN if kind.endswith("mean") else ops.SUM
         x = x.contiguous()
         gathered = ops.cast_bf16(x) if half else x        # 1e-2 mode: the gathered operand in bf16, fp32 arithmetic
-        out = ops.spmm(layout.csr, gathered, w_fwd, reduce, x if self_scale != 0.0 else None, self_scale, bias)
+        if residual is not None:      # out = A x + residual (+ bias): the residual rides in the epilogue's self term
+            if self_scale != 0.0:
+                raise ValueError("aggregate: residual excludes self_scale")
+            out = ops.spmm(layout.csr, gathered, w_fwd, reduce, residual.contiguous(), 1.0, bias)
+        else:
+            out = ops.spmm(layout.csr, gathered, w_fwd, reduce, x if self_scale != 0.0 else None, self_scale, bias)
         ctx.layout, ctx.kind, ctx.self_scale, ctx.half = layout, kind, self_scale, half
-        ctx.has_bias = bias is not None
+        ctx.has_bias, ctx.has_residual = bias is not None, residual is not None
         return out
 
     @staticmethod
@@ -34,15 +39,15 @@ class _Aggregate(torch.autograd.Function):
                           ctx.self_scale, None)
         if ctx.has_bias and ctx.needs_input_grad[4]:
             gb = ops.colsum(g)
-        return gx, None, None, None, gb, None
+        return gx, None, None, None, gb, None, (g if ctx.has_residual else None)
 
 
-def aggregate(x, layout, kind="sum", self_scale=0.0, bias=None):
-    """out[i] = reduce_{j->i} w_ji x[j] + self_scale * x[i] + bias.  ``cfg.b200.gather_dtype = 'bf16'`` stores the
-    gathered operand in bf16 (forward and backward) when the width allows it (f % 8 == 0, f <= 256)."""
+def aggregate(x, layout, kind="sum", self_scale=0.0, bias=None, residual=None):
+    """out[i] = reduce_{j->i} w_ji x[j] + self_scale * x[i] + residual[i] + bias.  ``cfg.b200.gather_dtype = 'bf16'``
+    stores the gathered operand in bf16 (forward and backward) when the width allows it (f % 8 == 0, f <= 256)."""
     from .config import cfg
     half = cfg.b200.gather_dtype == "bf16" and ops.bf16_gather_ok(x.size(1))
-    return _Aggregate.apply(x, layout, kind, float(self_scale), bias, half)
+    return _Aggregate.apply(x, layout, kind, float(self_scale), bias, half, residual)
 
 
 class _SegLinear(torch.autograd.Function):

@@ -58,6 +58,7 @@ class GraphLayout:
         'mean'     forward divides in the kernel; backward weight = 1/indeg(target)
         'gcn_src'  D^-1/2 A D^-1/2 with the degree summed over edge_index[0] (ref: idconv.py:143-148)
         'gcn_tgt'  same with the degree summed over edge_index[1] (PyG >= 1.6 GCNConv, layer.py:138)
+        'gcn_src_mean'  'gcn_src' weights reduced with a mean over the target's in-edges
         """
         if kind not in self._weights:
             if kind == "sum":
@@ -68,6 +69,12 @@ class GraphLayout:
             elif kind in ("gcn_src", "gcn_tgt"):
                 deg = ops.segment_degree(self.csc if kind == "gcn_src" else self.csr)
                 w = (ops.gcn_norm(self.csr, deg), ops.gcn_norm(self.csc, deg))
+            elif kind == "gcn_src_mean":
+                # MessagePassing(aggr='mean') over the normalised messages (ref: idconv.py:19,89-92 with
+                # cfg.gnn.agg = 'mean' and normalize_adj): forward = mean_i(w_e h_j); backward weight = w_e / indeg(target).
+                # One elementwise product per layout (layout-build level, cached).
+                w_csr, w_csc = self.weights("gcn_src")
+                w = (w_csr, w_csc * ops.mean_weights(self.csc, ops.segment_degree(self.csr)))
             else:
                 raise KeyError(kind)
             self._weights[kind] = w

@@ -21,6 +21,7 @@ from graphgym_b200 import functional as F_
 from graphgym_b200 import ops
 from graphgym_b200.config import cfg
 from graphgym_b200.contrib.layer import idconv as _idconv  # registers the ID layers
+from graphgym_b200.contrib.layer import generalconv as _generalconv  # registers sageinitconv; GeneralConv is a built-in
 from graphgym_b200.contrib.layer.idconv import _mlp, glorot_, zeros_
 from graphgym_b200.graph import get_layout
 
@@ -190,6 +191,7 @@ _builtin = {
     'sageconv': SAGEConv,
     'gatconv': GATConv,
     'ginconv': GINConv,
+    'generalconv': _generalconv.GeneralConv,
 }
 
 # built-ins win on a name clash, contrib registrations fill the rest (ref: layer.py:238)

@@ -439,6 +439,16 @@ int gg_collate_rows_f32(const gg_rows_segment* segments_dev, int num_segments, i
                         float* out, int64_t ldo, int64_t col_offset, int64_t* scratch_ends_dev, gg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Label / feature binning (csrc/binning.cu) — the numpy preprocessing of
+ * graphgym/models/feature_augment.py:139-140,219-231 in float64 on the device:
+ *   gg_f64_sort_keys: order-preserving 64-bit keys of x split into two u32 words, index[i] = i.  Ascending stable order =
+ *     gg_sort_pairs_u32(key_lo, index) then gg_sort_pairs_u32(gg_gather_u32(key_hi, order), order), 32 bits each.
+ *   gg_digitize_f64:  out[i] = #{j : bins[j] <= x[i]} - 1 for ascending bins (= np.digitize(x, bins) - 1). */
+int gg_f64_sort_keys(const double* x, int64_t n, uint32_t* key_hi, uint32_t* key_lo, uint32_t* index, gg_stream_t stream);
+int gg_gather_u32(const uint32_t* src, const uint32_t* index, int64_t n, uint32_t* dst, gg_stream_t stream);
+int gg_digitize_f64(const double* x, int64_t n, const double* bins, int num_bins, int64_t* out, gg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Fused layer post-ops (csrc/postops.cu) — what GeneralLayer / GNNStackStage apply after the
  * message-passing layer (ref: graphgym/models/layer.py:26-46, graphgym/models/gnn.py:76-81):
  *   a = BatchNorm1d(y)   (mean / invstd null: no BN; gamma / beta null: no affine)

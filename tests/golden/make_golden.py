@@ -14,6 +14,7 @@ oracle/pyg_shim.py), feeds them seeded inputs and stores inputs, parameters, out
     identity.npz        compute_identity on K3 / P3 / C4 and two bundled fixture graphs
     egonets.npz         ego_nets (canonicalised: member sets + induced edge sets per centre) on C4 and
                         on bundled fixture graphs, radius 1..3
+    contrib_layers.npz  generalconv (3 self_msg modes x agg x normalize_adj), sageinitconv, idconv(normalize_adj, mean), fwd + bwd
     scalefree16.npz     the Cfg-A workload: graphs [0:16] of datasets/scalefree.pkl as one block-diagonal
                         batch (edge lists, node offsets), the reference label of the node task — nx.clustering
                         (feature_augment.py:81-82) — its 10-way balanced binning restated from feature_augment.py:208-231
@@ -227,6 +228,51 @@ def egonets(ns):
     print('egonets.npz', len(out), 'arrays')
 
 
+def contrib_layers(ns):
+    """generalconv (GeneralConvLayer, ref: contrib/layer/generalconv.py:12-113), sageinitconv (sageinitconv.py:12-115) and
+    idconv with normalize_adj + agg='mean', run through the reference's own files."""
+    root = os.path.join(REF, 'graphgym')
+    gen = pyg_shim._load('graphgym.contrib.layer.generalconv', os.path.join(root, 'contrib/layer/generalconv.py'))
+    pyg_shim._load('graphgym.contrib.layer.sageinitconv', os.path.join(root, 'contrib/layer/sageinitconv.py'))
+
+    class GeneralConv(torch.nn.Module):           # ref: graphgym/models/layer.py:188-196 (imports pyg at module level)
+        def __init__(self, dim_in, dim_out, bias=False, **kwargs):
+            super().__init__()
+            self.model = gen.GeneralConvLayer(dim_in, dim_out, bias=bias)
+
+        def forward(self, batch):
+            batch.node_feature = self.model(batch.node_feature, batch.edge_index)
+            return batch
+    ns.register.layer_dict['generalconv'] = GeneralConv
+    out, tags = {}, []
+    for self_msg in ('none', 'add', 'concat'):
+        for kw in ({}, {'agg': 'mean'}, {'normalize_adj': True}, {'agg': 'mean', 'normalize_adj': True}):
+            ns.cfg.gnn.self_msg = self_msg
+            tags.append(run_layer(ns, 'generalconv', kw, n=41, fin=12, fout=16, seed=500 + len(tags), out=out,
+                                  suffix='_selfmsg-' + self_msg))
+    tags.append(run_layer(ns, 'sageinitconv', {}, n=53, fin=20, fout=24, seed=600, out=out))
+    tags.append(run_layer(ns, 'idconv', {'agg': 'mean', 'normalize_adj': True}, n=37, fin=12, fout=16, seed=601, out=out))
+    out['tags'] = np.array(tags)
+    np.savez_compressed(os.path.join(HERE, 'contrib_layers.npz'), **out)
+    print('contrib_layers.npz', len(tags), 'cases')
+
+
+def driver_cfg():
+    """The keys of the reference's config/idgcn_tf/idgcn_node_scalefree.yaml the main_zd-style driver reads, re-emitted as
+    a fixture (the reference tree is absent at test time)."""
+    import yaml
+    with open(os.path.join(REF, 'config/idgcn_tf/idgcn_node_scalefree.yaml')) as f:
+        c = yaml.safe_load(f)
+    keep = {'dataset': ['name', 'task', 'task_type', 'split', 'augment_feature', 'augment_feature_dims', 'augment_feature_repr',
+                        'augment_label', 'augment_label_dims', 'transform'],
+            'train': ['batch_size'], 'gnn': None, 'optim': ['optimizer', 'base_lr']}
+    out = {sec: {k: v for k, v in c[sec].items() if keys is None or k in keys} for sec, keys in keep.items()}
+    with open(os.path.join(HERE, 'idgcn_node_scalefree.yaml'), 'w') as f:
+        f.write('# derived from the reference's config/idgcn_tf/idgcn_node_scalefree.yaml by tests/golden/make_golden.py\n')
+        yaml.safe_dump(out, f, sort_keys=True)
+    print('idgcn_node_scalefree.yaml', out['gnn'])
+
+
 def scalefree16(ns):
     graphs = fixture_graphs('scalefree', range(16))
     out, eis, ptr, clus, ego_nodes, ego_edges = {}, [], [0], [], [], []
@@ -259,11 +305,13 @@ def scalefree16(ns):
 
 if __name__ == '__main__':
     ns = pyg_shim.install(REF)
-    if len(sys.argv) > 1 and sys.argv[1] == 'scalefree16':
-        scalefree16(ns)
+    if len(sys.argv) > 1 and sys.argv[1] in ('scalefree16', 'contrib_layers'):
+        {'scalefree16': scalefree16, 'contrib_layers': contrib_layers}[sys.argv[1]](ns)
         sys.exit(0)
     layers(ns)
     identity(ns)
     egonets(ns)
     pooling(ns)
     scalefree16(ns)
+    contrib_layers(ns)
+    driver_cfg()

@@ -67,3 +67,28 @@ def test_preprocess_concat_columns(cuda):
     out = pre(batch)
     assert out is batch and torch.equal(batch.node_feature, want)
     reset_cfg()
+
+
+def test_balanced_binning_matches_reference_numpy(cuda, golden_dir):
+    """Cfg-A labels: clustering coefficient (cycle kernel) -> balanced 10-way bins == the numpy pipeline of
+    feature_augment.py:134-143,219-231 run by tests/golden/make_golden.py over graphs [0:16] of scalefree.pkl."""
+    import os
+    import numpy as np
+    from graphgym_b200.contrib.transform import binning
+    from graphgym_b200.contrib.transform.clustering import clustering_coefficient
+    d = np.load(os.path.join(golden_dir, 'scalefree16.npz'))
+    ei = torch.from_numpy(d['edge_index']).to(cuda)
+    gp = torch.from_numpy(d['graph_ptr']).to(cuda)
+    n = int(d['graph_ptr'][-1])
+    clus = clustering_coefficient(ei, n, graph_ptr=gp.int())
+    assert np.abs(clus.cpu().numpy() - d['clustering']).max() < 1e-12
+    labels, edges = binning.balanced_labels(torch.from_numpy(d['clustering']).to(cuda), 10)
+    assert np.array_equal(edges, d['bin_edges'])
+    assert np.array_equal(labels.cpu().numpy(), d['label'])
+    # float64 argsort: stable ascending, incl. negative values, zeros and ties
+    g = torch.Generator().manual_seed(0)
+    v = torch.cat([torch.randn(5000, generator=g, dtype=torch.float64), torch.zeros(100, dtype=torch.float64),
+                   -torch.zeros(3, dtype=torch.float64), torch.randn(50, generator=g, dtype=torch.float64).repeat(20)])
+    order = binning.argsort_f64(v.to(cuda)).cpu().long()
+    want = torch.from_numpy(np.argsort(np.where(v.numpy() == 0, 0.0, v.numpy()), kind='stable'))
+    assert torch.equal(v[order], v[want])

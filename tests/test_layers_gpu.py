@@ -283,3 +283,33 @@ def test_bf16_gather_mode_layers(cuda):
             tol = 1e-1 if (name == 'ginconv' and i > 0) else 1e-2
             assert rel_err(a, b) < tol, (name, i)
         assert any(not torch.equal(a, b) for a, b in zip(res['bf16'], res['f32'])), 'bf16 mode did not engage'
+
+
+def test_golden_reference_contrib_layers(cuda, golden_dir):
+    """generalconv (self_msg none / add / concat x agg x normalize_adj), sageinitconv and idconv(normalize_adj, mean) against
+    vectors produced by the reference's OWN contrib/layer/generalconv.py, sageinitconv.py and idconv.py."""
+    d = np.load(os.path.join(golden_dir, 'contrib_layers.npz'))
+    checked = 0
+    for tag in [str(t) for t in d['tags']]:
+        name = tag.split('_')[0]
+        reset_cfg()
+        cfg.gnn.agg = 'mean' if 'agg-mean' in tag else 'add'
+        cfg.gnn.normalize_adj = 'normalize_adj-True' in tag
+        if '_selfmsg-' in tag:
+            cfg.gnn.self_msg = tag.split('_selfmsg-')[1]
+        x = torch.from_numpy(d[tag + '/x'])
+        ei = torch.from_numpy(d[tag + '/edge_index'])
+        ids = torch.from_numpy(d[tag + '/ids'])
+        layer = layer_dict[name](x.size(1), d[tag + '/y'].shape[1], bias=True)
+        params = {k.split('/param/')[1]: torch.from_numpy(d[k]) for k in d.files if k.startswith(tag + '/param/')}
+        missing, unexpected = layer.load_state_dict(params, strict=False)
+        assert not unexpected and not missing, (tag, missing, unexpected)
+        y, gx, grads = run_ours(layer, x, ei, ids, torch.from_numpy(d[tag + '/gy']), cuda)
+        assert rel_err(y, d[tag + '/y']) < FP32_TOL, tag
+        assert np.allclose(y.numpy(), d[tag + '/y'], rtol=1e-4, atol=1e-5), tag      # element-wise as well
+        assert rel_err(gx, d[tag + '/gx']) < FP32_TOL, tag
+        for k, g in grads.items():
+            assert rel_err(g, d[tag + '/grad/' + k]) < FP32_TOL, (tag, k)
+        checked += 1
+    reset_cfg()
+    assert checked == 14

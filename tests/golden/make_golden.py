@@ -268,7 +268,7 @@ def driver_cfg():
             'train': ['batch_size'], 'gnn': None, 'optim': ['optimizer', 'base_lr']}
     out = {sec: {k: v for k, v in c[sec].items() if keys is None or k in keys} for sec, keys in keep.items()}
     with open(os.path.join(HERE, 'idgcn_node_scalefree.yaml'), 'w') as f:
-        f.write('# derived from the reference's config/idgcn_tf/idgcn_node_scalefree.yaml by tests/golden/make_golden.py\n')
+        f.write('# derived from the reference config file config/idgcn_tf/idgcn_node_scalefree.yaml by tests/golden/make_golden.py\n')
         yaml.safe_dump(out, f, sort_keys=True)
     print('idgcn_node_scalefree.yaml', out['gnn'])
 

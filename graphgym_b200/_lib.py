@@ -83,6 +83,8 @@ SIGNATURES = {
     "gg_peer_free": (c_int, [c_ptr]),
     "gg_peer_barrier": (c_int, [ctypes.POINTER(c_ptr), c_int, c_int, c_ptr]),
     "gg_peer_scatter_cols_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, ctypes.POINTER(c_ptr), c_int, c_i64, c_ptr]),
+    "gg_peer_push_rows_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_int, c_int, ctypes.POINTER(c_ptr), c_ptr]),
+    "gg_peer_gather_slices_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_int, c_ptr, c_i64, c_ptr]),
     "gg_id_gemm_f32": (c_int, [ctypes.POINTER(GemmSegment), c_int, c_int, c_i64, c_i64, c_ptr, c_int,
                                c_ptr, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_id_gemm_tc_workspace_bytes": (c_size, [ctypes.POINTER(GemmSegment), c_int, c_i64]),
@@ -139,6 +141,16 @@ SIGNATURES = {
                                    c_i64, c_ptr, c_ptr]),
     "gg_postops_bwd_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_int,
                                    c_int, c_f32, c_int, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "gg_gat_sell_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "gg_sell_compose_map": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    "gg_gat_sell_fwd_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr,
+                                    c_i64, c_i64, c_f32, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_size, c_ptr]),
+    "gg_gat_sell_bwd_edge_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64,
+                                         c_ptr, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32,
+                                         c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
+    "gg_gat_sell_bwd_src_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64,
+                                        c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_f32, c_ptr, c_i64,
+                                        c_ptr, c_ptr, c_ptr, c_size, c_ptr]),
     "gg_gather_rows_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_scatter_add_rows_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr]),
     "gg_relu_grad_f32": (c_int, [c_ptr, c_i64, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr]),

@@ -1,0 +1,552 @@
+// GAT (heads = 1) fused into the sliced-ELL aggregation (ref: GATIDConvLayer.message / update,
+// graphgym/contrib/layer/idconv.py:317-342; PyG softmax: exp(z - max) / (sum + 1e-16)).
+//
+// gat_mp.cu materialises alpha: gat_alpha (E' floats out) -> SpMM (alpha in) -> SDDMM (dalpha out) -> gat_dz (alpha,
+// dalpha in, dz out) -> gat_csc_gather (alpha, dz gathered through the slot map, alpha_T out) -> SpMM (alpha_T in):
+// 20.0 ms per step on the products graph against 11.0 for GCN (profiles/r01_bench_products_gat.json).  Here the edge
+// softmax lives inside the three heavy passes and alpha never touches memory:
+//   forward      gat_sell_fwd       one walk over the CSR sliced-ELL layout: logits from the per-node halves, ONLINE softmax
+//                                   (running max / sum, accumulator rescaled when the max grows) fused with the weighted
+//                                   aggregation; saves (max, sum) per row — 8 bytes per node instead of 4 per edge
+//   backward     gat_sell_bwd_edge  same layout: dalpha = <g_i, h_j> (4 slots reduced across the row's lanes by one
+//                                   multi-value butterfly), alpha recomputed from (max, sum), D_i = <g_i, out_i - b>
+//                                   (= sum_e alpha_e dalpha_e), dz written once in CSR slot order, da_tgt per row
+//                gat_sell_bwd_src   CSC sliced-ELL layout: alpha recomputed per slot from a 16-byte per-target record
+//                                   (a_tgt, max, 1/sum: a 39 MB array, L2 resident), dH_j = sum alpha g_i + rank-1 terms,
+//                                   da_src_j = sum dz gathered through a precomposed slot map
+// Rows cut into virtual rows (layout `seg`) carry (max, sum, partial accumulator) / partial sums to small fix-up kernels.
+// Every row is walked by one group of lanes in slot order: deterministic.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace gg {
+
+constexpr int kGsRows = 8;        // virtual rows per chunk (= spmm_sell.cu)
+constexpr int kGsThreads = 256;
+constexpr int32_t kGsNoRow = INT32_MIN;
+
+struct GatSellArgs {
+    // layout (CSR for fwd / bwd_edge, CSC for bwd_src)
+    const uint32_t* chunk_ptr;
+    int chunks;
+    const int4* idx4;
+    const int4* slot4;       // bwd_edge: CSR slot of every entry; bwd_src: CSR slot of the same edge (composed map)
+    const int32_t* vdst;
+    const int32_t* hub_rows;
+    const int32_t* hub_pptr;
+    int hubs;
+    int64_t n;
+    int f;
+    float slope;
+    // operands
+    const float* h;          // fwd / bwd_edge: gathered rows; bwd_src: g
+    int64_t ldh;
+    const float* g;          // bwd_edge: gradient rows of the targets
+    int64_t ldg;
+    const float* fout;       // bwd_edge: forward output (for D_i)
+    int64_t ldfo;
+    const float* a_tgt;
+    const float* a_src;
+    const float* bias;
+    float2* rowstat;         // [n] (max, sum)
+    const float4* tstat;     // bwd_src: [n] (a_tgt, max, 1 / (sum + 1e-16), 0)
+    const float* dz_in;      // bwd_src
+    const float* da_tgt_in;  // bwd_src: complete da_tgt
+    const float* att_src;    // bwd_src: [f]
+    const float* att_tgt;
+    float* out;              // fwd: out; bwd_src: dh
+    int64_t ldo;
+    float* dz;               // bwd_edge out (CSR slot order)
+    float* da;               // bwd_edge: da_tgt; bwd_src: da_src
+    // split rows
+    float* pacc;             // [partial rows, f]
+    float2* pstat;           // [partial rows]: fwd (max, sum); bwd: (sum, -)
+    int* counter;
+};
+
+__device__ __forceinline__ float gs_leaky(float z, float slope) { return z > 0.f ? z : slope * z; }
+// exp(e - m) with the conventions of a running softmax: a masked slot (e = -inf) weighs 0 even while m is still -inf
+__device__ __forceinline__ float gs_p(float e, float m) { return e == -CUDART_INF_F ? 0.f : expf(e - m); }
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ int4 gs_ldg_i4(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// the row a virtual row belongs to: itself, or (piece of a split row) the hub whose partial range holds the piece
+__device__ __forceinline__ int gs_row_of(const GatSellArgs& a, int d) {
+    if (d >= 0 || d == kGsNoRow) return d;
+    const int p = -d - 1;
+    int lo = 0, hi = a.hubs - 1;   // last h with hub_pptr[h] <= p
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(a.hub_pptr + mid) <= p) lo = mid;
+        else hi = mid - 1;
+    }
+    return __ldg(a.hub_rows + lo);
+}
+
+template <int G>
+__device__ __forceinline__ float gs_group_sum(float v) {
+#pragma unroll
+    for (int m = G / 2; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+// Four per-lane partial sums -> every lane ends with the complete sum (over its group of G lanes) of ONE of them:
+// value kcls = 2 * bit(G/2) + bit(G/4) of its lane id.  log2(G) + 1 shuffles instead of 4 log2(G).
+template <int G>
+__device__ __forceinline__ float gs_reduce4(float p0, float p1, float p2, float p3, int gl) {
+    const bool up = (gl & (G / 2)) != 0;
+    const float s0 = up ? p0 : p2, s1 = up ? p1 : p3;          // what the partner keeps
+    float q0 = (up ? p2 : p0) + __shfl_xor_sync(0xffffffffu, s0, G / 2);
+    float q1 = (up ? p3 : p1) + __shfl_xor_sync(0xffffffffu, s1, G / 2);
+    const bool up2 = (gl & (G / 4)) != 0;
+    float r = (up2 ? q1 : q0) + __shfl_xor_sync(0xffffffffu, up2 ? q0 : q1, G / 4);
+#pragma unroll
+    for (int m = G / 8; m > 0; m >>= 1) r += __shfl_xor_sync(0xffffffffu, r, m);
+    return r;
+}
+__device__ __forceinline__ int gs_pick(const int4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+
+// ---- forward -------------------------------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(kGsThreads, 3) gat_sell_fwd_kernel(const __grid_constant__ GatSellArgs a) {
+    constexpr int S = 32 / G, P = kGsRows / S;
+    const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
+    const int nvec = a.f >> 2;
+    const bool act = gl < nvec;
+    const char* __restrict__ xg = reinterpret_cast<const char*>(a.h) + (act ? gl : nvec - 1) * 16;
+    uint32_t row_bytes = (uint32_t)a.ldh * 4u;
+    asm volatile("" : "+l"(xg), "+r"(row_bytes));
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto gather = [&](int j) {
+        float4 v = zero4;
+        if (j >= 0) v = ldg_nc_f4(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)j * row_bytes));
+        return v;
+    };
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(a.counter, 1);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    while (chunk < a.chunks) {
+        int next = 0;
+        if (lane == 0) next = atomicAdd(a.counter, 1);
+        const uint32_t base = __ldg(a.chunk_ptr + chunk);
+        const int nk = (int)(__ldg(a.chunk_ptr + chunk + 1) - base) / kGsRows;   // 4-slot units per row
+        for (int p = 0; p < P; ++p) {
+            const int q = p * S + grp;
+            const int d = __ldg(a.vdst + (int64_t)chunk * kGsRows + q);
+            const int row = gs_row_of(a, d);
+            const float at = row >= 0 ? __ldg(a.a_tgt + row) : 0.f;
+            const int4* __restrict__ ip = a.idx4 + base + q;
+            float m = -CUDART_INF_F, s = 0.f;
+            float4 acc = zero4;
+            for (int k4 = 0; k4 < nk; k4 += 2) {
+                const int4 ia = gs_ldg_i4(ip + (int64_t)k4 * kGsRows);
+                const int4 ib = k4 + 1 < nk ? gs_ldg_i4(ip + (int64_t)(k4 + 1) * kGsRows) : make_int4(-1, -1, -1, -1);
+                const float4 v0 = gather(ia.x), v1 = gather(ia.y), v2 = gather(ia.z), v3 = gather(ia.w);
+                const float4 v4 = gather(ib.x), v5 = gather(ib.y), v6 = gather(ib.z), v7 = gather(ib.w);
+                auto logit = [&](int j) { return j >= 0 ? gs_leaky(at + __ldg(a.a_src + j), a.slope) : -CUDART_INF_F; };
+                const float e0 = logit(ia.x), e1 = logit(ia.y), e2 = logit(ia.z), e3 = logit(ia.w);
+                const float e4 = logit(ib.x), e5 = logit(ib.y), e6 = logit(ib.z), e7 = logit(ib.w);
+                const float mn = fmaxf(fmaxf(fmaxf(fmaxf(e0, e1), fmaxf(e2, e3)), fmaxf(fmaxf(e4, e5), fmaxf(e6, e7))), m);
+                const float sc = m == mn ? 1.f : gs_p(m, mn);     // m = -inf (first slots of the row): 0
+                const float p0 = gs_p(e0, mn), p1 = gs_p(e1, mn), p2 = gs_p(e2, mn), p3 = gs_p(e3, mn);
+                const float p4 = gs_p(e4, mn), p5 = gs_p(e5, mn), p6 = gs_p(e6, mn), p7 = gs_p(e7, mn);
+                acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+                fma4(acc, p0, v0); fma4(acc, p1, v1); fma4(acc, p2, v2); fma4(acc, p3, v3);
+                fma4(acc, p4, v4); fma4(acc, p5, v5); fma4(acc, p6, v6); fma4(acc, p7, v7);
+                s = fmaf(s, sc, ((p0 + p1) + (p2 + p3)) + ((p4 + p5) + (p6 + p7)));
+                m = mn;
+            }
+            if (d >= 0) {
+                const float inv = 1.0f / (s + 1e-16f);
+                if (act) {
+                    float4 r = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+                    if (a.bias) add4(r, __ldg(reinterpret_cast<const float4*>(a.bias) + gl));
+                    reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[gl] = r;
+                }
+                if (gl == 0) a.rowstat[row] = make_float2(m, s);
+            } else if (d != kGsNoRow) {
+                const int pr = -d - 1;
+                if (act) reinterpret_cast<float4*>(a.pacc + (int64_t)pr * a.f)[gl] = acc;
+                if (gl == 0) a.pstat[pr] = make_float2(m, s);
+            }
+        }
+        chunk = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+// split rows: merge the pieces' (max, sum, accumulator) in piece order
+__global__ void __launch_bounds__(256) gat_sell_fwd_fixup_kernel(const __grid_constant__ GatSellArgs a) {
+    const int nvec = a.f >> 2;
+    const int64_t total = (int64_t)a.hubs * nvec;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int hb = (int)(e / nvec), gl = (int)(e - (int64_t)hb * nvec);
+        const int p0 = __ldg(a.hub_pptr + hb), p1 = __ldg(a.hub_pptr + hb + 1);
+        float M = -CUDART_INF_F;
+        for (int p = p0; p < p1; ++p) M = fmaxf(M, a.pstat[p].x);
+        float S = 0.f;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = p0; p < p1; ++p) {
+            const float2 st = a.pstat[p];
+            const float w = gs_p(st.x, M);
+            S = fmaf(st.y, w, S);
+            fma4(r, w, reinterpret_cast<const float4*>(a.pacc + (int64_t)p * a.f)[gl]);
+        }
+        const float inv = 1.0f / (S + 1e-16f);
+        r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
+        if (a.bias) add4(r, __ldg(reinterpret_cast<const float4*>(a.bias) + gl));
+        const int row = __ldg(a.hub_rows + hb);
+        reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[gl] = r;
+        if (gl == 0) a.rowstat[row] = make_float2(M, S);
+    }
+}
+
+// ---- backward, edge side (CSR layout) ------------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(kGsThreads, 3) gat_sell_bwd_edge_kernel(const __grid_constant__ GatSellArgs a) {
+    constexpr int S = 32 / G, P = kGsRows / S;
+    const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
+    const int nvec = a.f >> 2;
+    const bool act = gl < nvec;
+    const char* __restrict__ xg = reinterpret_cast<const char*>(a.h) + (act ? gl : nvec - 1) * 16;
+    uint32_t row_bytes = (uint32_t)a.ldh * 4u;
+    asm volatile("" : "+l"(xg), "+r"(row_bytes));
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto gather = [&](int j) {
+        float4 v = zero4;
+        if (j >= 0) v = ldg_nc_f4(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)j * row_bytes));
+        return v;
+    };
+    const int kcls = ((gl & (G / 2)) ? 2 : 0) + ((gl & (G / 4)) ? 1 : 0);   // the slot of a unit this lane finishes
+    const bool writer = (gl & (G / 4 - 1)) == 0;                           // one lane per class and group
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(a.counter, 1);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    while (chunk < a.chunks) {
+        int next = 0;
+        if (lane == 0) next = atomicAdd(a.counter, 1);
+        const uint32_t base = __ldg(a.chunk_ptr + chunk);
+        const int nk = (int)(__ldg(a.chunk_ptr + chunk + 1) - base) / kGsRows;
+        for (int p = 0; p < P; ++p) {
+            const int q = p * S + grp;
+            const int d = __ldg(a.vdst + (int64_t)chunk * kGsRows + q);
+            const int row = gs_row_of(a, d);
+            const bool live = row >= 0;
+            const float at = live ? __ldg(a.a_tgt + row) : 0.f;
+            const float2 st = live ? a.rowstat[row] : make_float2(0.f, 1.f);
+            const float inv = 1.0f / (st.y + 1e-16f);
+            float4 gi = zero4;
+            float dpart = 0.f;
+            if (live && act) {
+                gi = __ldg(reinterpret_cast<const float4*>(a.g + (int64_t)row * a.ldg) + gl);
+                float4 o = __ldg(reinterpret_cast<const float4*>(a.fout + (int64_t)row * a.ldfo) + gl);
+                if (a.bias) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias) + gl);
+                    o.x -= b.x; o.y -= b.y; o.z -= b.z; o.w -= b.w;
+                }
+                dpart = dot4(gi, o);
+            }
+            const float D = gs_group_sum<G>(dpart);    // = sum_e alpha_e dalpha_e of the WHOLE row
+            const int4* __restrict__ ip = a.idx4 + base + q;
+            const int4* __restrict__ sp = a.slot4 + base + q;
+            float dsum = 0.f;
+            for (int k4 = 0; k4 < nk; k4 += 2) {
+                const int4 ia = gs_ldg_i4(ip + (int64_t)k4 * kGsRows);
+                const bool two = k4 + 1 < nk;
+                const int4 ib = two ? gs_ldg_i4(ip + (int64_t)(k4 + 1) * kGsRows) : make_int4(-1, -1, -1, -1);
+                const float4 v0 = gather(ia.x), v1 = gather(ia.y), v2 = gather(ia.z), v3 = gather(ia.w);
+                const float4 v4 = gather(ib.x), v5 = gather(ib.y), v6 = gather(ib.z), v7 = gather(ib.w);
+                const float da0 = gs_reduce4<G>(dot4(gi, v0), dot4(gi, v1), dot4(gi, v2), dot4(gi, v3), gl);
+                const float da1 = gs_reduce4<G>(dot4(gi, v4), dot4(gi, v5), dot4(gi, v6), dot4(gi, v7), gl);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int j = gs_pick(u ? ib : ia, kcls);
+                    if (writer && j >= 0) {
+                        const float z = at + __ldg(a.a_src + j);
+                        const float alpha = expf(gs_leaky(z, a.slope) - st.x) * inv;
+                        const float v = alpha * ((u ? da1 : da0) - D) * (z > 0.f ? 1.f : a.slope);
+                        const int4 so = gs_ldg_i4(sp + (int64_t)(k4 + u) * kGsRows);
+                        a.dz[gs_pick(so, kcls)] = v;
+                        dsum += v;
+                    }
+                }
+            }
+            const float da = gs_group_sum<G>(dsum);
+            if (gl == 0) {
+                if (d >= 0) a.da[row] = da;
+                else if (d != kGsNoRow) a.pstat[-d - 1] = make_float2(da, 0.f);
+            }
+        }
+        chunk = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) gat_sell_bwd_edge_fixup_kernel(const __grid_constant__ GatSellArgs a) {
+    for (int hb = blockIdx.x * blockDim.x + threadIdx.x; hb < a.hubs; hb += gridDim.x * blockDim.x) {
+        const int p0 = __ldg(a.hub_pptr + hb), p1 = __ldg(a.hub_pptr + hb + 1);
+        float s = 0.f;
+        for (int p = p0; p < p1; ++p) s += a.pstat[p].x;
+        a.da[__ldg(a.hub_rows + hb)] = s;
+    }
+}
+
+// ---- backward, source side (CSC layout) ----------------------------------------------------------------------------
+template <int G>
+__global__ void __launch_bounds__(kGsThreads, 3) gat_sell_bwd_src_kernel(const __grid_constant__ GatSellArgs a) {
+    constexpr int S = 32 / G, P = kGsRows / S;
+    const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
+    const int nvec = a.f >> 2;
+    const bool act = gl < nvec;
+    const char* __restrict__ xg = reinterpret_cast<const char*>(a.h) + (act ? gl : nvec - 1) * 16;   // a.h = g here
+    uint32_t row_bytes = (uint32_t)a.ldh * 4u;
+    asm volatile("" : "+l"(xg), "+r"(row_bytes));
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto gather = [&](int j) {
+        float4 v = zero4;
+        if (j >= 0) v = ldg_nc_f4(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)j * row_bytes));
+        return v;
+    };
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(a.counter, 1);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    while (chunk < a.chunks) {
+        int next = 0;
+        if (lane == 0) next = atomicAdd(a.counter, 1);
+        const uint32_t base = __ldg(a.chunk_ptr + chunk);
+        const int nk = (int)(__ldg(a.chunk_ptr + chunk + 1) - base) / kGsRows;
+        for (int p = 0; p < P; ++p) {
+            const int q = p * S + grp;
+            const int d = __ldg(a.vdst + (int64_t)chunk * kGsRows + q);
+            const int row = gs_row_of(a, d);
+            const float as = row >= 0 ? __ldg(a.a_src + row) : 0.f;
+            const int4* __restrict__ ip = a.idx4 + base + q;
+            const int4* __restrict__ mp = a.slot4 + base + q;
+            float4 acc = zero4;
+            float dsum = 0.f;
+            for (int k4 = 0; k4 < nk; k4 += 2) {
+                const int4 ia = gs_ldg_i4(ip + (int64_t)k4 * kGsRows);
+                const bool two = k4 + 1 < nk;
+                const int4 ib = two ? gs_ldg_i4(ip + (int64_t)(k4 + 1) * kGsRows) : make_int4(-1, -1, -1, -1);
+                const int4 ma = gs_ldg_i4(mp + (int64_t)k4 * kGsRows);
+                const int4 mb = two ? gs_ldg_i4(mp + (int64_t)(k4 + 1) * kGsRows) : make_int4(-1, -1, -1, -1);
+                const float4 v0 = gather(ia.x), v1 = gather(ia.y), v2 = gather(ia.z), v3 = gather(ia.w);
+                const float4 v4 = gather(ib.x), v5 = gather(ib.y), v6 = gather(ib.z), v7 = gather(ib.w);
+                auto wgt = [&](int i) {      // alpha of the edge (source = this row, target = i), recomputed
+                    if (i < 0) return 0.f;
+                    const float4 t = __ldg(a.tstat + i);
+                    return expf(gs_leaky(t.x + as, a.slope) - t.y) * t.z;
+                };
+                auto dzv = [&](int s) { return s >= 0 ? __ldg(a.dz_in + s) : 0.f; };
+                fma4(acc, wgt(ia.x), v0); fma4(acc, wgt(ia.y), v1); fma4(acc, wgt(ia.z), v2); fma4(acc, wgt(ia.w), v3);
+                fma4(acc, wgt(ib.x), v4); fma4(acc, wgt(ib.y), v5); fma4(acc, wgt(ib.z), v6); fma4(acc, wgt(ib.w), v7);
+                dsum += ((dzv(ma.x) + dzv(ma.y)) + (dzv(ma.z) + dzv(ma.w))) + ((dzv(mb.x) + dzv(mb.y)) + (dzv(mb.z) + dzv(mb.w)));
+            }
+            if (d >= 0) {
+                if (act) {   // dH_j = sum alpha g_i + da_src_j att_src + da_tgt_j att_tgt
+                    fma4(acc, dsum, __ldg(reinterpret_cast<const float4*>(a.att_src) + gl));
+                    fma4(acc, __ldg(a.da_tgt_in + row), __ldg(reinterpret_cast<const float4*>(a.att_tgt) + gl));
+                    reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[gl] = acc;
+                }
+                if (gl == 0) a.da[row] = dsum;
+            } else if (d != kGsNoRow) {
+                const int pr = -d - 1;
+                if (act) reinterpret_cast<float4*>(a.pacc + (int64_t)pr * a.f)[gl] = acc;
+                if (gl == 0) a.pstat[pr] = make_float2(dsum, 0.f);
+            }
+        }
+        chunk = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) gat_sell_bwd_src_fixup_kernel(const __grid_constant__ GatSellArgs a) {
+    const int nvec = a.f >> 2;
+    const int64_t total = (int64_t)a.hubs * nvec;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int hb = (int)(e / nvec), gl = (int)(e - (int64_t)hb * nvec);
+        const int p0 = __ldg(a.hub_pptr + hb), p1 = __ldg(a.hub_pptr + hb + 1);
+        float dsum = 0.f;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = p0; p < p1; ++p) {
+            dsum += a.pstat[p].x;
+            add4(r, reinterpret_cast<const float4*>(a.pacc + (int64_t)p * a.f)[gl]);
+        }
+        const int row = __ldg(a.hub_rows + hb);
+        fma4(r, dsum, __ldg(reinterpret_cast<const float4*>(a.att_src) + gl));
+        fma4(r, __ldg(a.da_tgt_in + row), __ldg(reinterpret_cast<const float4*>(a.att_tgt) + gl));
+        reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[gl] = r;
+        if (gl == 0) a.da[row] = dsum;
+    }
+}
+
+// per-target record of the source-side pass; composed slot map of the CSC layout
+__global__ void __launch_bounds__(256) gat_tstat_kernel(const float* __restrict__ a_tgt, const float2* __restrict__ rowstat,
+                                                        int64_t n, float4* __restrict__ tstat) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 st = rowstat[i];
+        tstat[i] = make_float4(a_tgt[i], st.x, 1.0f / (st.y + 1e-16f), 0.f);
+    }
+}
+__global__ void __launch_bounds__(256) sell_compose_map_kernel(const int32_t* __restrict__ slot_of, int64_t total,
+                                                               const int32_t* __restrict__ map, int32_t* __restrict__ out) {
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < total; d += (int64_t)gridDim.x * blockDim.x) {
+        const int s = slot_of[d];
+        out[d] = s >= 0 ? map[s] : -1;
+    }
+}
+
+static inline int gs_grid(int64_t total, int per_block) {
+    int64_t b = ceil_div(total, per_block);
+    if (b > (int64_t)kNumSMs * 8) b = (int64_t)kNumSMs * 8;
+    return (int)(b < 1 ? 1 : b);
+}
+static inline int gs_lanes(int64_t f) {
+    if (f <= 0 || f % 4 != 0 || f > 128) return 0;
+    const int nvec = (int)(f / 4);
+    return nvec <= 4 ? 4 : nvec <= 8 ? 8 : nvec <= 16 ? 16 : 32;
+}
+static inline bool gs_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+#define GS_DISPATCH(kernel, g, grid, st, a)                                   \
+    do {                                                                      \
+        if (g == 4) kernel<4><<<grid, kGsThreads, 0, st>>>(a);               \
+        else if (g == 8) kernel<8><<<grid, kGsThreads, 0, st>>>(a);          \
+        else if (g == 16) kernel<16><<<grid, kGsThreads, 0, st>>>(a);        \
+        else kernel<32><<<grid, kGsThreads, 0, st>>>(a);                     \
+    } while (0)
+
+static int gs_main_grid(int64_t chunks) {
+    int grid = (int)ceil_div(chunks, kGsThreads / 32);
+    if (grid > kNumSMs * 3) grid = kNumSMs * 3;
+    return grid < 1 ? 1 : grid;
+}
+
+}  // namespace gg
+
+using namespace gg;
+
+extern "C" {
+
+size_t gg_gat_sell_workspace_bytes(int64_t partial_rows, int64_t f) {
+    const size_t pr = (size_t)(partial_rows > 0 ? partial_rows : 0);
+    return 512 + align_up(pr * (size_t)f * sizeof(float), 256) + align_up(pr * sizeof(float2), 256);
+}
+
+int gg_sell_compose_map(const int32_t* slot_of, int64_t total, const int32_t* map, int32_t* out, gg_stream_t stream) {
+    GG_REQUIRE(total >= 0, "gg_sell_compose_map: negative size");
+    if (total == 0) return GG_OK;
+    GG_REQUIRE(slot_of && map && out, "gg_sell_compose_map: null pointer");
+    sell_compose_map_kernel<<<gs_grid(total, 256 * 4), 256, 0, as_stream(stream)>>>(slot_of, total, map, out);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
+#define GS_COMMON_CHECKS(who)                                                                                          \
+    GG_REQUIRE(n >= 0 && f >= 0 && chunks >= 0 && hubs >= 0 && partial_rows >= 0, who ": negative size");              \
+    if (n == 0 || f == 0) return GG_OK;                                                                                \
+    const int g_lanes = gs_lanes(f);                                                                                   \
+    if (!g_lanes) {                                                                                                    \
+        set_error(who ": needs f %% 4 == 0 and f <= 128 (got %lld)", (long long)f);                                    \
+        return GG_ERR_UNSUPPORTED;                                                                                     \
+    }                                                                                                                  \
+    GG_REQUIRE(chunk_ptr && idx && vdst && workspace && (hubs == 0 || (hub_rows && hub_pptr)), who ": null pointer");  \
+    GG_REQUIRE(chunks < ((int64_t)1 << 31) && n < ((int64_t)1 << 31), who ": sizes out of range");                     \
+    if (workspace_bytes < gg_gat_sell_workspace_bytes(partial_rows, f)) {                                              \
+        set_error(who ": workspace %zu < %zu", workspace_bytes, gg_gat_sell_workspace_bytes(partial_rows, f));          \
+        return GG_ERR_WORKSPACE;                                                                                       \
+    }                                                                                                                  \
+    cudaStream_t st = as_stream(stream);                                                                               \
+    Carver c(workspace);                                                                                               \
+    int* counter = c.take<int>(64);                                                                                    \
+    float* pacc = c.take<float>((size_t)partial_rows * f);                                                             \
+    float2* pstat = c.take<float2>((size_t)partial_rows);                                                              \
+    GG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+
+int gg_gat_sell_fwd_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const int32_t* vdst,
+                        const int32_t* hub_rows, const int32_t* hub_pptr, int64_t hubs, int64_t partial_rows,
+                        const float* h, int64_t ldh, const float* a_tgt, const float* a_src, int64_t n, int64_t f,
+                        float slope, const float* bias, float* out, int64_t ldo, float* rowstat, void* workspace,
+                        size_t workspace_bytes, gg_stream_t stream) {
+    GS_COMMON_CHECKS("gg_gat_sell_fwd_f32")
+    GG_REQUIRE(h && a_tgt && a_src && out && rowstat && ldh >= f && ldh < ((int64_t)1 << 30) && ldh % 4 == 0 &&
+                   ldo % 4 == 0 && gs_al16(h) && gs_al16(out) && gs_al16(idx) && (!bias || gs_al16(bias)) &&
+                   (reinterpret_cast<uintptr_t>(rowstat) & 7) == 0,
+               "gg_gat_sell_fwd_f32: bad operands (rows must be 16-byte aligned)");
+    GatSellArgs a{};
+    a.chunk_ptr = chunk_ptr; a.chunks = (int)chunks; a.idx4 = reinterpret_cast<const int4*>(idx); a.vdst = vdst;
+    a.hub_rows = hub_rows; a.hub_pptr = hub_pptr; a.hubs = (int)hubs; a.n = n; a.f = (int)f; a.slope = slope;
+    a.h = h; a.ldh = ldh; a.a_tgt = a_tgt; a.a_src = a_src; a.bias = bias; a.out = out; a.ldo = ldo;
+    a.rowstat = reinterpret_cast<float2*>(rowstat); a.pacc = pacc; a.pstat = pstat; a.counter = counter;
+    GS_DISPATCH(gat_sell_fwd_kernel, g_lanes, gs_main_grid(chunks), st, a);
+    GG_LAUNCHED();
+    if (hubs > 0) {
+        gat_sell_fwd_fixup_kernel<<<gs_grid(hubs * (f / 4), 256), 256, 0, st>>>(a);
+        GG_LAUNCHED();
+    }
+    return GG_OK;
+}
+
+int gg_gat_sell_bwd_edge_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const int32_t* slot_of,
+                             const int32_t* vdst, const int32_t* hub_rows, const int32_t* hub_pptr, int64_t hubs,
+                             int64_t partial_rows, const float* h, int64_t ldh, const float* g, int64_t ldg,
+                             const float* fwd_out, int64_t ld_out, const float* bias, const float* a_tgt,
+                             const float* a_src, const float* rowstat, int64_t n, int64_t f, float slope, float* dz,
+                             float* da_tgt, void* workspace, size_t workspace_bytes, gg_stream_t stream) {
+    GS_COMMON_CHECKS("gg_gat_sell_bwd_edge_f32")
+    GG_REQUIRE(h && g && fwd_out && a_tgt && a_src && rowstat && dz && da_tgt && slot_of && ldh >= f &&
+                   ldh < ((int64_t)1 << 30) && ldh % 4 == 0 && ldg % 4 == 0 && ld_out % 4 == 0 && gs_al16(h) && gs_al16(g) &&
+                   gs_al16(fwd_out) && gs_al16(idx) && gs_al16(slot_of) && (!bias || gs_al16(bias)),
+               "gg_gat_sell_bwd_edge_f32: bad operands (rows must be 16-byte aligned)");
+    GatSellArgs a{};
+    a.chunk_ptr = chunk_ptr; a.chunks = (int)chunks; a.idx4 = reinterpret_cast<const int4*>(idx);
+    a.slot4 = reinterpret_cast<const int4*>(slot_of); a.vdst = vdst; a.hub_rows = hub_rows; a.hub_pptr = hub_pptr;
+    a.hubs = (int)hubs; a.n = n; a.f = (int)f; a.slope = slope; a.h = h; a.ldh = ldh; a.g = g; a.ldg = ldg;
+    a.fout = fwd_out; a.ldfo = ld_out; a.bias = bias; a.a_tgt = a_tgt; a.a_src = a_src;
+    a.rowstat = reinterpret_cast<float2*>(const_cast<float*>(rowstat)); a.dz = dz; a.da = da_tgt; a.pacc = pacc;
+    a.pstat = pstat; a.counter = counter;
+    GS_DISPATCH(gat_sell_bwd_edge_kernel, g_lanes, gs_main_grid(chunks), st, a);
+    GG_LAUNCHED();
+    if (hubs > 0) {
+        gat_sell_bwd_edge_fixup_kernel<<<gs_grid(hubs, 256), 256, 0, st>>>(a);
+        GG_LAUNCHED();
+    }
+    return GG_OK;
+}
+
+int gg_gat_sell_bwd_src_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const int32_t* edge_map,
+                            const int32_t* vdst, const int32_t* hub_rows, const int32_t* hub_pptr, int64_t hubs,
+                            int64_t partial_rows, const float* g, int64_t ldg, const float* a_tgt, const float* a_src,
+                            const float* rowstat, const float* dz, const float* da_tgt, const float* att_src,
+                            const float* att_tgt, int64_t n, int64_t f, float slope, float* dh, int64_t ld_dh,
+                            float* da_src, float* tstat_scratch, void* workspace, size_t workspace_bytes,
+                            gg_stream_t stream) {
+    GS_COMMON_CHECKS("gg_gat_sell_bwd_src_f32")
+    GG_REQUIRE(g && a_tgt && a_src && rowstat && dz && da_tgt && att_src && att_tgt && dh && da_src && tstat_scratch &&
+                   edge_map && ldg >= f && ldg < ((int64_t)1 << 30) && ldg % 4 == 0 && ld_dh % 4 == 0 && gs_al16(g) &&
+                   gs_al16(dh) && gs_al16(idx) && gs_al16(edge_map) && gs_al16(att_src) && gs_al16(att_tgt) &&
+                   gs_al16(tstat_scratch),
+               "gg_gat_sell_bwd_src_f32: bad operands (rows must be 16-byte aligned)");
+    gat_tstat_kernel<<<gs_grid(n, 256), 256, 0, st>>>(a_tgt, reinterpret_cast<const float2*>(rowstat), n,
+                                                      reinterpret_cast<float4*>(tstat_scratch));
+    GG_LAUNCHED();
+    GatSellArgs a{};
+    a.chunk_ptr = chunk_ptr; a.chunks = (int)chunks; a.idx4 = reinterpret_cast<const int4*>(idx);
+    a.slot4 = reinterpret_cast<const int4*>(edge_map); a.vdst = vdst; a.hub_rows = hub_rows; a.hub_pptr = hub_pptr;
+    a.hubs = (int)hubs; a.n = n; a.f = (int)f; a.slope = slope; a.h = g; a.ldh = ldg; a.a_src = a_src;
+    a.tstat = reinterpret_cast<const float4*>(tstat_scratch); a.dz_in = dz; a.da_tgt_in = da_tgt; a.att_src = att_src;
+    a.att_tgt = att_tgt; a.out = dh; a.ldo = ld_dh; a.da = da_src; a.pacc = pacc; a.pstat = pstat; a.counter = counter;
+    GS_DISPATCH(gat_sell_bwd_src_kernel, g_lanes, gs_main_grid(chunks), st, a);
+    GG_LAUNCHED();
+    if (hubs > 0) {
+        gat_sell_bwd_src_fixup_kernel<<<gs_grid(hubs * (f / 4), 256), 256, 0, st>>>(a);
+        GG_LAUNCHED();
+    }
+    return GG_OK;
+}
+
+}  // extern "C"

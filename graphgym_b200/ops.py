@@ -591,7 +591,81 @@ def _f32(shape, dev):
     return torch.empty(max(n, 1), dtype=torch.float32, device=dev)[:n].view(*shape)
 
 
-GAT_ALGO = _os.environ.get("GG_GAT_ALGO", "auto")   # auto | mp (split passes on merge-path kernels) | row
+GAT_ALGO = _os.environ.get("GG_GAT_ALGO", "auto")   # auto | sell (fused, sliced ELL) | mp (split passes, merge-path) | row
+
+
+def _gat_use_sell(csr, f, heads):
+    if heads != 1 or f % 4 != 0 or f > 128 or GAT_ALGO in ("row", "mp"):
+        return False
+    return GAT_ALGO == "sell" or csr.num_nodes + csr.num_slots >= 1 << 14
+
+
+def gat_sell_forward(csr, h, ldh, a_tgt, a_src, slope, bias):
+    """-> (out, rowstat [n, 2] = per-row (max, sum of exp)); alpha is never materialised (csrc/gat_sell.cu)."""
+    sl = sell_layout(csr)
+    n, f = h.shape
+    L = lib()
+    out = torch.empty((n, f), dtype=torch.float32, device=h.device)
+    rowstat = torch.empty((max(n, 1), 2), dtype=torch.float32, device=h.device)[:n]
+    ws_bytes = int(L.gg_gat_sell_workspace_bytes(sl.partial_rows, f))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=h.device)
+    if bias is not None:
+        bias = bias.contiguous()
+    check(L.gg_gat_sell_fwd_f32(_ptr(sl.chunk_ptr), sl.chunks, _ptr(sl.idx), _ptr(sl.vdst), _ptr(sl.hub_rows),
+                                _ptr(sl.hub_pptr), sl.hubs, sl.partial_rows, _ptr(h), ldh, _ptr(a_tgt), _ptr(a_src), n, f,
+                                float(slope), _ptr(bias), _ptr(out), f, _ptr(rowstat), _ptr(ws), ws_bytes, _stream()),
+          "gg_gat_sell_fwd_f32")
+    return out, rowstat
+
+
+def _sell_edge_map(csc, csc2csr):
+    """CSR slot of the edge behind every entry of the CSC sliced-ELL layout (-1 for padding); built once per layout."""
+    sl = sell_layout(csc)
+    hit = getattr(sl, "_edge_map", None)
+    if hit is None or hit[0] is not csc2csr:
+        out = torch.empty(max(sl.total, 4), dtype=torch.int32, device=csc2csr.device)
+        check(lib().gg_sell_compose_map(_ptr(sl.slot_of), sl.total, _ptr(csc2csr), _ptr(out), _stream()),
+              "gg_sell_compose_map")
+        sl._edge_map = hit = (csc2csr, out)
+    return hit[1]
+
+
+def gat_sell_backward(csr, csc, csc2csr, h, att, slope, bias, rowstat, a_tgt, a_src, out, g):
+    """-> dh [n, f], datt [1, 2c] (heads = 1)."""
+    h, ldh = _rows(h, "h")
+    g, ldg = _rows(g, "g")
+    out, ldo = _rows(out, "out")
+    n, f = h.shape
+    dev = h.device
+    att = att.contiguous().view(1, 2 * f)
+    L = lib()
+    s1, s2 = sell_layout(csr), sell_layout(csc)
+    if bias is not None:
+        bias = bias.contiguous()
+    dz = _f32((csr.num_slots,), dev)
+    da_tgt, da_src = _f32((n,), dev), _f32((n,), dev)
+    ws_bytes = int(L.gg_gat_sell_workspace_bytes(max(s1.partial_rows, s2.partial_rows), f))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(L.gg_gat_sell_bwd_edge_f32(_ptr(s1.chunk_ptr), s1.chunks, _ptr(s1.idx), _ptr(s1.slot_of), _ptr(s1.vdst),
+                                     _ptr(s1.hub_rows), _ptr(s1.hub_pptr), s1.hubs, s1.partial_rows, _ptr(h), ldh, _ptr(g),
+                                     ldg, _ptr(out), ldo, _ptr(bias), _ptr(a_tgt), _ptr(a_src), _ptr(rowstat), n, f,
+                                     float(slope), _ptr(dz), _ptr(da_tgt), _ptr(ws), ws_bytes, _stream()),
+          "gg_gat_sell_bwd_edge_f32")
+    emap = _sell_edge_map(csc, csc2csr)
+    dh = torch.empty((n, f), dtype=torch.float32, device=dev)
+    tstat = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
+    att_tgt, att_src = att[0, :f].contiguous(), att[0, f:].contiguous()
+    check(L.gg_gat_sell_bwd_src_f32(_ptr(s2.chunk_ptr), s2.chunks, _ptr(s2.idx), _ptr(emap), _ptr(s2.vdst),
+                                    _ptr(s2.hub_rows), _ptr(s2.hub_pptr), s2.hubs, s2.partial_rows, _ptr(g), ldg,
+                                    _ptr(a_tgt), _ptr(a_src), _ptr(rowstat), _ptr(dz), _ptr(da_tgt), _ptr(att_src),
+                                    _ptr(att_tgt), n, f, float(slope), _ptr(dh), f, _ptr(da_src), _ptr(tstat), _ptr(ws),
+                                    ws_bytes, _stream()), "gg_gat_sell_bwd_src_f32")
+    datt = torch.empty((1, 2 * f), dtype=torch.float32, device=dev)
+    ws2_bytes = int(L.gg_gat_att_grad_workspace_bytes(n, 1, f))
+    ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device=dev)
+    check(L.gg_gat_att_grad_f32(_ptr(h), ldh, _ptr(da_tgt), _ptr(da_src), n, 1, f, _ptr(datt), _ptr(ws2), ws2_bytes,
+                                _stream()), "gg_gat_att_grad_f32")
+    return dh, datt
 
 
 def _gat_use_mp(csr, f, heads):
@@ -611,6 +685,9 @@ def gat_forward(csr, h, att, heads, slope, bias):
     L = lib()
     check(L.gg_gat_scores_f32(_ptr(h), ldh, _ptr(att), n, heads, c, _ptr(a_tgt), _ptr(a_src), _stream()),
           "gg_gat_scores_f32")
+    if _gat_use_sell(csr, f, heads) and ldh % 4 == 0:
+        out, rowstat = gat_sell_forward(csr, h, ldh, a_tgt, a_src, slope, bias)
+        return out, rowstat, a_tgt, a_src          # rowstat [n, 2] stands in for alpha [E', 1]
     alpha = _f32((csr.num_slots, heads), h.device)
     if _gat_use_mp(csr, f, heads):
         check(L.gg_gat_alpha_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(a_tgt), _ptr(a_src), n, float(slope),
@@ -627,7 +704,9 @@ def gat_forward(csr, h, att, heads, slope, bias):
 
 
 def gat_backward(csr, csc, csc2csr, h, att, heads, slope, bias, alpha, a_tgt, a_src, out, g):
-    """-> dh [n, f], datt [heads, 2c]."""
+    """-> dh [n, f], datt [heads, 2c].  ``alpha`` is the per-row (max, sum) record when the forward ran fused."""
+    if alpha.dim() == 2 and alpha.size(0) == h.size(0) and alpha.size(1) == 2 and _gat_use_sell(csr, h.size(1), heads):
+        return gat_sell_backward(csr, csc, csc2csr, h, att, slope, bias, alpha, a_tgt, a_src, out, g)
     h, ldh = _rows(h, "h")
     g, ldg = _rows(g, "g")
     out, ldo = _rows(out, "out")

@@ -338,6 +338,7 @@ class PeerPool:
         PeerPool._shared = {k: v for k, v in PeerPool._shared.items() if v is not self}
 
 
+PEER_RETURN = os.environ.get('GG_PEER_RETURN', 'push')   # push (bulk, contiguous) | fused (aggregation epilogue stores to the owners)
 _TRACE = os.environ.get('GG_PEER_TRACE', '0') == '1'   # CUDA-event timing of the exchange phases (diagnostics)
 _trace_events = []
 
@@ -417,12 +418,31 @@ def _from_slices(playout, layout, w, x_slice, rows, reduce, bias, self_scale=0.0
     if playout.exchange == 'sliced':
         pool = playout.pool
         ob = pool.get(('rows', per, f), per * f * 4)
-        ops.spmm(layout, x_slice, w, reduce, x_self, self_scale, b, rank1=rank1,
-                 out_peers=ops.PeerRows([q + part.rank * fs * 4 for q in ob.ptrs], per, f))
+        if PEER_RETURN == 'fused':
+            # rows stored into their owners' blocks by the aggregation kernel's epilogue (one kernel, fs*4-byte stores)
+            ops.spmm(layout, x_slice, w, reduce, x_self, self_scale, b, rank1=rank1,
+                     out_peers=ops.PeerRows([q + part.rank * fs * 4 for q in ob.ptrs], per, f))
+            _mark('aggregated')
+            pool.barrier()                                   # every slice of my rows has landed
+            _mark('barrier2')
+            res = ob.view(per, f)[:rows].clone()             # the block is reused by the next exchange
+            _mark('cloned')
+            return res
+        # default: aggregate into a local slice, push it to the owners in contiguous blocks (full NVLink packets), then
+        # assemble the owner's rows from the P received slices — the assembly doubles as the copy out of the reused block
+        out_slice = ops.spmm(layout, x_slice, w, reduce, x_self, self_scale, b, rank1=rank1)
         _mark('aggregated')
+        arr = (ctypes.c_void_p * P)(*ob.ptrs)
+        check(lib().gg_peer_push_rows_f32(ctypes.c_void_p(out_slice.data_ptr()), n, fs, per, P, part.rank, arr,
+                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), 'gg_peer_push_rows_f32')
+        _mark('pushed')
         pool.barrier()                                       # every slice of my rows has landed
         _mark('barrier2')
-        res = ob.view(per, f)[:rows].clone()                 # the block is reused by the next exchange
+        res = torch.empty((rows, f), dtype=torch.float32, device=x_slice.device)
+        check(lib().gg_peer_gather_slices_f32(ctypes.c_void_p(ob.ptrs[part.rank]), per, rows, fs, P,
+                                              ctypes.c_void_p(res.data_ptr()), f,
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+              'gg_peer_gather_slices_f32')
         _mark('cloned')
         return res
     out_slice = ops.spmm(layout, x_slice, w, reduce, x_self, self_scale, b, rank1=rank1)

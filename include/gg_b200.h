@@ -472,6 +472,36 @@ int gg_postops_bwd_f32(const float* go, int64_t ld_go, const float* out, int64_t
                        int act, float slope, int l2norm, const float* rownorm, float* dy, int64_t ld_dy, float* dgamma,
                        float* dbeta, void* workspace, size_t workspace_bytes, gg_stream_t stream);
 
+/* GAT (heads = 1) fused into the sliced-ELL aggregation (csrc/gat_sell.cu): alpha never touches memory.
+ *   gg_gat_sell_fwd_f32       CSR sliced-ELL layout (gg_sell_build): logits leaky_relu(a_tgt[i] + a_src[j]), online softmax
+ *                             fused with out[i] = sum_j alpha_ij h_j (+ bias); rowstat[2 i .. 2 i + 1] = (max, sum of exp)
+ *   gg_gat_sell_bwd_edge_f32  same layout: dalpha = <g_i, h_j>, alpha recomputed from rowstat, D_i = <g_i, out_i - bias>;
+ *                             writes dz[CSR slot] (gradient of the pre-activation logits) and da_tgt[i] = sum_e dz_e
+ *   gg_gat_sell_bwd_src_f32   CSC sliced-ELL layout + `edge_map` (gg_sell_compose_map(slot_of_csc, csc->csr slot map)):
+ *                             dh[j] = sum_i alpha_ij g_i + da_src[j] att_src + da_tgt[j] att_tgt, da_src[j] = sum_e dz_e;
+ *                             `tstat_scratch`: 4 n floats of scratch (per-target record a_tgt, max, 1/(sum + 1e-16))
+ * f % 4 == 0, f <= 128; workspace gg_gat_sell_workspace_bytes(partial rows of the layout, f). */
+size_t gg_gat_sell_workspace_bytes(int64_t partial_rows, int64_t f);
+int gg_sell_compose_map(const int32_t* slot_of, int64_t total, const int32_t* map, int32_t* out, gg_stream_t stream);
+int gg_gat_sell_fwd_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const int32_t* vdst,
+                        const int32_t* hub_rows, const int32_t* hub_pptr, int64_t hubs, int64_t partial_rows,
+                        const float* h, int64_t ldh, const float* a_tgt, const float* a_src, int64_t n, int64_t f,
+                        float slope, const float* bias, float* out, int64_t ldo, float* rowstat, void* workspace,
+                        size_t workspace_bytes, gg_stream_t stream);
+int gg_gat_sell_bwd_edge_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const int32_t* slot_of,
+                             const int32_t* vdst, const int32_t* hub_rows, const int32_t* hub_pptr, int64_t hubs,
+                             int64_t partial_rows, const float* h, int64_t ldh, const float* g, int64_t ldg,
+                             const float* fwd_out, int64_t ld_out, const float* bias, const float* a_tgt,
+                             const float* a_src, const float* rowstat, int64_t n, int64_t f, float slope, float* dz,
+                             float* da_tgt, void* workspace, size_t workspace_bytes, gg_stream_t stream);
+int gg_gat_sell_bwd_src_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const int32_t* edge_map,
+                            const int32_t* vdst, const int32_t* hub_rows, const int32_t* hub_pptr, int64_t hubs,
+                            int64_t partial_rows, const float* g, int64_t ldg, const float* a_tgt, const float* a_src,
+                            const float* rowstat, const float* dz, const float* da_tgt, const float* att_src,
+                            const float* att_tgt, int64_t n, int64_t f, float slope, float* dh, int64_t ld_dh,
+                            float* da_src, float* tstat_scratch, void* workspace, size_t workspace_bytes,
+                            gg_stream_t stream);
+
 /* Row gather / scatter-add / ReLU gradient used by the GIN-ID branch (ref: idconv.py:372-375):
  *   gather:      out[r,:]      = x[id[r],:]
  *   scatter_add: out[id[r],:] += x[r,:]      (atomicAdd: exact order-independence only for unique id,
@@ -511,6 +541,15 @@ int gg_peer_free(void* ptr);
 int gg_peer_barrier(void* const* flags_host, int world, int rank, gg_stream_t stream);
 int gg_peer_scatter_cols_f32(const float* src, int64_t ld, int64_t rows, int64_t f, float* const* dst_host,
                              int world, int64_t row_base, gg_stream_t stream);
+/* Return leg of the feature-sliced exchange as a bulk push (the alternative to the peer-output epilogue of the
+ * aggregation kernels): gg_peer_push_rows_f32 sends this rank's finished slice src[n, fs] to the rows' owners — owner o
+ * receives rows [o * rows_per_rank, ...) as one contiguous block recv_o[rank][i][0:fs] (recv_host: HOST array of `world`
+ * DEVICE pointers to the owners' receive buffers of world * rows_per_rank * fs floats); after a gg_peer_barrier the owner
+ * assembles out[i, c * fs + k] = recv[c][i][k] with gg_peer_gather_slices_f32 (local). */
+int gg_peer_push_rows_f32(const float* src, int64_t n, int64_t fs, int64_t rows_per_rank, int world, int rank,
+                          float* const* recv_host, gg_stream_t stream);
+int gg_peer_gather_slices_f32(const float* recv, int64_t rows_per_rank, int64_t rows, int64_t fs, int world, float* out,
+                              int64_t ldo, gg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Graph-level pooling: global_add / mean / max_pool, ref: graphgym/models/pooling.py:12-33

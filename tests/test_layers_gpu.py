@@ -224,15 +224,22 @@ def test_gat_multi_head(cuda, heads, c):
         assert rel_err(p.grad, P[k].grad) < FP32_TOL, k
 
 
-@pytest.mark.parametrize('algo', ['mp', 'row'])
+@pytest.mark.parametrize('fout', [128, 16, 36])
+@pytest.mark.parametrize('algo', ['sell', 'sell_split', 'mp', 'row'])
 @pytest.mark.parametrize('name', ['gatconv', 'gatidconv'])
-def test_gat_merge_path_and_row_kernels_agree_with_oracle(cuda, monkeypatch, algo, name):
-    """heads = 1 GAT runs as split passes on the merge-path kernels ('mp') or as the fused warp-per-row
-    kernels ('row'); both must match the oracle on a hub-heavy graph."""
+def test_gat_merge_path_and_row_kernels_agree_with_oracle(cuda, monkeypatch, algo, name, fout):
+    """heads = 1 GAT runs fused into the sliced-ELL aggregation ('sell': online softmax, alpha never stored; 'sell_split':
+    the same with rows cut into virtual rows of 8 slots, so the (max, sum, accumulator) merge of split rows is exercised),
+    as split passes on the merge-path kernels ('mp') or as the fused warp-per-row kernels ('row'); all must match the
+    oracle on a hub-heavy graph."""
     from graphgym_b200 import ops
-    monkeypatch.setattr(ops, 'GAT_ALGO', algo)
+    monkeypatch.setattr(ops, 'GAT_ALGO', algo.split('_')[0])
+    if algo == 'sell_split':
+        monkeypatch.setattr(ops, 'SELL_SEG', 8)
+    if fout != 128 and algo in ('mp', 'row'):
+        pytest.skip('narrow widths: the sliced-ELL path only')
     reset_cfg()
-    n, fin, fout = 6000, 40, 128
+    n, fin = 6000, 40
     ei = powerlaw_graph(7, n, 14)
     g = torch.Generator().manual_seed(3)
     x = torch.randn(n, fin, generator=g)
@@ -247,6 +254,7 @@ def test_gat_merge_path_and_row_kernels_agree_with_oracle(cuda, monkeypatch, alg
     yo.backward(gy.double())
     y, gx, grads = run_ours(layer, x, ei, ids, gy, cuda)
     assert rel_err(y, yo.detach()) < FP32_TOL
+    assert torch.allclose(y.double(), yo.detach(), rtol=1e-4, atol=1e-5)        # element-wise as well
     assert rel_err(gx, xd.grad) < FP32_TOL
     for k, gk in grads.items():
         assert rel_err(gk, P[k].grad) < FP32_TOL, k

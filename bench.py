@@ -684,8 +684,10 @@ def run_ours(args, spec, rank, world, dev):
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
     start.record()
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         step(x_loc, ei, playout)
+    host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps    # time to ENQUEUE a step: ~ms_per_step => host bound
     end.record()
     sync_all()
     ops.spmm = orig_spmm
@@ -862,6 +864,7 @@ def run_ours(args, spec, rank, world, dev):
                    'layout_cached_across_steps': True},
         'clocks': clocks.summary(), 'e2e': e2e, 'gpu_launches': int(launches),
         'roofline': roofline, 'cpu_baseline': cpu,
+        'host_enqueue_ms_per_step': round(host_ms, 3),
         'parity_vs_1gpu': parity, 'comparators': comparators,
         'exchange_trace_ms': exchange_trace,   # GG_PEER_TRACE=1: mean ms between the exchange's phase marks, rank 0, timed steps
         # the reference re-runs its COO edits + normalisation on every forward (idconv.py:69-87); `value` caches the layout

@@ -617,6 +617,51 @@ class RowPartitionedGAT(torch.nn.Module):
         return _DistGatSliced.apply(h, m.att, m.bias, playout, float(m.negative_slope))
 
 
+class RowPartitionedGATID(torch.nn.Module):
+    """``gatidconv`` (ref: idconv.py:266-347, heads = 1) on a row partition: the heterogeneous transform X W (+ X W_id on the
+    centre rows, ``node_id_index`` cut to this rank's rows) is row-local; attention + aggregation run on the feature-sliced
+    exchange exactly as for ``gatconv``."""
+
+    def __init__(self, dim_in, dim_out, bias=True):
+        super().__init__()
+        from .contrib.layer.idconv import GATIDConvLayer
+        self.model = GATIDConvLayer(dim_in, dim_out, heads=1, bias=bias)
+
+    def forward(self, x_local, playout, node_id_index):
+        from .graph import IdIndex
+        if not playout.sliced:
+            raise NotImplementedError('row-partitioned gatidconv runs on the feature-sliced exchange '
+                                      '(exchange="sliced" or "sliced_nccl")')
+        m = self.model
+        h = F_.id_linear(x_local, m.weight, m.weight_id, IdIndex(_local_ids(node_id_index, playout.part), x_local.size(0)))
+        return _DistGatSliced.apply(h, m.att, m.bias, playout, float(m.negative_slope))
+
+
+class RowPartitionedIDConv(torch.nn.Module):
+    """``idconv`` (GeneralIDConvLayer, ref: idconv.py:16-101) on a row partition: ID transform row-local, aggregation kind
+    from ``cfg.gnn.agg`` / ``cfg.gnn.normalize_adj`` as the single-GPU layer reads them at construction."""
+
+    def __init__(self, dim_in, dim_out, bias=True):
+        super().__init__()
+        from .contrib.layer.idconv import GeneralIDConvLayer
+        self.model = GeneralIDConvLayer(dim_in, dim_out, bias=bias)
+
+    @staticmethod
+    def policy_and_kind():
+        from .config import cfg
+        if cfg.gnn.normalize_adj:
+            if cfg.gnn.agg == 'mean':
+                raise NotImplementedError('row-partitioned idconv: normalize_adj with agg="mean" (single-GPU only)')
+            return ops.LOOPS_ADD_REMAINING, 'gcn_src'
+        return ops.LOOPS_KEEP, ('mean' if cfg.gnn.agg == 'mean' else 'sum')
+
+    def forward(self, x_local, playout, node_id_index):
+        from .graph import IdIndex
+        m = self.model
+        h = F_.id_linear(x_local, m.weight, m.weight_id, IdIndex(_local_ids(node_id_index, playout.part), x_local.size(0)))
+        return dist_aggregate(h, playout, self.policy_and_kind()[1], m.bias)
+
+
 class RowPartitionedGCNID(torch.nn.Module):
     """``gcnidconv`` (ID-GNN's GCN layer, ref: idconv.py:104-189) on a row partition: the heterogeneous transform
     X W (+ X W_id on the centre rows) is row-local — ``node_id_index`` is cut to this rank's rows — and the
@@ -685,4 +730,6 @@ ROW_PARTITIONED = {'gcnconv': (RowPartitionedGCN, ops.LOOPS_ADD_REMAINING, 'gcn_
                    'gcnidconv': (RowPartitionedGCNID, ops.LOOPS_ADD_REMAINING, 'gcn_src'),
                    'sageconv': (RowPartitionedSAGE, ops.LOOPS_KEEP, 'mean'),
                    'ginconv': (RowPartitionedGIN, ops.LOOPS_KEEP, 'sum'),
-                   'gatconv': (RowPartitionedGAT, ops.LOOPS_REMOVE_ADD, 'sum')}
+                   'gatconv': (RowPartitionedGAT, ops.LOOPS_REMOVE_ADD, 'sum'),
+                   'gatidconv': (RowPartitionedGATID, ops.LOOPS_REMOVE_ADD, 'sum'),
+                   'idconv': (RowPartitionedIDConv, ops.LOOPS_KEEP, 'sum')}   # idconv: cfg.gnn defaults (add, no normalisation)

@@ -1,0 +1,29 @@
+"""ncu target (round 2): one launch each of the kernels the round-1 verdict asked captures for — radix sort scatter (layout
+build), edge-softmax passes (split: gat_alpha / sddmm / dz; fused: gat_sell_*), ego-net BFS, closed-walk kernels — on the
+shapes the benches use."""
+import sys, torch
+sys.path.insert(0, '/root/repo')
+import bench
+from graphgym_b200 import ops
+from graphgym_b200.graph import GraphLayout
+from graphgym_b200.models import transform as gtr
+from graphgym_b200.contrib.transform import identity as gid
+dev = torch.device('cuda')
+n, ei = bench.gen_graph(bench.WORKLOADS['products_gat'], dev)
+lay = GraphLayout(ei, n, ops.LOOPS_REMOVE_ADD)
+csr, csc, m = lay.csr, lay.csc, lay.csc2csr          # radix_hist / radix_scatter / layout kernels
+f = 128
+h = torch.randn(n, f, device=dev); g = torch.randn(n, f, device=dev)
+att = torch.randn(1, 1, 2 * f, device=dev) * 0.1; bias = torch.zeros(f, device=dev)
+for algo in ('mp', 'sell'):
+    ops.GAT_ALGO = algo
+    out, al, a_tgt, a_src = ops.gat_forward(csr, h, att, 1, 0.2, bias)
+    ops.gat_backward(csr, csc, m, h, att, 1, 0.2, bias, al, a_tgt, a_src, out, g)
+torch.cuda.synchronize()
+del h, g, lay, csr, csc, m, out, al
+spec = bench.WORKLOADS['ego_idgin']
+n2, ei2, gptr = bench.gen_ba_batch(spec, dev)
+gtr.ego_nets_batch(ei2, n2, 3, gptr)                  # egonet_sizes / egonet_fill
+gid.closed_walk_counts(ei2, n2, 6, graph_ptr=gptr)    # walk_* int64
+gid.compute_identity(ei2, n2, 10, graph_ptr=gptr)     # walk_* f32
+torch.cuda.synchronize()

@@ -45,6 +45,28 @@ def test_layout_is_a_stable_counting_sort(big):
             assert torch.equal(perm[~orig] - E, rowid[~orig]) and torch.equal(nbr[~orig], rowid[~orig])
 
 
+def test_aggregation_equals_fp64_scatter_at_full_size(big):
+    """Direct comparison at BASELINE's full size: the aggregation kernels (sliced-ELL default, merge-path) against the
+    reference's gather / scale / index_add_ evaluated in float64 on the device over slot chunks (a checker: library ops
+    only) — norm-wise 1e-5 and element-wise."""
+    spec, n, ei = big
+    f = 128
+    lay = GraphLayout(ei, n, ops.LOOPS_ADD_REMAINING)
+    w_csr, _ = lay.weights('gcn_tgt')
+    x = torch.randn(n, f, device=ei.device, generator=torch.Generator(device=ei.device).manual_seed(3))
+    csr = lay.csr
+    want = torch.zeros((n, f), dtype=torch.float64, device=ei.device)
+    chunk = 1 << 21
+    for s0 in range(0, csr.num_slots, chunk):
+        sl = slice(s0, min(csr.num_slots, s0 + chunk))
+        want.index_add_(0, csr.rowid[sl].long(), x.index_select(0, csr.nbr[sl].long()).double() * w_csr[sl].double().view(-1, 1))
+    for algo in ('auto', 'mpg'):
+        got = ops.spmm(csr, x, w_csr, algo=algo).double()
+        assert float((got - want).abs().max() / want.abs().max()) < 1e-5, algo
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-5 * float(want.abs().max())), algo
+    del want
+
+
 def test_aggregation_is_linear_and_csc_is_its_adjoint(big):
     spec, n, ei = big
     f = 128
@@ -75,13 +97,27 @@ def test_edge_softmax_rows_sum_to_one(big):
     g = torch.Generator(device=ei.device).manual_seed(2)
     h = torch.randn(n, 128, device=ei.device, generator=g)
     att = torch.randn(1, 1, 256, device=ei.device, generator=g) * 0.1
-    out, alpha, _, _ = ops.gat_forward(lay.csr, h, att, 1, 0.2, None)
+    import pytest
+    mp = pytest.MonkeyPatch()
+    try:
+        mp.setattr(ops, 'GAT_ALGO', 'mp')                       # split passes: alpha is materialised
+        out, alpha, _, _ = ops.gat_forward(lay.csr, h, att, 1, 0.2, None)
+    finally:
+        mp.undo()
     sums = torch.zeros(n, device=ei.device, dtype=torch.float64).index_add_(0, lay.csr.rowid.long(),
                                                                              alpha.view(-1).double())
     assert float((sums - 1.0).abs().max()) < 1e-5
     assert bool((alpha >= 0).all()) and bool(torch.isfinite(out).all())
     # a convex combination of rows stays inside the per-column range of h
     assert float(out.max()) <= float(h.max()) + 1e-4 and float(out.min()) >= float(h.min()) - 1e-4
+    # fused path (online softmax inside the sliced-ELL aggregation, alpha never stored): the same output, and on h = 1
+    # every row is sum_e alpha_e = 1
+    fused, rowstat, a_tgt, a_src = ops.gat_forward(lay.csr, h, att, 1, 0.2, None)
+    assert rowstat.shape == (n, 2)
+    assert float((fused - out).abs().max()) / float(out.abs().max()) < 1e-5
+    ones = torch.ones(n, 128, device=ei.device)
+    one_out, _ = ops.gat_sell_forward(lay.csr, ones, 128, a_tgt.view(-1), a_src.view(-1), 0.2, None)
+    assert float((one_out - 1.0).abs().max()) < 1e-5
 
 
 def test_cycle_counts_and_ego_invariants_on_a_large_batch():

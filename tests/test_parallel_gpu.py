@@ -33,7 +33,7 @@ def _worker(rank, world, port, exchange, ret, name='gcnconv'):
         from graphgym_b200 import ops, parallel
         from graphgym_b200.models.layer import Batch, layer_dict
         from util import powerlaw_graph, rel_err
-        n, fin, fout = 30001, (100 if name in ('gcnconv', 'gatconv', 'gcnidconv') else 128), 128
+        n, fin, fout = 30001, (100 if name in ('gcnconv', 'gatconv', 'gcnidconv', 'gatidconv', 'idconv') else 128), 128
         ei = powerlaw_graph(2, n, 12).to(dev)
         g = torch.Generator().manual_seed(1)
         x = torch.randn(n, fin, generator=g).to(dev)
@@ -120,8 +120,10 @@ def test_two_gpu_gat(exchange):
 
 
 @pytest.mark.parametrize('exchange', ['allgather', 'sliced'])
-@pytest.mark.parametrize('name', ['sageconv', 'ginconv', 'gcnidconv', 'sageidconv', 'ginidconv'])
+@pytest.mark.parametrize('name', ['sageconv', 'ginconv', 'gcnidconv', 'sageidconv', 'ginidconv', 'idconv', 'gatidconv'])
 def test_two_gpu_sage_gin_gcnid(name, exchange):
+    if name == 'gatidconv' and exchange == 'allgather':
+        pytest.skip('the edge-softmax layers run on the feature-sliced exchange')
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
     ret = mp.Manager().dict()

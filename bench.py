@@ -367,14 +367,26 @@ def run_aux(args, spec, dev, rank=0, world=1):
         L = ops.lib()
         item_row, item_slot, items = csr.plan
         use_mp = gid.MP_STEP
-        ws = torch.empty(int(L.gg_cycle_diag_mp_workspace_bytes(n, items)), dtype=torch.uint8, device=dev)
+        use_sell = gid.CYCLE_STEP == 'sell'
+        if use_sell:
+            sl = ops.sell_layout(csr)
+            w_sell = sl.weights(w)
+            ws = torch.empty(int(L.gg_cycle_diag_sell_workspace_bytes(n, sl.partial_rows)), dtype=torch.uint8, device=dev)
+        else:
+            ws = torch.empty(int(L.gg_cycle_diag_mp_workspace_bytes(n, items)), dtype=torch.uint8, device=dev)
         out = torch.empty((128, k), dtype=torch.float32, device=dev)
         blk = [rank]
 
         def one_block():   # 128 consecutive sources: 5 hops over the whole graph + 10 dot products; rank r takes blocks r, r+P, ...
             sb = (blk[0] * 128) % (n - 128)
             blk[0] += world
-            if use_mp:
+            if use_sell:
+                ops.check(L.gg_cycle_diag_sell_f32(ops._ptr(csr.rowptr), ops._ptr(sl.chunk_ptr), sl.chunks, ops._ptr(sl.idx),
+                                                   ops._ptr(w_sell), ops._ptr(sl.vdst), ops._ptr(sl.hub_rows),
+                                                   ops._ptr(sl.hub_pptr), sl.hubs, sl.partial_rows, n, k, 1, sb, 128,
+                                                   ops._ptr(out), k, ops._ptr(ws), ws.numel(), ops._stream()),
+                          'gg_cycle_diag_sell_f32')
+            elif use_mp:
                 ops.check(L.gg_cycle_diag_mp_f32(ops._ptr(csr.rowptr), ops._ptr(csr.nbr), ops._ptr(w), ops._ptr(item_row),
                                                  ops._ptr(item_slot), items, n, k, 1, sb, 128, ops._ptr(out), k,
                                                  ops._ptr(ws), ws.numel(), ops._stream()), 'gg_cycle_diag_mp_f32')
@@ -404,7 +416,7 @@ def run_aux(args, spec, dev, rank=0, world=1):
                            'whole_graph_seconds': round(ms * 1e-3 * (n / 128) / world, 1),
                            'l2_policy': 'inputs larger than L2 (two 512 MB walk matrices)'},
                 'clocks': clocks.summary(), 'e2e': None, 'gpu_launches': launches,
-                'roofline': {'bound': 'hbm', 'kernel': ('spmm_mpg_kernel' if use_mp else 'walk_step_kernel') + ' (+ walk_dot) over one block of 128 sources (per GPU)',
+                'roofline': {'bound': 'hbm', 'kernel': ('spmm_sell_kernel' if use_sell else 'spmm_mpg_kernel' if use_mp else 'walk_step_kernel') + ' (+ walk_dot) over one block of 128 sources (per GPU)',
                              'achieved': round(ach, 1), 'peak': peak, 'unit': 'GB/s', 'frac': round(ach / peak, 4),
                              'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_step': step_bytes},
                 'cpu_baseline': cpu}

@@ -116,6 +116,9 @@ SIGNATURES = {
     "gg_cycle_diag_mp_workspace_bytes": (c_size, [c_i64, c_i64]),
     "gg_cycle_diag_mp_f32": (c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_int, c_ptr,
                                      c_i64, c_ptr, c_size, c_ptr]),
+    "gg_cycle_diag_sell_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "gg_cycle_diag_sell_f32": (c_int, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_i64, c_int,
+                                       c_int, c_i64, c_int, c_ptr, c_i64, c_ptr, c_size, c_ptr]),
     "gg_cycle_diag_i64": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_int, c_i64, c_int, c_ptr, c_i64, c_ptr,
                                   c_ptr, c_size, c_ptr]),
     "gg_egonet_workspace_bytes": (c_size, [c_i64, c_i64]),

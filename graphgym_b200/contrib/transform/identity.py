@@ -16,7 +16,8 @@ from graphgym_b200 import ops
 from graphgym_b200.ops import _ptr, _stream, check, lib
 
 
-MP_STEP = os.environ.get("GG_CYCLE_STEP", "mp") == "mp"   # mp (merge-path aggregation kernel) | row (one warp per row)
+CYCLE_STEP = os.environ.get("GG_CYCLE_STEP", "sell")   # sell (sliced-ELL aggregation) | mp (merge-path) | row (one warp per row)
+MP_STEP = CYCLE_STEP in ("mp", "sell")
 
 
 def _ranges(n, graph_ptr, block):
@@ -47,11 +48,16 @@ def _run(layout_csr, w_slot, n, k, symmetric, graph_ptr, integer):
     gp = graph_ptr.cpu() if graph_ptr is not None else None
     # one big graph in float mode: every hop is a whole-graph aggregation -> the load-balanced merge-path kernel
     use_mp = (not integer) and gp is None and n + layout_csr.num_slots >= (1 << 14) and MP_STEP
-    if use_mp:
+    use_sell = use_mp and CYCLE_STEP == "sell"
+    if use_sell:
+        sl = ops.sell_layout(layout_csr)
+        w_sell = sl.weights(w_slot)
+    elif use_mp:
         item_row, item_slot, items = layout_csr.plan
     ws = None
     for rb, re, sb, sc in _ranges(n, gp, block):
-        need = int(L.gg_cycle_diag_mp_workspace_bytes(n, items)) if use_mp else int(L.gg_cycle_diag_workspace_bytes(re - rb))
+        need = int(L.gg_cycle_diag_sell_workspace_bytes(n, sl.partial_rows)) if use_sell else \
+            int(L.gg_cycle_diag_mp_workspace_bytes(n, items)) if use_mp else int(L.gg_cycle_diag_workspace_bytes(re - rb))
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, dtype=torch.uint8, device=dev)
         dst = out[sb:sb + sc]
@@ -59,6 +65,11 @@ def _run(layout_csr, w_slot, n, k, symmetric, graph_ptr, integer):
             check(L.gg_cycle_diag_i64(_ptr(layout_csr.rowptr), _ptr(layout_csr.nbr), rb, re, k, int(symmetric),
                                       sb, sc, _ptr(dst), k, _ptr(overflow), _ptr(ws), ws.numel(), _stream()),
                   "gg_cycle_diag_i64")
+        elif use_sell:
+            check(L.gg_cycle_diag_sell_f32(_ptr(layout_csr.rowptr), _ptr(sl.chunk_ptr), sl.chunks, _ptr(sl.idx), _ptr(w_sell),
+                                           _ptr(sl.vdst), _ptr(sl.hub_rows), _ptr(sl.hub_pptr), sl.hubs, sl.partial_rows, n, k,
+                                           int(symmetric), sb, sc, _ptr(dst), k, _ptr(ws), ws.numel(), _stream()),
+                  "gg_cycle_diag_sell_f32")
         elif use_mp:
             check(L.gg_cycle_diag_mp_f32(_ptr(layout_csr.rowptr), _ptr(layout_csr.nbr), _ptr(w_slot), _ptr(item_row),
                                          _ptr(item_slot), items, n, k, int(symmetric), sb, sc, _ptr(dst), k, _ptr(ws),

@@ -196,6 +196,15 @@ struct WalkPlan {
     const int32_t* item_row;
     const int32_t* item_slot;
     int64_t items;
+    // sliced-ELL layout of the same graph (gg_sell_build): when given, the hops run on gg_spmm_sell_f32
+    const uint32_t* chunk_ptr = nullptr;
+    int64_t chunks = 0;
+    const int32_t* idx = nullptr;
+    const float* w_sell = nullptr;
+    const int32_t* vdst = nullptr;
+    const int32_t* hub_rows = nullptr;
+    const int32_t* hub_pptr = nullptr;
+    int64_t hubs = 0, partial_rows = 0;
 };
 
 template <typename T, typename Out>
@@ -210,7 +219,9 @@ int cycle_diag(const int32_t* rowptr, const int32_t* nbr, const float* w, int64_
     GG_REQUIRE(src_begin >= row_begin && src_begin + src_count <= row_end,
                "gg_cycle_diag: sources outside the row range");
     GG_REQUIRE(rowptr && out && workspace && ld_out >= k, "gg_cycle_diag: bad operands");
-    const size_t mp_bytes = plan ? align_up(gg_spmm_mp_workspace_bytes(plan->items, W::kCols), 256) : 0;
+    const size_t mp_bytes = !plan ? 0
+                            : plan->chunk_ptr ? align_up(gg_spmm_sell_workspace_bytes(plan->partial_rows, W::kCols), 256)
+                                              : align_up(gg_spmm_mp_workspace_bytes(plan->items, W::kCols), 256);
     if (workspace_bytes < cycle_ws_bytes<T>(rows) + mp_bytes) {
         set_error("gg_cycle_diag: workspace %zu < %zu", workspace_bytes, cycle_ws_bytes<T>(rows) + mp_bytes);
         return GG_ERR_WORKSPACE;
@@ -232,6 +243,16 @@ int cycle_diag(const int32_t* rowptr, const int32_t* nbr, const float* w, int64_
     void* mp_ws = plan ? c.take<char>(mp_bytes) : nullptr;
     int step_rc = GG_OK;
     auto step = [&](const Vec* in, Vec* o) {
+        if (plan && plan->chunk_ptr) {   // degree-sorted sliced-ELL aggregation (round 2: 3.3 vs 4.3 ms at 128 columns)
+            const int rc = gg_spmm_sell_f32(plan->chunk_ptr, plan->chunks, plan->idx, plan->w_sell, plan->vdst, rowptr,
+                                            plan->hub_rows, plan->hub_pptr, plan->hubs, plan->partial_rows,
+                                            reinterpret_cast<const float*>(in), W::kCols, reinterpret_cast<float*>(o),
+                                            W::kCols, nullptr, 1, rows, rows, W::kCols, GG_SUM, nullptr, 0, 0.f, nullptr,
+                                            nullptr, nullptr, nullptr, nullptr, mp_ws, mp_bytes, 4,
+                                            reinterpret_cast<gg_stream_t>(st));
+            if (rc != GG_OK) step_rc = rc;
+            return;
+        }
         if (plan) {  // load-balanced, TMA-staged aggregation kernel (hub rows no longer serialise one warp)
             const int rc = gg_spmm_mpg_f32(rowptr, nbr, w, plan->item_row, plan->item_slot, plan->items,
                                            reinterpret_cast<const float*>(in), W::kCols, reinterpret_cast<float*>(o),
@@ -302,6 +323,23 @@ int gg_cycle_diag_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float*
     if constexpr (sizeof(float4) != 16) return GG_ERR_UNSUPPORTED;
     WalkPlan plan{item_row, item_slot, items};
     return cycle_diag<float, float>(rowptr, nbr, w_slot, 0, num_rows, k, symmetric, src_begin, src_count, out, ld_out,
+                                    nullptr, workspace, workspace_bytes, as_stream(stream), &plan);
+}
+
+size_t gg_cycle_diag_sell_workspace_bytes(int64_t num_rows, int64_t partial_rows) {
+    return gg_cycle_diag_workspace_bytes(num_rows) + align_up(gg_spmm_sell_workspace_bytes(partial_rows, 128), 256) + 256;
+}
+
+int gg_cycle_diag_sell_f32(const int32_t* rowptr, const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx,
+                           const float* w_sell, const int32_t* vdst, const int32_t* hub_rows, const int32_t* hub_pptr,
+                           int64_t hubs, int64_t partial_rows, int64_t num_rows, int k, int symmetric, int64_t src_begin,
+                           int src_count, float* out, int64_t ld_out, void* workspace, size_t workspace_bytes,
+                           gg_stream_t stream) {
+    GG_REQUIRE(chunk_ptr && idx && vdst && chunks >= 1, "gg_cycle_diag_sell_f32: missing sliced-ELL layout");
+    WalkPlan plan{nullptr, nullptr, 0};
+    plan.chunk_ptr = chunk_ptr; plan.chunks = chunks; plan.idx = idx; plan.w_sell = w_sell; plan.vdst = vdst;
+    plan.hub_rows = hub_rows; plan.hub_pptr = hub_pptr; plan.hubs = hubs; plan.partial_rows = partial_rows;
+    return cycle_diag<float, float>(rowptr, nullptr, w_sell, 0, num_rows, k, symmetric, src_begin, src_count, out, ld_out,
                                     nullptr, workspace, workspace_bytes, as_stream(stream), &plan);
 }
 

@@ -353,6 +353,14 @@ int gg_cycle_diag_mp_f32(const int32_t* rowptr, const int32_t* nbr, const float*
                          const int32_t* item_slot, int64_t items, int64_t num_rows, int k, int symmetric,
                          int64_t src_begin, int src_count, float* out, int64_t ld_out, void* workspace,
                          size_t workspace_bytes, gg_stream_t stream);
+/* Same as gg_cycle_diag_mp_f32 with the propagation hops on the sliced-ELL aggregation (gg_sell_build layout of the
+ * whole graph; `w_sell`: the normalisation weights re-laid by gg_sell_permute_f32). */
+size_t gg_cycle_diag_sell_workspace_bytes(int64_t num_rows, int64_t partial_rows);
+int gg_cycle_diag_sell_f32(const int32_t* rowptr, const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx,
+                           const float* w_sell, const int32_t* vdst, const int32_t* hub_rows, const int32_t* hub_pptr,
+                           int64_t hubs, int64_t partial_rows, int64_t num_rows, int k, int symmetric, int64_t src_begin,
+                           int src_count, float* out, int64_t ld_out, void* workspace, size_t workspace_bytes,
+                           gg_stream_t stream);
 int gg_cycle_diag_i64(const int32_t* rowptr, const int32_t* nbr, int64_t row_begin, int64_t row_end, int k,
                       int symmetric, int64_t src_begin, int src_count, int64_t* out, int64_t ld_out,
                       int32_t* overflow_count, void* workspace, size_t workspace_bytes, gg_stream_t stream);

@@ -105,3 +105,38 @@ def test_merge_path_propagation_step(cuda, monkeypatch):
     assert rel_err(got_mp, want) < FP32_TOL
     assert rel_err(got_mp_general, want) < FP32_TOL
     assert rel_err(got_row, want) < FP32_TOL
+
+
+def test_whole_graph_hops_on_sliced_ell_merge_path_and_row_kernels_agree(cuda, monkeypatch):
+    """one big graph: the propagation hops run on the sliced-ELL aggregation (default), the merge-path kernel or the
+    warp-per-row walk kernel — all three must give the reference's diag(A_hat^p) (checked against each other and, on a
+    sub-sampled set of nodes, against sparse fp64 powers)."""
+    import numpy as np
+    import scipy.sparse as sp
+    from graphgym_b200.contrib.transform import identity as gid
+    from util import powerlaw_graph
+    n, k = 20000, 6
+    ei = powerlaw_graph(11, n, 8)
+    res = {}
+    for mode in ('sell', 'mp', 'row'):
+        monkeypatch.setattr(gid, 'CYCLE_STEP', mode)
+        monkeypatch.setattr(gid, 'MP_STEP', mode in ('mp', 'sell'))
+        res[mode] = gid.compute_identity(ei.to(cuda), n, k).cpu().double()
+    # fp64 reference: A_hat = D^-1/2 (A + I) D^-1/2 with duplicate edges summed (identity.py:7-35)
+    e = ei.numpy()
+    keep = e[0] != e[1]
+    r = np.concatenate([e[0][keep], np.arange(n)])
+    c = np.concatenate([e[1][keep], np.arange(n)])
+    a = sp.coo_matrix((np.ones(r.size), (r, c)), shape=(n, n)).tocsr()
+    deg = np.asarray(a.sum(axis=1)).ravel()
+    dis = np.where(deg > 0, deg ** -0.5, 0.0)
+    ah = sp.diags(dis) @ a @ sp.diags(dis)
+    cols = np.arange(0, n, 97)
+    v = np.zeros((n, cols.size)); v[cols, np.arange(cols.size)] = 1.0
+    want = np.zeros((cols.size, k))
+    for p in range(k):
+        v = ah @ v
+        want[:, p] = v[cols, np.arange(cols.size)]
+    for mode, got in res.items():
+        assert np.abs(got.numpy()[cols] - want).max() / np.abs(want).max() < 1e-5, mode
+    assert float((res['sell'] - res['mp']).abs().max()) < 1e-6

@@ -338,7 +338,9 @@ class PeerPool:
         PeerPool._shared = {k: v for k, v in PeerPool._shared.items() if v is not self}
 
 
-PEER_RETURN = os.environ.get('GG_PEER_RETURN', 'push')   # push (bulk, contiguous) | fused (aggregation epilogue stores to the owners)
+# return leg of the sliced exchange: fused (aggregation epilogue stores rows to their owners) | push (bulk, contiguous) |
+# auto (fused while a row piece fills an NVLink packet, fs * 4 >= 128 bytes, i.e. up to 4 ranks at 128 columns; push beyond)
+PEER_RETURN = os.environ.get('GG_PEER_RETURN', 'auto')
 _TRACE = os.environ.get('GG_PEER_TRACE', '0') == '1'   # CUDA-event timing of the exchange phases (diagnostics)
 _trace_events = []
 
@@ -418,7 +420,7 @@ def _from_slices(playout, layout, w, x_slice, rows, reduce, bias, self_scale=0.0
     if playout.exchange == 'sliced':
         pool = playout.pool
         ob = pool.get(('rows', per, f), per * f * 4)
-        if PEER_RETURN == 'fused':
+        if PEER_RETURN == 'fused' or (PEER_RETURN == 'auto' and fs >= 32):
             # rows stored into their owners' blocks by the aggregation kernel's epilogue (one kernel, fs*4-byte stores)
             ops.spmm(layout, x_slice, w, reduce, x_self, self_scale, b, rank1=rank1,
                      out_peers=ops.PeerRows([q + part.rank * fs * 4 for q in ob.ptrs], per, f))

@@ -32,6 +32,10 @@ def _worker(rank, world, port, exchange, ret, name='gcnconv'):
     try:
         from graphgym_b200 import ops, parallel
         from graphgym_b200.models.layer import Batch, layer_dict
+        if exchange == 'sliced_push':       # the bulk-push return leg (the default beyond 4 ranks), forced at any world size
+            exchange, parallel.PEER_RETURN = 'sliced', 'push'
+        elif exchange == 'sliced':
+            parallel.PEER_RETURN = 'fused'
         from util import powerlaw_graph, rel_err
         n, fin, fout = 30001, (100 if name in ('gcnconv', 'gatconv', 'gcnidconv', 'gatidconv', 'idconv') else 128), 128
         ei = powerlaw_graph(2, n, 12).to(dev)
@@ -81,7 +85,7 @@ def _worker(rank, world, port, exchange, ret, name='gcnconv'):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('exchange', ['allgather', 'pipelined', 'sliced_nccl', 'sliced'])
+@pytest.mark.parametrize('exchange', ['allgather', 'pipelined', 'sliced_nccl', 'sliced', 'sliced_push'])
 def test_two_gpu_row_partition_matches_single_gpu(exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
@@ -94,8 +98,8 @@ def test_two_gpu_row_partition_matches_single_gpu(exchange):
 
 
 @pytest.mark.parametrize('world', [4, 8])
-@pytest.mark.parametrize('name,exchange', [('gcnconv', 'sliced'), ('gcnconv', 'allgather'), ('gatconv', 'sliced'),
-                                           ('sageconv', 'sliced'), ('ginidconv', 'sliced')])
+@pytest.mark.parametrize('name,exchange', [('gcnconv', 'sliced'), ('gcnconv', 'sliced_push'), ('gcnconv', 'allgather'),
+                                           ('gatconv', 'sliced_push'), ('sageconv', 'sliced'), ('ginidconv', 'sliced_push')])
 def test_four_and_eight_gpu_row_partition(world, name, exchange):
     """the sliced exchange at F/P = 32 and 16 columns (sliced-ELL kernel with peer-memory output) and the all-gather form"""
     if torch.cuda.device_count() < world:
@@ -107,7 +111,7 @@ def test_four_and_eight_gpu_row_partition(world, name, exchange):
         assert ok, errs
 
 
-@pytest.mark.parametrize('exchange', ['sliced_nccl', 'sliced'])
+@pytest.mark.parametrize('exchange', ['sliced_nccl', 'sliced', 'sliced_push'])
 def test_two_gpu_gat(exchange):
     """edge-softmax layer: per-node logits all-gathered, sliced aggregations, sliced SDDMM + all-reduce"""
     if torch.cuda.device_count() < 2:

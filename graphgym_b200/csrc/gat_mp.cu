@@ -409,3 +409,66 @@ int gg_gat_sddmm_mpg_f32(const int32_t* rowptr, const int32_t* nbr, const int32_
 }
 
 }  // extern "C"
+
+// ---- generic per-row softmax over given logits (Tfg scaled dot-product attention, ref: TfgIDLayer.py:336-345,
+// sparse_adj.py:136-151 -> tf_geometric segment_softmax: exp(z - max) / sum, no epsilon) -------------------------------
+namespace gg {
+
+// one warp per row: alpha[s] = exp(scale * z[s] - max) / sum
+__global__ void __launch_bounds__(kGmThreads)
+    segment_softmax_kernel(const int32_t* __restrict__ rowptr, const float* __restrict__ z, int64_t n, float scale,
+                           float* __restrict__ alpha) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kGmWarps + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    float m = -CUDART_INF_F;
+    for (int s = beg + lane; s < end; s += 32) m = fmaxf(m, scale * __ldg(z + s));
+    m = gm_warp_max(m);
+    float sum = 0.f;
+    for (int s = beg + lane; s < end; s += 32) sum += expf(scale * __ldg(z + s) - m);
+    const float inv = 1.0f / gm_warp_sum(sum);
+    for (int s = beg + lane; s < end; s += 32) alpha[s] = expf(scale * __ldg(z + s) - m) * inv;
+}
+
+// dz[s] = scale * alpha[s] * (dalpha[s] - sum_row alpha dalpha)
+__global__ void __launch_bounds__(kGmThreads)
+    segment_softmax_bwd_kernel(const int32_t* __restrict__ rowptr, const float* __restrict__ alpha,
+                               const float* __restrict__ dalpha, int64_t n, float scale, float* __restrict__ dz) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kGmWarps + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+    float d = 0.f;
+    for (int s = beg + lane; s < end; s += 32) d = fmaf(__ldg(alpha + s), __ldg(dalpha + s), d);
+    d = gm_warp_sum(d);
+    for (int s = beg + lane; s < end; s += 32) dz[s] = scale * __ldg(alpha + s) * (__ldg(dalpha + s) - d);
+}
+
+}  // namespace gg
+
+extern "C" {
+
+int gg_segment_softmax_f32(const int32_t* rowptr, const float* z, int64_t n, float scale, float* alpha,
+                           gg_stream_t stream) {
+    GG_REQUIRE(n >= 0, "gg_segment_softmax_f32: negative size");
+    if (n == 0) return GG_OK;
+    GG_REQUIRE(rowptr && z && alpha, "gg_segment_softmax_f32: null pointer");
+    gg::segment_softmax_kernel<<<(int)gg::ceil_div(n, gg::kGmWarps), gg::kGmThreads, 0, gg::as_stream(stream)>>>(rowptr, z, n, scale,
+                                                                                                                alpha);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
+int gg_segment_softmax_bwd_f32(const int32_t* rowptr, const float* alpha, const float* dalpha, int64_t n, float scale,
+                               float* dz, gg_stream_t stream) {
+    GG_REQUIRE(n >= 0, "gg_segment_softmax_bwd_f32: negative size");
+    if (n == 0) return GG_OK;
+    GG_REQUIRE(rowptr && alpha && dalpha && dz, "gg_segment_softmax_bwd_f32: null pointer");
+    gg::segment_softmax_bwd_kernel<<<(int)gg::ceil_div(n, gg::kGmWarps), gg::kGmThreads, 0, gg::as_stream(stream)>>>(
+        rowptr, alpha, dalpha, n, scale, dz);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
+}  // extern "C"

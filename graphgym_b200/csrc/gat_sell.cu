@@ -73,9 +73,15 @@ __device__ __forceinline__ float gs_p(float e, float m) { return e == -CUDART_IN
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
     return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
+// index / map units are streamed once: evict_first in L2, so that they do not push out the feature rows (evict_last);
+// the first version used plain loads and moved 24-39 GB of DRAM traffic per pass against 17.5 GB for the plain aggregation
 __device__ __forceinline__ int4 gs_ldg_i4(const int4* p) {
     int4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
     return r;
 }
 
@@ -139,10 +145,12 @@ __global__ void __launch_bounds__(kGsThreads, 3) gat_sell_fwd_kernel(const __gri
     const char* __restrict__ xg = reinterpret_cast<const char*>(a.h) + (act ? gl : nvec - 1) * 16;
     uint32_t row_bytes = (uint32_t)a.ldh * 4u;
     asm volatile("" : "+l"(xg), "+r"(row_bytes));
+    const uint64_t pol_keep = l2_policy(1), pol_stream = l2_policy(2);
+    (void)pol_stream;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto gather = [&](int j) {
         float4 v = zero4;
-        if (j >= 0) v = ldg_nc_f4(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)j * row_bytes));
+        if (j >= 0) v = ldg_nc_f4_hint(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)j * row_bytes), pol_keep);
         return v;
     };
     int chunk = 0;
@@ -260,10 +268,12 @@ __global__ void __launch_bounds__(kGsThreads, 3) gat_sell_bwd_edge_kernel(const 
     const char* __restrict__ xg = reinterpret_cast<const char*>(a.h) + (act ? gl : nvec - 1) * 16;
     uint32_t row_bytes = (uint32_t)a.ldh * 4u;
     asm volatile("" : "+l"(xg), "+r"(row_bytes));
+    const uint64_t pol_keep = l2_policy(1), pol_stream = l2_policy(2);
+    (void)pol_stream;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto gather = [&](int j) {
         float4 v = zero4;
-        if (j >= 0) v = ldg_nc_f4(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)j * row_bytes));
+        if (j >= 0) v = ldg_nc_f4_hint(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)j * row_bytes), pol_keep);
         return v;
     };
     const int kcls = ((gl & (G / 2)) ? 2 : 0) + ((gl & (G / 4)) ? 1 : 0);   // the slot of a unit this lane finishes
@@ -371,10 +381,12 @@ __global__ void __launch_bounds__(kGsThreads, 3) gat_sell_bwd_src_kernel(const _
     const char* __restrict__ xg = reinterpret_cast<const char*>(a.h) + (act ? gl : nvec - 1) * 16;   // a.h = g here
     uint32_t row_bytes = (uint32_t)a.ldh * 4u;
     asm volatile("" : "+l"(xg), "+r"(row_bytes));
+    const uint64_t pol_keep = l2_policy(1), pol_stream = l2_policy(2);
+    (void)pol_stream;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto gather = [&](int j) {
         float4 v = zero4;
-        if (j >= 0) v = ldg_nc_f4(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)j * row_bytes));
+        if (j >= 0) v = ldg_nc_f4_hint(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)j * row_bytes), pol_keep);
         return v;
     };
     int chunk = 0;
@@ -422,7 +434,7 @@ __global__ void __launch_bounds__(kGsThreads, 3) gat_sell_bwd_src_kernel(const _
                     const int k = (gl & 7) + t * GsOwn<G>::kLanes;
                     const int i = gs_pick8(ia, ib, k), ms = gs_pick8(ma, mb, k);
                     ts[t] = i >= 0 ? __ldg(a.tstat + i) : make_float4(0.f, 0.f, 0.f, -1.f);   // .w < 0 marks padding
-                    dzl[t] = ms >= 0 ? __ldg(a.dz_in + ms) : 0.f;
+                    dzl[t] = ms >= 0 ? ldg_nc_f32_hint(a.dz_in + ms, pol_stream) : 0.f;
                 }
                 const float4 v0 = gather(ia.x), v1 = gather(ia.y), v2 = gather(ia.z), v3 = gather(ia.w);
                 const float4 v4 = gather(ib.x), v5 = gather(ib.y), v6 = gather(ib.z), v7 = gather(ib.w);

@@ -22,6 +22,7 @@ from graphgym_b200 import ops
 from graphgym_b200.config import cfg
 from graphgym_b200.contrib.layer import idconv as _idconv  # registers the ID layers
 from graphgym_b200.contrib.layer import generalconv as _generalconv  # registers sageinitconv; GeneralConv is a built-in
+from graphgym_b200.contrib.layer import tfg as _tfg  # registers Tfg-idgcn / Tfg-idsage / Tfg-idgin / Tfg-idgat
 from graphgym_b200.contrib.layer.idconv import _mlp, glorot_, zeros_
 from graphgym_b200.graph import get_layout
 
@@ -197,11 +198,11 @@ _builtin = {
 # built-ins win on a name clash, contrib registrations fill the rest (ref: layer.py:238)
 layer_dict = {**register.layer_dict, **_builtin}
 
-# main_zd.py aliases (ref: main_zd.py:299-308): the Tfg-* names select the same operators
+# main_zd.py names (ref: main_zd.py:299-308).  The four ID layers of TfgIDLayer.py are registered with THEIR semantics
+# (contrib/layer/tfg.py: 'Tfg-idgcn', 'Tfg-idsage', 'Tfg-idgin', 'Tfg-idgat').  The plain Tfg-* layers are tf_geometric's
+# own (un-vendored third party, not in the reference tree): those names select the PyG-semantics operators.
 TFG_ALIASES = {
-    'Tfg-gcnconv': 'gcnconv', 'Tfg-sageconv': 'sageconv', 'Tfg-ginconv': 'ginconv',
-    'Tfg-gatconv': 'gatconv', 'Tfg-idgcn': 'gcnidconv', 'Tfg-idsage': 'sageidconv',
-    'Tfg-idgin': 'ginidconv', 'Tfg-idgat': 'gatidconv',
+    'Tfg-gcnconv': 'gcnconv', 'Tfg-sageconv': 'sageconv', 'Tfg-ginconv': 'ginconv', 'Tfg-gatconv': 'gatconv',
 }
 
 

@@ -768,6 +768,34 @@ def gat_sddmm_slice(csr, h_slice, g_slice):
     return dalpha
 
 
+def sddmm(csr, h, g):
+    """z[s] = <g[row(s), :], h[nbr[s], :]> over the layout's slots (merge-path SDDMM, f % 4 == 0, f <= 1024)."""
+    _need_cuda(h, g)
+    h, ldh = _rows(h, "h")
+    g, ldg = _rows(g, "g")
+    n, f = csr.num_nodes, h.size(1)
+    item_row, item_slot, items = csr.plan
+    z = _f32((csr.num_slots,), h.device)
+    counter = torch.empty(64, dtype=torch.int32, device=h.device)
+    check(lib().gg_gat_sddmm_mp_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(item_row), _ptr(item_slot), items, _ptr(h), ldh,
+                                    _ptr(g), ldg, n, f, _ptr(z), _ptr(counter), _stream()), "gg_gat_sddmm_mp_f32")
+    return z
+
+
+def segment_softmax(csr, z, scale=1.0):
+    alpha = _f32((csr.num_slots,), z.device)
+    check(lib().gg_segment_softmax_f32(_ptr(csr.rowptr), _ptr(z.contiguous()), csr.num_nodes, float(scale), _ptr(alpha),
+                                       _stream()), "gg_segment_softmax_f32")
+    return alpha
+
+
+def segment_softmax_bwd(csr, alpha, dalpha, scale=1.0):
+    dz = _f32((csr.num_slots,), alpha.device)
+    check(lib().gg_segment_softmax_bwd_f32(_ptr(csr.rowptr), _ptr(alpha), _ptr(dalpha.contiguous()), csr.num_nodes,
+                                           float(scale), _ptr(dz), _stream()), "gg_segment_softmax_bwd_f32")
+    return dz
+
+
 # ---- the GAT passes one by one (heads = 1), as the row-partitioned layer composes them ------------------
 def gat_scores(h, att_row):
     """a_tgt[i] = <att[:c], h_i>, a_src[i] = <att[c:], h_i> for the rows of ``h``; ``att_row``: [1, 2c]."""

@@ -480,6 +480,14 @@ int gg_postops_bwd_f32(const float* go, int64_t ld_go, const float* out, int64_t
                        int act, float slope, int l2norm, const float* rownorm, float* dy, int64_t ld_dy, float* dgamma,
                        float* dbeta, void* workspace, size_t workspace_bytes, gg_stream_t stream);
 
+/* Per-row softmax over GIVEN per-slot logits and its backward — the scaled dot-product scorer of the Tfg GAT variant
+ * (ref: TfgIDLayer.py:336-345, sparse_adj.py:136-151): alpha[s] = exp(scale z[s] - max_row) / sum_row;
+ * dz[s] = scale alpha[s] (dalpha[s] - sum_row alpha dalpha).  The logits come from gg_gat_sddmm_mp_f32 (<Q_i, K_j>). */
+int gg_segment_softmax_f32(const int32_t* rowptr, const float* z, int64_t n, float scale, float* alpha,
+                           gg_stream_t stream);
+int gg_segment_softmax_bwd_f32(const int32_t* rowptr, const float* alpha, const float* dalpha, int64_t n, float scale,
+                               float* dz, gg_stream_t stream);
+
 /* GAT (heads = 1) fused into the sliced-ELL aggregation (csrc/gat_sell.cu): alpha never touches memory.
  *   gg_gat_sell_fwd_f32       CSR sliced-ELL layout (gg_sell_build): logits leaky_relu(a_tgt[i] + a_src[j]), online softmax
  *                             fused with out[i] = sum_j alpha_ij h_j (+ bias); rowstat[2 i .. 2 i + 1] = (max, sum of exp)

@@ -21,9 +21,11 @@ def test_registry_names_and_duplicate_key_error():
 
 
 def test_tfg_aliases_cover_main_zd_names():
-    assert set(TFG_ALIASES) == {'Tfg-gcnconv', 'Tfg-sageconv', 'Tfg-gatconv', 'Tfg-ginconv', 'Tfg-idgcn',
-                                'Tfg-idsage', 'Tfg-idgat', 'Tfg-idgin'}
-    assert resolve_layer('Tfg-idsage') is layer_dict['sageidconv']
+    # plain Tfg-* names (tf_geometric's own layers, not in the reference tree) select the PyG-semantics operators; the four
+    # ID layers of TfgIDLayer.py are registered under their main_zd.py names with their own semantics
+    assert set(TFG_ALIASES) == {'Tfg-gcnconv', 'Tfg-sageconv', 'Tfg-gatconv', 'Tfg-ginconv'}
+    assert {'Tfg-idgcn', 'Tfg-idsage', 'Tfg-idgat', 'Tfg-idgin'} <= set(layer_dict)
+    assert resolve_layer('Tfg-idsage') is layer_dict['Tfg-idsage'] and resolve_layer('Tfg-sageconv') is layer_dict['sageconv']
 
 
 def test_parameter_names_match_reference_state_dict():
@@ -103,8 +105,18 @@ def test_new_entry_points_have_no_cpu_path():
         clustering_coefficient(torch.tensor([[0, 1], [1, 0]]), 2)
     with pytest.raises(RuntimeError, match='CUDA tensors only'):
         ops.cast_bf16(x)
-    assert sorted(parallel.ROW_PARTITIONED) == ['gatconv', 'gcnconv', 'gcnidconv', 'ginconv', 'ginidconv', 'sageconv',
-                                                'sageidconv']
+    # round 2: fused post-ops, collation, binning, the Tfg scorer passes
+    from graphgym_b200 import functional as F_
+    from graphgym_b200 import loader
+    from graphgym_b200.contrib.transform import binning
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        F_.post_ops(x, None, True, ops.ACT_RELU, 0.0, True)
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        loader.collate([loader.GraphData(node_feature=x, edge_index=torch.zeros((2, 0), dtype=torch.int64))])
+    with pytest.raises(RuntimeError, match='CUDA tensors only'):
+        binning.argsort_f64(torch.zeros(4, dtype=torch.float64))
+    assert sorted(parallel.ROW_PARTITIONED) == ['gatconv', 'gatidconv', 'gcnconv', 'gcnidconv', 'ginconv', 'ginidconv',
+                                                'idconv', 'sageconv', 'sageidconv']
     assert ops.bf16_gather_ok(128) and not ops.bf16_gather_ok(100) and not ops.bf16_gather_ok(512)
 
 

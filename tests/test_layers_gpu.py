@@ -180,7 +180,7 @@ def test_general_layer_harness_and_tfg_aliases(cuda):
         out = gl(Batch(x, ei, ids)).node_feature
         assert out.shape == (n, 32) and torch.isfinite(out).all()
         out.sum().backward()
-    assert resolve_layer('Tfg-idgcn') is layer_dict['gcnidconv']
+    assert resolve_layer('Tfg-idgcn') is layer_dict['Tfg-idgcn']      # TfgIDLayer.py semantics (contrib/layer/tfg.py)
     assert resolve_layer('Tfg-gcnconv') is layer_dict['gcnconv']
 
 

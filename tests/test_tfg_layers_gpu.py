@@ -1,0 +1,72 @@
+"""The TensorFlow ID-GNN layers of TfgIDLayer.py on the accelerated path (graphgym_b200/contrib/layer/tfg.py) against the
+torch restatement of the reference's own source (oracle/tfg.py; TensorFlow / tf_geometric are not installable here — the
+third-party helper semantics are restated, "parity unpinned" for them), forward and backward, 1e-5 relative."""
+import pytest
+import torch
+
+from graphgym_b200.contrib.layer import tfg
+from graphgym_b200.models.layer import Batch, resolve_layer
+from oracle import tfg as otfg
+from util import FP32_TOL, powerlaw_graph, random_graph, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(layer, x, ei, ids, gy, dev, as_list):
+    layer = layer.to(dev)
+    xg = x.clone().to(dev).requires_grad_(True)
+    if as_list:
+        y = layer([xg, ei.to(dev).int(), ids.to(dev)], training=True)      # the Keras call shape, int32 edge list
+    else:
+        y = layer(Batch(xg, ei.to(dev), ids.to(dev))).node_feature
+    y.backward(gy.to(dev))
+    return y.detach().cpu(), xg.grad.cpu(), {k: p.grad.cpu() for k, p in layer.named_parameters()}
+
+
+def _check(got, want_y, xd, P):
+    y, gx, grads = got
+    assert rel_err(y, want_y.detach()) < FP32_TOL
+    assert torch.allclose(y.double(), want_y.detach(), rtol=1e-4, atol=1e-5)
+    assert rel_err(gx, xd.grad) < FP32_TOL
+    for k, g in grads.items():
+        assert rel_err(g, P[k].grad) < FP32_TOL, k
+
+
+@pytest.mark.parametrize('shape', [(400, 20, 32), (6000, 40, 128)])
+@pytest.mark.parametrize('as_list', [False, True])
+def test_tfg_id_layers_match_the_restated_tensorflow_layers(cuda, shape, as_list):
+    n, fin, units = shape
+    ei = powerlaw_graph(3, n, 10) if n > 1000 else random_graph(4, n, 2500, loops=7, dups=9, symmetric=True)
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(n, fin, generator=g)
+    ids = torch.randperm(n, generator=g)[:n // 8].sort().values
+    gy = torch.randn(n, units, generator=g)
+    torch.manual_seed(1)
+    for name in ('Tfg-idgcn', 'Tfg-idsage', 'Tfg-idgat', 'Tfg-idgin'):
+        layer = resolve_layer(name)(fin, units, bias=True)
+        with torch.no_grad():
+            for p in layer.parameters():
+                if p.dim() == 1:
+                    p.uniform_(-0.3, 0.3)
+        P = {k: v.detach().clone().double().requires_grad_(True) for k, v in layer.named_parameters()}
+        xd = x.double().requires_grad_(True)
+        if name == 'Tfg-idgcn':
+            yo = otfg.gcn_id(xd, ei, ids, P['model.kernel'], P['model.kernel_id'], P['model.bias'])
+        elif name == 'Tfg-idsage':
+            yo = otfg.id_sage(xd, ei, ids, P['model.self_kernel'], P['model.id_kernel'], P['model.neighbor_kernel'], P['model.bias'])
+        elif name == 'Tfg-idgat':
+            yo = otfg.gat_id(xd, ei, ids, P['model.query_kernel'], P['model.query_bias'], P['model.key_kernel'],
+                             P['model.key_bias'], P['model.kernel'], P['model.kernel_id'], P['model.bias'])
+        else:
+            if n > 1000:
+                continue     # GIN's ReLU gates on a hub-heavy graph: covered by the gate rule of test_layers_gpu.py
+            mlp = lambda pre: (lambda h: torch.relu(h @ P[pre + '.0.weight'].t() + P[pre + '.0.bias']) @ P[pre + '.2.weight'].t()
+                               + P[pre + '.2.bias'])
+            yo = otfg.id_gin(xd, ei, ids, mlp('model.mlp_model'), mlp('model.mlp_id'))
+        yo.backward(gy.double())
+        _check(_run(layer, x, ei, ids, gy, cuda, as_list), yo, xd, P)
+
+
+def test_tfg_semantics_differ_from_the_pyg_layers(cuda):
+    """a graph with existing self loops: gcn_id APPENDS loops (TfgIDLayer.py:547-548) where gcnidconv keeps one per node"""
+    assert tfg.TfgIDGCNConv is resolve_layer('Tfg-idgcn') and resolve_layer('Tfg-gcnconv') is resolve_layer('gcnconv')

@@ -17,6 +17,7 @@
 // Rows cut into virtual rows (layout `seg`) carry (max, sum, partial accumulator) / partial sums to small fix-up kernels.
 // Every row is walked by one group of lanes in slot order: deterministic.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -63,6 +64,7 @@ struct GatSellArgs {
     float* pacc;             // [partial rows, f]
     float2* pstat;           // [partial rows]: fwd (max, sum); bwd: (sum, -)
     int* counter;
+    int l2_hint;             // feature rows evict_last, index / map / dz streams evict_first (GG_GAT_L2HINT, default on)
 };
 
 __device__ __forceinline__ float gs_leaky(float z, float slope) { return z > 0.f ? z : slope * z; }
@@ -75,15 +77,14 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
 }
 // index / map units are streamed once: evict_first in L2, so that they do not push out the feature rows (evict_last);
 // the first version used plain loads and moved 24-39 GB of DRAM traffic per pass against 17.5 GB for the plain aggregation
-__device__ __forceinline__ int4 gs_ldg_i4(const int4* p) {
+__device__ __forceinline__ int4 gs_ldg_i4_pol(const int4* p, uint64_t pol) {
     int4 r;
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p), "l"(pol));
     return r;
 }
+#define gs_ldg_i4(p) gs_ldg_i4_pol((p), pol_stream)
 
 // the row a virtual row belongs to: itself, or (piece of a split row) the hub whose partial range holds the piece
 __device__ __forceinline__ int gs_row_of(const GatSellArgs& a, int d) {
@@ -145,8 +146,7 @@ __global__ void __launch_bounds__(kGsThreads, 3) gat_sell_fwd_kernel(const __gri
     const char* __restrict__ xg = reinterpret_cast<const char*>(a.h) + (act ? gl : nvec - 1) * 16;
     uint32_t row_bytes = (uint32_t)a.ldh * 4u;
     asm volatile("" : "+l"(xg), "+r"(row_bytes));
-    const uint64_t pol_keep = l2_policy(1), pol_stream = l2_policy(2);
-    (void)pol_stream;
+    const uint64_t pol_keep = l2_policy(a.l2_hint ? 1 : 0), pol_stream = l2_policy(a.l2_hint ? 2 : 0);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto gather = [&](int j) {
         float4 v = zero4;
@@ -268,8 +268,7 @@ __global__ void __launch_bounds__(kGsThreads, 3) gat_sell_bwd_edge_kernel(const 
     const char* __restrict__ xg = reinterpret_cast<const char*>(a.h) + (act ? gl : nvec - 1) * 16;
     uint32_t row_bytes = (uint32_t)a.ldh * 4u;
     asm volatile("" : "+l"(xg), "+r"(row_bytes));
-    const uint64_t pol_keep = l2_policy(1), pol_stream = l2_policy(2);
-    (void)pol_stream;
+    const uint64_t pol_keep = l2_policy(a.l2_hint ? 1 : 0), pol_stream = l2_policy(a.l2_hint ? 2 : 0);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto gather = [&](int j) {
         float4 v = zero4;
@@ -381,8 +380,7 @@ __global__ void __launch_bounds__(kGsThreads, 3) gat_sell_bwd_src_kernel(const _
     const char* __restrict__ xg = reinterpret_cast<const char*>(a.h) + (act ? gl : nvec - 1) * 16;   // a.h = g here
     uint32_t row_bytes = (uint32_t)a.ldh * 4u;
     asm volatile("" : "+l"(xg), "+r"(row_bytes));
-    const uint64_t pol_keep = l2_policy(1), pol_stream = l2_policy(2);
-    (void)pol_stream;
+    const uint64_t pol_keep = l2_policy(a.l2_hint ? 1 : 0), pol_stream = l2_policy(a.l2_hint ? 2 : 0);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     auto gather = [&](int j) {
         float4 v = zero4;
@@ -515,6 +513,13 @@ static inline int gs_lanes(int64_t f) {
     return nvec <= 4 ? 4 : nvec <= 8 ? 8 : nvec <= 16 ? 16 : 32;
 }
 static inline bool gs_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline int gs_l2_hint() {
+    static const int v = [] {
+        const char* e = getenv("GG_GAT_L2HINT");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return v;
+}
 
 #define GS_DISPATCH(kernel, g, grid, st, a)                                   \
     do {                                                                      \
@@ -585,7 +590,7 @@ int gg_gat_sell_fwd_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t
     a.chunk_ptr = chunk_ptr; a.chunks = (int)chunks; a.idx4 = reinterpret_cast<const int4*>(idx); a.vdst = vdst;
     a.hub_rows = hub_rows; a.hub_pptr = hub_pptr; a.hubs = (int)hubs; a.n = n; a.f = (int)f; a.slope = slope;
     a.h = h; a.ldh = ldh; a.a_tgt = a_tgt; a.a_src = a_src; a.bias = bias; a.out = out; a.ldo = ldo;
-    a.rowstat = reinterpret_cast<float2*>(rowstat); a.pacc = pacc; a.pstat = pstat; a.counter = counter;
+    a.rowstat = reinterpret_cast<float2*>(rowstat); a.pacc = pacc; a.pstat = pstat; a.counter = counter; a.l2_hint = gs_l2_hint();
     GS_DISPATCH(gat_sell_fwd_kernel, g_lanes, gs_main_grid(chunks), st, a);
     GG_LAUNCHED();
     if (hubs > 0) {
@@ -612,7 +617,7 @@ int gg_gat_sell_bwd_edge_f32(const uint32_t* chunk_ptr, int64_t chunks, const in
     a.hubs = (int)hubs; a.n = n; a.f = (int)f; a.slope = slope; a.h = h; a.ldh = ldh; a.g = g; a.ldg = ldg;
     a.fout = fwd_out; a.ldfo = ld_out; a.bias = bias; a.a_tgt = a_tgt; a.a_src = a_src;
     a.rowstat = reinterpret_cast<float2*>(const_cast<float*>(rowstat)); a.dz = dz; a.da = da_tgt; a.pacc = pacc;
-    a.pstat = pstat; a.counter = counter;
+    a.pstat = pstat; a.counter = counter; a.l2_hint = gs_l2_hint();
     GS_DISPATCH(gat_sell_bwd_edge_kernel, g_lanes, gs_main_grid(chunks), st, a);
     GG_LAUNCHED();
     if (hubs > 0) {
@@ -644,6 +649,7 @@ int gg_gat_sell_bwd_src_f32(const uint32_t* chunk_ptr, int64_t chunks, const int
     a.hubs = (int)hubs; a.n = n; a.f = (int)f; a.slope = slope; a.h = g; a.ldh = ldg; a.a_src = a_src;
     a.tstat = reinterpret_cast<const float4*>(tstat_scratch); a.dz_in = dz; a.da_tgt_in = da_tgt; a.att_src = att_src;
     a.att_tgt = att_tgt; a.out = dh; a.ldo = ld_dh; a.da = da_src; a.pacc = pacc; a.pstat = pstat; a.counter = counter;
+    a.l2_hint = gs_l2_hint();
     GS_DISPATCH(gat_sell_bwd_src_kernel, g_lanes, gs_main_grid(chunks), st, a);
     GG_LAUNCHED();
     if (hubs > 0) {

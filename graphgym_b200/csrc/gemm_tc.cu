@@ -753,7 +753,7 @@ static inline size_t tc_image_floats(int64_t k, int64_t f) {
 using namespace gg;
 
 // The tensor core accumulates with truncation: the result is biased towards zero by ~6e-9 * K relative
-// (measured, scratch/tc_err_probe.py).  To stay inside 1e-5 for any K the reduction is cut into launches
+// (measured, profiles/probes/tc_err_probe.py).  To stay inside 1e-5 for any K the reduction is cut into launches
 // of at most kTcMaxKPerLaunch = 256 k (bias <= 1.6e-6); each launch's partial tile is added to `out` in
 // fp32 (round to nearest) by the next launch's epilogue.  GNN hidden sizes (K <= 256) take one launch.
 constexpr int kTcMaxKPerLaunch = 256;

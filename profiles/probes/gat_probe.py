@@ -1,6 +1,6 @@
 """Per-pass times of the GAT layer on the products-shaped graph: fused sliced-ELL passes vs the split merge-path passes."""
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 import bench
 from graphgym_b200 import ops
 from graphgym_b200.graph import GraphLayout

@@ -2,10 +2,10 @@
 slots at F/P columns and is slot-rate bound (43 G slots/s, DRAM row activations).  Here the sources are cut into K blocks
 whose column slice fits the L2; block b's sub-layout is aggregated into the same output (accumulating epilogue).
 
-    gpurun -- 'python scratch/l2block_probe.py'
+    gpurun -- 'python profiles/probes/l2block_probe.py'
 """
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 import bench
 from graphgym_b200 import ops
 dev = torch.device('cuda')

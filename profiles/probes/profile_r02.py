@@ -2,7 +2,7 @@
 build), edge-softmax passes (split: gat_alpha / sddmm / dz; fused: gat_sell_*), ego-net BFS, closed-walk kernels — on the
 shapes the benches use."""
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 import bench
 from graphgym_b200 import ops
 from graphgym_b200.graph import GraphLayout

@@ -1,7 +1,7 @@
 """ncu target: the sliced-ELL aggregation at F = 16 and 32 on the products-shaped graph (what a rank of the 8- / 4-GPU
 feature-sliced exchange runs), plus the fused post-ops at F = 128."""
 import sys, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 import bench
 from graphgym_b200 import ops, functional as F_
 dev = torch.device('cuda')

@@ -1,6 +1,6 @@
 """Times the sliced-ELL aggregation against the grouped-slot merge-path kernel on the products-shaped graph, all rows."""
 import sys, time, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))))
 import bench
 from graphgym_b200 import ops
 dev = torch.device('cuda')

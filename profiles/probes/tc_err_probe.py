@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))); sys.path.insert(0, '/root/repo/tests')
 from graphgym_b200 import ops
 from util import rel_err
 dev = torch.device('cuda')

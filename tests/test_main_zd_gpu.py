@@ -23,3 +23,49 @@ def test_driver_plain_layer_on_synthetic_batch(cuda):
     from graphgym_b200 import main_zd
     r = main_zd.main(['--model', 'Tfg-sageconv', '--epochs', '2'])[0]
     assert r['graphs'] == 64 and r['train_loss'] == r['train_loss']
+
+
+def test_cfg_a_stack_matches_the_fp64_oracle(cuda, golden_dir):
+    """Cfg-A: graphs [0:16] of datasets/scalefree.pkl, 3-hop ego-nets on the device (sizes equal to the
+    reference's own transform.py), X = ones, then the stage GraphGym builds for idgcn_tf — 3 x GeneralLayer('gcnidconv')
+    with BatchNorm1d (batch statistics) + ReLU and the stage's final L2 normalisation — against the oracle layers
+    (oracle/layers.py::gcn_idconv) + torch's own BatchNorm1d / relu / normalize in float64, forward and backward."""
+    import numpy as np
+    import torch
+    import torch.nn.functional as Fn
+    from graphgym_b200.config import reset_cfg
+    from graphgym_b200.models import transform as gtr
+    from graphgym_b200.models.gnn import GNNStackStage
+    from graphgym_b200.models.layer import Batch
+    from oracle import layers as olayers
+    from util import FP32_TOL, rel_err
+    reset_cfg()
+    d = np.load(os.path.join(golden_dir, 'scalefree16.npz'))
+    ei = torch.from_numpy(d['edge_index']).to(cuda)
+    gp = torch.from_numpy(d['graph_ptr']).to(cuda).int()
+    n = int(d['graph_ptr'][-1])
+    res = gtr.ego_nets_batch(ei, n, 3, gp)
+    per_graph = (res['out_node_ptr'][1:] - res['out_node_ptr'][:-1]).cpu().numpy()
+    assert np.array_equal(per_graph, d['ego_nodes'])
+    assert int(res['edge_index'].size(1)) == 2 * int(d['ego_undirected_edges'].sum())
+    eo, ids, n_out = res['edge_index'], res['node_id_index'], res['num_nodes']
+    torch.manual_seed(0)
+    stage = GNNStackStage(1, 32, 3, 'gcnidconv').to(cuda)
+    x = torch.ones(n_out, 1, device=cuda, requires_grad=True)
+    gy = torch.randn(n_out, 32, generator=torch.Generator().manual_seed(1)).to(cuda)
+    out = stage(Batch(x, eo, ids)).node_feature
+    out.backward(gy)
+    # oracle
+    P = {k: v.detach().cpu().double().requires_grad_(True) for k, v in stage.named_parameters()}
+    h = torch.ones(n_out, 1, dtype=torch.float64)
+    eo_c, ids_c = eo.cpu(), ids.cpu()
+    for i in range(3):
+        h = olayers.gcn_idconv(h, eo_c, ids_c, P[f'layer{i}.layer.model.weight'], P[f'layer{i}.layer.model.weight_id'], None)
+        h = Fn.batch_norm(h, None, None, P[f'layer{i}.post_layer.0.weight'], P[f'layer{i}.post_layer.0.bias'], True, 0.1, 1e-5)
+        h = torch.relu(h)
+    h = Fn.normalize(h, p=2, dim=1)
+    h.backward(gy.cpu().double())
+    assert rel_err(out.detach(), h.detach()) < 5e-5          # three BN + ReLU layers deep: 1e-5 per layer accumulates
+    for k, v in stage.named_parameters():
+        assert rel_err(v.grad, P[k].grad) < 2e-4, k           # ReLU gates near zero may differ between fp32 and fp64
+    reset_cfg()

@@ -53,23 +53,27 @@ __global__ void __launch_bounds__(32) peer_barrier_kernel(const __grid_constant_
 
 // ---- column-slice scatter -------------------------------------------------------------------------
 // dst[c][(row_base + i) * fs + k] = src[i * ld + c * fs + k],  c = 0..world-1, fs = f / world.
-// One 16-byte vector per thread and iteration, enumerated in DESTINATION order (peer, row, column): a warp's store is
-// 512 contiguous bytes in one peer — full NVLink packets — while its loads are fs*4-byte pieces of consecutive local rows
-// (cheap: local, and the neighbouring warps read the rest of the same lines).  The first version walked the source rows
-// and left fs*4-byte stores per peer: 0.34 ms for 137 MB at 8 GPUs (64-byte packets, profiles/r02 N=8 trace).
+// One 16-byte vector per lane; a WARP owns a chunk of 32 consecutive vectors of ONE peer's destination (512 contiguous
+// bytes = full NVLink packets) and consecutive warps go to different peers, starting from rank + 1: at any moment every
+// rank writes to every peer.  History (8 GPUs, 137 MB per rank, profiles/r02 traces): walking the source rows left
+// fs*4 = 64-byte stores (0.34 ms + 0.02 ms drain at the barrier); enumerating peer-major made all ranks sweep the same
+// peer at the same time (0.23 ms + 0.27 ms drain: the destination's ingress is shared by the 8 senders).
 __global__ void __launch_bounds__(256) peer_scatter_cols_kernel(const float* __restrict__ src, int64_t ld,
                                                                 int64_t rows, int f, int fs,
                                                                 const __grid_constant__ PeerPtrs dst,
-                                                                int64_t row_base) {
-    const int svec = fs >> 2;
-    const int64_t per_peer = rows * svec;
-    const int64_t total = per_peer * (f / fs);
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(e / per_peer);
-        const int64_t rem = e - (int64_t)c * per_peer;
-        const int64_t i = rem / svec;
-        const int k = (int)(rem - i * svec);
+                                                                int64_t row_base, int rank) {
+    const int svec = fs >> 2, world = f / fs;
+    const int64_t per_peer = rows * svec;                       // vectors per peer
+    const int64_t chunks_per_peer = (per_peer + 31) >> 5;
+    const int64_t total_chunks = chunks_per_peer * world;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < total_chunks; q += nwarps) {
+        const int c = (int)((q % world + rank + 1) % world);
+        const int64_t v = (q / world) * 32 + lane;
+        if (v >= per_peer) continue;
+        const int64_t i = v / svec;
+        const int k = (int)(v - i * svec);
         const float4 val = __ldg(reinterpret_cast<const float4*>(src + i * ld + (int64_t)c * fs) + k);
         reinterpret_cast<float4*>(static_cast<float*>(dst.p[c]) + (row_base + i) * fs)[k] = val;
     }
@@ -77,17 +81,22 @@ __global__ void __launch_bounds__(256) peer_scatter_cols_kernel(const float* __r
 
 // Return leg of the feature-sliced exchange as a bulk push: this rank's finished slice src[n, fs] (all rows, its fs
 // columns) goes to the rows' owners; owner o receives rows [o * per, (o + 1) * per) as ONE contiguous block
-// recv_o[rank][i][k] (slice-major), so every warp store is 512 contiguous bytes in one peer.  (Storing the rows from the
-// aggregation kernel's epilogue — 64-byte pieces at random rows — cost 0.45 ms on top of a 0.61 ms kernel at 8 GPUs.)
+// recv_o[rank][i][k] (slice-major).  Same striping as the scatter: a warp stores 512 contiguous bytes into one owner,
+// consecutive warps serve different owners.  (Storing the rows from the aggregation kernel's epilogue — 64-byte pieces at
+// random rows — cost 0.45 ms on top of a 0.61 ms kernel at 8 GPUs.)
 __global__ void __launch_bounds__(256) peer_push_rows_kernel(const float* __restrict__ src, int64_t n, int fs, int64_t per,
-                                                             int rank, const __grid_constant__ PeerPtrs dst) {
+                                                             int rank, int world, const __grid_constant__ PeerPtrs dst) {
     const int svec = fs >> 2;
-    const int64_t total = n * svec;
     const int64_t per_vec = per * svec;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        const int o = (int)(e / per_vec);
-        const int64_t rem = e - (int64_t)o * per_vec;
+    const int64_t chunks_per_owner = (per_vec + 31) >> 5;
+    const int64_t total_chunks = chunks_per_owner * world;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < total_chunks; q += nwarps) {
+        const int o = (int)((q % world + rank + 1) % world);
+        const int64_t rem = (q / world) * 32 + lane;             // vector inside the owner's block
+        const int64_t e = (int64_t)o * per_vec + rem;            // vector inside src
+        if (rem >= per_vec || e >= n * svec) continue;
         const float4 val = __ldg(reinterpret_cast<const float4*>(src) + e);
         reinterpret_cast<float4*>(static_cast<float*>(dst.p[o]) + (int64_t)rank * per * fs)[rem] = val;
     }
@@ -167,9 +176,10 @@ int gg_peer_barrier(void* const* flags_host, int world, int rank, gg_stream_t st
 }
 
 int gg_peer_scatter_cols_f32(const float* src, int64_t ld, int64_t rows, int64_t f, float* const* dst_host,
-                             int world, int64_t row_base, gg_stream_t stream) {
+                             int world, int rank, int64_t row_base, gg_stream_t stream) {
     GG_REQUIRE(rows >= 0 && f >= 0 && row_base >= 0, "gg_peer_scatter_cols_f32: negative size");
-    GG_REQUIRE(dst_host && world >= 1 && world <= GG_PEER_MAX, "gg_peer_scatter_cols_f32: world=%d", world);
+    GG_REQUIRE(dst_host && world >= 1 && world <= GG_PEER_MAX && rank >= 0 && rank < world,
+               "gg_peer_scatter_cols_f32: world=%d rank=%d", world, rank);
     if (rows == 0 || f == 0) return GG_OK;
     GG_REQUIRE(f % (4 * world) == 0, "gg_peer_scatter_cols_f32: f=%lld must be a multiple of 4*world=%d",
                (long long)f, 4 * world);
@@ -186,7 +196,7 @@ int gg_peer_scatter_cols_f32(const float* src, int64_t ld, int64_t rows, int64_t
     if (grid > (int64_t)kNumSMs * 8) grid = (int64_t)kNumSMs * 8;
     if (grid < 1) grid = 1;
     peer_scatter_cols_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(src, ld, rows, (int)f, (int)(f / world), d,
-                                                                      row_base);
+                                                                      row_base, rank);
     GG_LAUNCHED();
     return GG_OK;
 }
@@ -210,7 +220,7 @@ int gg_peer_push_rows_f32(const float* src, int64_t n, int64_t fs, int64_t rows_
     int64_t total = n * (fs / 4);
     int64_t grid = ceil_div(total, 256 * 4);
     if (grid > (int64_t)kNumSMs * 8) grid = (int64_t)kNumSMs * 8;
-    peer_push_rows_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(src, n, (int)fs, rows_per_rank, rank, d);
+    peer_push_rows_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(src, n, (int)fs, rows_per_rank, rank, world, d);
     GG_LAUNCHED();
     return GG_OK;
 }

@@ -369,11 +369,11 @@ def sliced_width(f, world):
     return f // world
 
 
-def _peer_scatter_cols(local, ptrs, row_base):
+def _peer_scatter_cols(local, ptrs, row_base, rank):
     local, ld = ops._rows(local, 'local')
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
     check(lib().gg_peer_scatter_cols_f32(ctypes.c_void_p(local.data_ptr()), ld, local.size(0), local.size(1), arr,
-                                         len(ptrs), int(row_base),
+                                         len(ptrs), int(rank), int(row_base),
                                          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
           'gg_peer_scatter_cols_f32')
 
@@ -393,7 +393,7 @@ def _to_slices(playout, local):
         pool = playout.pool
         xs = pool.get(('slice', n, fs), n * fs * 4)
         _mark('enter')
-        _peer_scatter_cols(local, xs.ptrs, part.lo)
+        _peer_scatter_cols(local, xs.ptrs, part.lo, part.rank)
         _mark('scattered')
         pool.barrier()                                       # my slice is complete
         _mark('barrier1')

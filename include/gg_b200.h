@@ -556,7 +556,7 @@ int gg_peer_close(void* ptr);
 int gg_peer_free(void* ptr);
 int gg_peer_barrier(void* const* flags_host, int world, int rank, gg_stream_t stream);
 int gg_peer_scatter_cols_f32(const float* src, int64_t ld, int64_t rows, int64_t f, float* const* dst_host,
-                             int world, int64_t row_base, gg_stream_t stream);
+                             int world, int rank, int64_t row_base, gg_stream_t stream);
 /* Return leg of the feature-sliced exchange as a bulk push (the alternative to the peer-output epilogue of the
  * aggregation kernels): gg_peer_push_rows_f32 sends this rank's finished slice src[n, fs] to the rows' owners — owner o
  * receives rows [o * rows_per_rank, ...) as one contiguous block recv_o[rank][i][0:fs] (recv_host: HOST array of `world`

@@ -83,7 +83,7 @@ SIGNATURES = {
     "gg_peer_free": (c_int, [c_ptr]),
     "gg_peer_barrier": (c_int, [ctypes.POINTER(c_ptr), c_int, c_int, c_ptr]),
     "gg_peer_scatter_cols_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, ctypes.POINTER(c_ptr), c_int, c_int, c_i64, c_ptr]),
-    "gg_peer_push_rows_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_int, c_int, ctypes.POINTER(c_ptr), c_ptr]),
+    "gg_peer_push_rows_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_int, c_int, c_int, c_int, ctypes.POINTER(c_ptr), c_ptr]),
     "gg_peer_gather_slices_f32": (c_int, [c_ptr, c_i64, c_i64, c_i64, c_int, c_ptr, c_i64, c_ptr]),
     "gg_id_gemm_f32": (c_int, [ctypes.POINTER(GemmSegment), c_int, c_int, c_i64, c_i64, c_ptr, c_int,
                                c_ptr, c_i64, c_ptr, c_i64, c_ptr]),

@@ -85,16 +85,17 @@ __global__ void __launch_bounds__(256) peer_scatter_cols_kernel(const float* __r
 // consecutive warps serve different owners.  (Storing the rows from the aggregation kernel's epilogue — 64-byte pieces at
 // random rows — cost 0.45 ms on top of a 0.61 ms kernel at 8 GPUs.)
 __global__ void __launch_bounds__(256) peer_push_rows_kernel(const float* __restrict__ src, int64_t n, int fs, int64_t per,
-                                                             int rank, int world, const __grid_constant__ PeerPtrs dst) {
+                                                             int rank, int owner_begin, int owners,
+                                                             const __grid_constant__ PeerPtrs dst) {
     const int svec = fs >> 2;
     const int64_t per_vec = per * svec;
     const int64_t chunks_per_owner = (per_vec + 31) >> 5;
-    const int64_t total_chunks = chunks_per_owner * world;
+    const int64_t total_chunks = chunks_per_owner * owners;
     const int lane = threadIdx.x & 31;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < total_chunks; q += nwarps) {
-        const int o = (int)((q % world + rank + 1) % world);
-        const int64_t rem = (q / world) * 32 + lane;             // vector inside the owner's block
+        const int o = owner_begin + (int)((q % owners + rank + 1) % owners);
+        const int64_t rem = (q / owners) * 32 + lane;            // vector inside the owner's block
         const int64_t e = (int64_t)o * per_vec + rem;            // vector inside src
         if (rem >= per_vec || e >= n * svec) continue;
         const float4 val = __ldg(reinterpret_cast<const float4*>(src) + e);
@@ -202,8 +203,11 @@ int gg_peer_scatter_cols_f32(const float* src, int64_t ld, int64_t rows, int64_t
 }
 
 int gg_peer_push_rows_f32(const float* src, int64_t n, int64_t fs, int64_t rows_per_rank, int world, int rank,
-                          float* const* recv_host, gg_stream_t stream) {
+                          int owner_begin, int owner_end, float* const* recv_host, gg_stream_t stream) {
     GG_REQUIRE(n >= 0 && fs >= 0 && rows_per_rank >= 1, "gg_peer_push_rows_f32: bad sizes");
+    GG_REQUIRE(owner_begin >= 0 && owner_begin <= owner_end && owner_end <= world,
+               "gg_peer_push_rows_f32: owners [%d, %d) outside [0, %d)", owner_begin, owner_end, world);
+    if (owner_begin == owner_end) return GG_OK;
     GG_REQUIRE(recv_host && world >= 1 && world <= GG_PEER_MAX && rank >= 0 && rank < world &&
                    rows_per_rank * world >= n,
                "gg_peer_push_rows_f32: world=%d rank=%d rows_per_rank=%lld do not cover %lld rows", world, rank,
@@ -217,10 +221,12 @@ int gg_peer_push_rows_f32(const float* src, int64_t n, int64_t fs, int64_t rows_
                    "gg_peer_push_rows_f32: destination %d null or misaligned", i);
         d.p[i] = recv_host[i];
     }
-    int64_t total = n * (fs / 4);
+    int64_t total = rows_per_rank * (owner_end - owner_begin) * (fs / 4);
     int64_t grid = ceil_div(total, 256 * 4);
     if (grid > (int64_t)kNumSMs * 8) grid = (int64_t)kNumSMs * 8;
-    peer_push_rows_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(src, n, (int)fs, rows_per_rank, rank, world, d);
+    if (grid < 1) grid = 1;
+    peer_push_rows_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(src, n, (int)fs, rows_per_rank, rank, owner_begin,
+                                                                   owner_end - owner_begin, d);
     GG_LAUNCHED();
     return GG_OK;
 }

@@ -560,10 +560,12 @@ int gg_peer_scatter_cols_f32(const float* src, int64_t ld, int64_t rows, int64_t
 /* Return leg of the feature-sliced exchange as a bulk push (the alternative to the peer-output epilogue of the
  * aggregation kernels): gg_peer_push_rows_f32 sends this rank's finished slice src[n, fs] to the rows' owners — owner o
  * receives rows [o * rows_per_rank, ...) as one contiguous block recv_o[rank][i][0:fs] (recv_host: HOST array of `world`
- * DEVICE pointers to the owners' receive buffers of world * rows_per_rank * fs floats); after a gg_peer_barrier the owner
+ * DEVICE pointers to the owners' receive buffers of world * rows_per_rank * fs floats); only the owners in
+ * [owner_begin, owner_end) are served by a call, so that the push of one owner group can run on a second stream while the
+ * next group's rows are still being aggregated; after a gg_peer_barrier the owner
  * assembles out[i, c * fs + k] = recv[c][i][k] with gg_peer_gather_slices_f32 (local). */
 int gg_peer_push_rows_f32(const float* src, int64_t n, int64_t fs, int64_t rows_per_rank, int world, int rank,
-                          float* const* recv_host, gg_stream_t stream);
+                          int owner_begin, int owner_end, float* const* recv_host, gg_stream_t stream);
 int gg_peer_gather_slices_f32(const float* recv, int64_t rows_per_rank, int64_t rows, int64_t fs, int world, float* out,
                               int64_t ldo, gg_stream_t stream);
 

@@ -62,9 +62,10 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = 'products_gcn'
 DEFAULT_HALO = 'sliced'
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE aggregation launch from an `ncu --set full` capture of this bench
-# (profiles/r01_spmm_mpg128_final_ncu_raw.csv: spmm_mpg_kernel<32,1,0> 17.51 + 1.32 GB in 4.12 ms; the algorithmic figure
-# is 34.7 GB — the L2 serves the rest)
-NCU_TRAFFIC = {'products_gcn': 18_829_800_000}
+# (profiles/r02_spmm_sell128_bench_ncu_raw.csv: spmm_sell_kernel<32,1,0> 18.58 + 1.27 GB in 3.26 ms = 6.1 TB/s = 0.93 of
+# the measured copy peak; the algorithmic figure is 34.7 GB — the L2 serves the rest).  Keyed by (workload, kernel): a
+# line produced with another aggregation kernel reports null.
+NCU_TRAFFIC = {('products_gcn', 'sell'): 19_850_000_000, ('products_gcn', 'mpg'): 18_829_800_000}
 HALO_DESC = {
     'allgather': 'halo all-gather of the feature rows over NCCL, rank-local SpMM',
     'pipelined': 'P-1 NCCL send/recv rounds overlapped with the per-peer SpMMs',
@@ -722,12 +723,16 @@ def run_ours(args, spec, rank, world, dev):
                           + ((' — rank 0 of %d, ' % world) + ('all rows x F/%d columns (sub-warp-group kernel, rows stored '
                              'to their owners over NVLink)' % world if playout.sliced else 'rank-local rows') if multi else ''),
                 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
-                'frac': round(achieved / peak, 4), 'traffic': NCU_TRAFFIC.get(args.workload) if not (multi or half) else None,
+                'frac': round(achieved / peak, 4),
+                'traffic': NCU_TRAFFIC.get((args.workload, 'sell' if ops.SPMM_ALGO == 'auto' else ops.SPMM_ALGO)) if not (multi or half) else None,
                 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': per_launch_bytes,
                 'avg_launch_ms': round(avg_spmm_ms, 4), 'launches_timed': len(spmm_ms),
+                'frac_dram': None,   # filled below: ncu DRAM traffic / this run's launch time / peak
                 'share_of_step': round(sum(spmm_ms) / args.steps / ms, 3)}
 
+    if roofline['traffic']:
+        roofline['frac_dram'] = round(roofline['traffic'] / (avg_spmm_ms * 1e-3) / 1e9 / peak, 4)
     # ---- layout build alone (amortised over layers/epochs in training; reported, not in `value`) ---
     clear_cache()
     sync_all()

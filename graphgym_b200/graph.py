@@ -14,6 +14,12 @@ from . import ops
 
 _CACHE = OrderedDict()
 _CACHE_MAX = 16
+# A cached layout holds its edge_index, CSR + CSC, weights and the sliced-ELL re-layouts: ~85 bytes per edge, 5 GB for the
+# 62 M-edge products graph.  Sixteen of those would be 80 GB of HBM that the caching allocator has to cudaMalloc step by
+# step (measured: the e2e leg of bench.py went from 38 to 104 ms per step as the cache filled).  The cache is therefore
+# bounded by edges as well: the newest entries whose edge counts sum to at most _CACHE_MAX_EDGES stay (always at least two:
+# the step in flight and the one being built by a prefetching loader).
+_CACHE_MAX_EDGES = 1 << 27
 
 
 class GraphLayout:
@@ -91,6 +97,8 @@ def get_layout(edge_index, num_nodes, policy):
     lay = GraphLayout(edge_index, num_nodes, policy)
     _CACHE[key] = lay
     while len(_CACHE) > _CACHE_MAX:
+        _CACHE.popitem(last=False)
+    while len(_CACHE) > 2 and sum(int(v.edge_index.size(1)) for v in _CACHE.values()) > _CACHE_MAX_EDGES:
         _CACHE.popitem(last=False)
     return lay
 

@@ -217,7 +217,7 @@ def test_peer_output_and_column_scatter_on_one_gpu(cuda, world, f_total):
         lo, hi = min(n, r * per), min(n, (r + 1) * per)
         dst = (ctypes.c_void_p * world)(*[s.data_ptr() for s in slices])
         ops.check(L.gg_peer_scatter_cols_f32(ctypes.c_void_p(x[lo:hi].data_ptr()), f_total, hi - lo, f_total, dst,
-                                             world, lo, ops._stream()), 'gg_peer_scatter_cols_f32')
+                                             world, r, lo, ops._stream()), 'gg_peer_scatter_cols_f32')
     for c in range(world):
         assert torch.equal(slices[c], x[:, c * fs:(c + 1) * fs])
     blocks = [torch.full((per, f_total), float('nan'), device=cuda) for _ in range(world)]
@@ -229,6 +229,25 @@ def test_peer_output_and_column_scatter_on_one_gpu(cuda, world, f_total):
     want = ops.spmm(csr, x, w, ops.SUM, None, 0.0, bias)
     assert not torch.isnan(got).any()
     assert rel_err(got, want) < FP32_TOL
+    # the bulk-push return leg: local slice -> gg_peer_push_rows_f32 (whole world, then owner group by owner group) ->
+    # gg_peer_gather_slices_f32 on every owner; bitwise the fused-return result
+    for groups in ([(0, world)], [(o, o + 1) for o in range(world)]):
+        recv = [torch.full((world * per * fs,), float('nan'), device=cuda) for _ in range(world)]
+        arr = (ctypes.c_void_p * world)(*[t.data_ptr() for t in recv])
+        for c in range(world):
+            out_slice = ops.spmm(csr, slices[c], w, ops.SUM, None, 0.0, bias[c * fs:(c + 1) * fs].clone())
+            for o0, o1 in groups:
+                ops.check(L.gg_peer_push_rows_f32(ctypes.c_void_p(out_slice.data_ptr()), n, fs, per, world, c, o0, o1, arr,
+                                                  ops._stream()), 'gg_peer_push_rows_f32')
+        rows_out = []
+        for o in range(world):
+            rows = min(n, (o + 1) * per) - min(n, o * per)
+            res = torch.empty((rows, f_total), device=cuda)
+            ops.check(L.gg_peer_gather_slices_f32(ctypes.c_void_p(recv[o].data_ptr()), per, rows, fs, world,
+                                                  ctypes.c_void_p(res.data_ptr()), f_total, ops._stream()),
+                      'gg_peer_gather_slices_f32')
+            rows_out.append(res)
+        assert torch.equal(torch.cat(rows_out), got)
 
 
 @pytest.mark.parametrize('f', [16, 32, 64, 128])

@@ -65,6 +65,8 @@ SIGNATURES = {
     "gg_sell_build": (c_int, [c_ptr, c_ptr, c_i64, c_i64, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                               c_size, c_ptr]),
     "gg_sell_permute_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
+    "gg_sell_hub_hint_workspace_bytes": (c_size, [c_i64]),
+    "gg_sell_hub_hint": (c_int, [c_ptr, c_i64, c_i64, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_size, c_ptr]),
     "gg_spmm_sell_workspace_bytes": (c_size, [c_i64, c_i64]),
     "gg_spmm_sell_f32": (c_int, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_i64, c_ptr,
                                  c_i64, c_ptr, c_int, c_i64, c_i64, c_i64, c_int, c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_ptr,

@@ -143,6 +143,48 @@ __global__ void __launch_bounds__(256) sell_fill_kernel(const int32_t* __restric
     }
 }
 
+// ---- hub hint ----------------------------------------------------------------------------------------------------
+// The feature matrix is ~10x the L2 on the products graph and every gather used to be tagged evict_last: rows referenced
+// a handful of times (most of a power-law graph) evicted the rows referenced thousands of times just as often as the
+// other way round — L2 hit rate 35 %, 18.6 GB of DRAM reads for 33 GB of gathers at the DRAM roofline (0.93 of the copy
+// peak, profiles/r02_spmm_sell128_bench_ncu_raw.csv).  With the hint, bit 30 of an index marks a HUB source — one of the
+// ~`hubs` most referenced nodes, whose rows fit the L2 together — and the kernel keeps hub rows (evict_last) while it
+// streams the others through (evict_first).  Caching only: the results are bitwise unchanged.
+constexpr int32_t kSellHubBit = 1 << 30;
+constexpr int kSellFreqBins = 4096;
+
+__global__ void __launch_bounds__(256) sell_freq_kernel(const int32_t* __restrict__ nbr, int64_t slots, int32_t* __restrict__ freq) {
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(freq + nbr[s], 1);      // integer counts: the order of the additions does not matter
+}
+__global__ void __launch_bounds__(256) sell_freq_hist_kernel(const int32_t* __restrict__ freq, int64_t n, int32_t* __restrict__ bins) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = freq[i];
+        atomicAdd(bins + (f < kSellFreqBins ? f : kSellFreqBins - 1), 1);
+    }
+}
+// smallest threshold T >= 1 with #{freq >= T} <= hubs  (one thread: 4096 bins)
+__global__ void sell_freq_threshold_kernel(const int32_t* __restrict__ bins, int64_t hubs, int32_t* __restrict__ threshold) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int64_t above = 0;
+    int t = kSellFreqBins;          // nothing qualifies
+    for (int b = kSellFreqBins - 1; b >= 1; --b) {
+        if (above + bins[b] > hubs) break;
+        above += bins[b];
+        t = b;
+    }
+    *threshold = t;
+}
+__global__ void __launch_bounds__(256) sell_hub_flag_kernel(const int32_t* __restrict__ idx, int64_t total,
+                                                            const int32_t* __restrict__ freq,
+                                                            const int32_t* __restrict__ threshold, int32_t* __restrict__ out) {
+    const int t = *threshold;
+    for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < total; d += (int64_t)gridDim.x * blockDim.x) {
+        const int j = idx[d];
+        out[d] = (j >= 0 && freq[j] >= t) ? (j | kSellHubBit) : j;
+    }
+}
+
 __global__ void __launch_bounds__(256) sell_permute_kernel(const int32_t* __restrict__ slot_of, int64_t total,
                                                            const float* __restrict__ src, float* __restrict__ dst) {
     for (int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; d < total; d += (int64_t)gridDim.x * blockDim.x) {
@@ -184,6 +226,7 @@ struct SellArgs {
     float* partial;   // [partial rows, f]
     int* counter;
     int l2_hint;
+    int hub_hint;     // bit 30 of an index marks a hub source (gg_sell_hub_hint): hubs evict_last, the rest evict_first
 };
 
 template <bool PEER>
@@ -237,9 +280,13 @@ __global__ void __launch_bounds__(kSellThreads, G >= 16 ? 3 : 4)
     const uint64_t pol_keep = l2_policy(a.l2_hint ? 1 : 0), pol_stream = l2_policy(a.l2_hint ? 2 : 0);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const int4 none4 = make_int4(-1, -1, -1, -1);
+    const bool hub_hint = a.hub_hint != 0;
     auto gather = [&](int j) {
         float4 v = zero4;
-        if (j >= 0) v = ldg_nc_f4_hint(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)j * row_bytes), pol_keep);
+        if (j >= 0) {
+            const uint64_t pol = (hub_hint && !(j & kSellHubBit)) ? pol_stream : pol_keep;
+            v = ldg_nc_f4_hint(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)(j & ~kSellHubBit) * row_bytes), pol);
+        }
         return v;
     };
 
@@ -438,6 +485,39 @@ int gg_sell_build(const int32_t* rowptr, const int32_t* nbr, int64_t num_rows, i
     return GG_OK;
 }
 
+size_t gg_sell_hub_hint_workspace_bytes(int64_t num_nodes) {
+    return 512 + align_up((size_t)(num_nodes > 0 ? num_nodes : 1) * 4, 256) + align_up((size_t)kSellFreqBins * 4, 256);
+}
+
+int gg_sell_hub_hint(const int32_t* nbr, int64_t num_slots, int64_t num_nodes, const int32_t* idx, int64_t total,
+                     int64_t hubs, int32_t* idx_hint, void* workspace, size_t workspace_bytes, gg_stream_t stream) {
+    GG_REQUIRE(num_slots >= 0 && num_nodes >= 0 && total >= 0 && hubs >= 0, "gg_sell_hub_hint: negative size");
+    GG_REQUIRE(num_nodes < kSellHubBit, "gg_sell_hub_hint: node ids need bit 30");
+    if (total == 0) return GG_OK;
+    GG_REQUIRE(idx && idx_hint && workspace && (num_slots == 0 || nbr), "gg_sell_hub_hint: null pointer");
+    if (workspace_bytes < gg_sell_hub_hint_workspace_bytes(num_nodes)) {
+        set_error("gg_sell_hub_hint: workspace %zu < %zu", workspace_bytes, gg_sell_hub_hint_workspace_bytes(num_nodes));
+        return GG_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    Carver c(workspace);
+    int32_t* threshold = c.take<int32_t>(64);
+    int32_t* freq = c.take<int32_t>(num_nodes > 0 ? num_nodes : 1);
+    int32_t* bins = c.take<int32_t>(kSellFreqBins);
+    GG_CUDA(cudaMemsetAsync(workspace, 0, gg_sell_hub_hint_workspace_bytes(num_nodes), st));
+    if (num_slots > 0) {
+        sell_freq_kernel<<<sell_grid(num_slots, 256 * 4), 256, 0, st>>>(nbr, num_slots, freq);
+        GG_LAUNCHED();
+    }
+    sell_freq_hist_kernel<<<sell_grid(num_nodes, 256), 256, 0, st>>>(freq, num_nodes, bins);
+    GG_LAUNCHED();
+    sell_freq_threshold_kernel<<<1, 32, 0, st>>>(bins, hubs, threshold);
+    GG_LAUNCHED();
+    sell_hub_flag_kernel<<<sell_grid(total, 256 * 4), 256, 0, st>>>(idx, total, freq, threshold, idx_hint);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
 int gg_sell_permute_f32(const int32_t* slot_of, int64_t total, const float* src, float* dst, gg_stream_t stream) {
     GG_REQUIRE(total >= 0, "gg_sell_permute_f32: negative size");
     if (total == 0) return GG_OK;
@@ -501,7 +581,7 @@ int gg_spmm_sell_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* i
     GG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
     SellArgs a{chunk_ptr, (int)chunks, reinterpret_cast<const int4*>(idx), reinterpret_cast<const float4*>(w_sell), vdst,
                rowptr, hub_rows, hub_pptr, (int)hubs, x, ldx, out, ldo, (int)f, reduce, x_self, ld_self, self_scale,
-               bias, r1_s, r1_v, r2_s, r2_v, partial, counter, (flags & 4) ? 1 : 0};
+               bias, r1_s, r1_v, r2_s, r2_v, partial, counter, (flags & 4) ? 1 : 0, (flags & 8) ? 1 : 0};
     const int nvec = (int)(f / 4);
     if (nvec <= 4) launch_sell<4>(a, po, peer, st);
     else if (nvec <= 8) launch_sell<8>(a, po, peer, st);

@@ -241,7 +241,10 @@ def _spmm_bf16(csr, x, w_slot, reduce, x_self, self_scale, bias):
 
 
 SELL_SEG = int(_os.environ.get("GG_SELL_SEG", "256"))   # rows longer than this are cut into virtual rows (multiple of 4)
-SELL_MAX_F = int(_os.environ.get("GG_SELL_MAX_F", "128"))   # auto: widths up to this run on the sliced-ELL kernel
+SELL_MAX_F = int(_os.environ.get("GG_SELL_MAX_F", "128"))
+# hub hint of the sliced-ELL aggregation: rows of the ~SELL_HUB_BYTES / (4 f) most referenced source nodes are kept in L2,
+# the rest is streamed (0 = off).  Only used when the gathered matrix does not fit the L2 anyway.
+SELL_HUB_BYTES = int(_os.environ.get("GG_SELL_HUB_MB", "64")) << 20   # auto: widths up to this run on the sliced-ELL kernel
 
 
 class SellLayout:
@@ -268,6 +271,22 @@ class SellLayout:
         # layout alive until Python's cycle collector runs — measured as +3.5 GiB of HBM per e2e step)
         self.total = 4 * self.units        # entries of idx / slot_of in use (the arrays keep their capacity)
         self._w = None
+        self._hint = {}                    # hubs -> idx with the hub bit (gg_sell_hub_hint)
+        self._nbr, self._n, self._slots = csr.nbr, n, slots
+
+    def idx_hint(self, hubs):
+        """idx with bit 30 marking the `hubs` most referenced sources (built once per hub count)."""
+        hit = self._hint.get(hubs)
+        if hit is None:
+            L = lib()
+            dev = self.idx.device
+            hit = torch.empty_like(self.idx)
+            ws_bytes = int(L.gg_sell_hub_hint_workspace_bytes(self._n))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            check(L.gg_sell_hub_hint(_ptr(self._nbr), self._slots, self._n, _ptr(self.idx), self.total, int(hubs), _ptr(hit),
+                                     _ptr(ws), ws_bytes, _stream()), "gg_sell_hub_hint")
+            self._hint = {hubs: hit}
+        return hit
 
     def weights(self, w_slot):
         """Per-slot weights re-laid in unit order (padding = 0).  The last permutation is kept (a cached GCN norm hits
@@ -298,11 +317,17 @@ def _spmm_sell(csr, x, ldx, x_ptr, w_slot, reduce, x_self, ld_self, self_scale, 
     ws_bytes = int(L.gg_spmm_sell_workspace_bytes(sl.partial_rows, f))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
     peers = (out_peers._arr, len(out_peers.ptrs), out_peers.rows_per_rank) if out_peers is not None else (None, 1, max(csr.num_nodes, 1))
-    check(L.gg_spmm_sell_f32(_ptr(sl.chunk_ptr), sl.chunks, _ptr(sl.idx), _ptr(sl.weights(w_slot)), _ptr(sl.vdst),
+    idx, flags = sl.idx, _spmm_flags()
+    # hub hint: only when the gathered matrix is (much) larger than what the hint keeps resident
+    if SELL_HUB_BYTES and x.size(0) * f * 4 > 2 * SELL_HUB_BYTES and (flags & 4):
+        # hub count in powers of two: the hint array is rebuilt only when the width class changes
+        hubs = 1 << max(10, (SELL_HUB_BYTES // (4 * f)).bit_length() - 1)
+        idx, flags = sl.idx_hint(hubs), flags | 8
+    check(L.gg_spmm_sell_f32(_ptr(sl.chunk_ptr), sl.chunks, _ptr(idx), _ptr(sl.weights(w_slot)), _ptr(sl.vdst),
                              _ptr(csr.rowptr), _ptr(sl.hub_rows), _ptr(sl.hub_pptr), sl.hubs, sl.partial_rows, x_ptr, ldx,
                              _ptr(out), ldo, peers[0], peers[1], peers[2], csr.num_nodes, f, reduce, _ptr(x_self), ld_self,
                              float(self_scale), _ptr(bias), _ptr(r1[0]), _ptr(r1[1]), _ptr(r1[2]), _ptr(r1[3]), _ptr(ws),
-                             ws_bytes, _spmm_flags(), _stream()), "gg_spmm_sell_f32")
+                             ws_bytes, flags, _stream()), "gg_spmm_sell_f32")
 
 
 class PeerRows:

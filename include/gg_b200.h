@@ -218,6 +218,13 @@ int gg_sell_build(const int32_t* rowptr, const int32_t* nbr, int64_t num_rows, i
                   uint32_t* chunk_ptr, int32_t* idx, int32_t* slot_of, int32_t* vdst, int32_t* hub_rows,
                   int32_t* hub_pptr, int32_t* info, void* workspace, size_t workspace_bytes, gg_stream_t stream);
 int gg_sell_permute_f32(const int32_t* slot_of, int64_t total, const float* src, float* dst, gg_stream_t stream);
+/* Hub hint (caching only, results bitwise unchanged): idx_hint[d] = idx[d] with bit 30 set when the source node is one of
+ * the ~`hubs` most referenced nodes of the layout (reference counts from `nbr`; the threshold is the smallest count T with
+ * #{count >= T} <= hubs).  gg_spmm_sell_f32 with flags bit 3 set and idx = idx_hint keeps hub rows in L2 (evict_last) and
+ * streams the others (evict_first).  Workspace: gg_sell_hub_hint_workspace_bytes(num_nodes). */
+size_t gg_sell_hub_hint_workspace_bytes(int64_t num_nodes);
+int gg_sell_hub_hint(const int32_t* nbr, int64_t num_slots, int64_t num_nodes, const int32_t* idx, int64_t total,
+                     int64_t hubs, int32_t* idx_hint, void* workspace, size_t workspace_bytes, gg_stream_t stream);
 size_t gg_spmm_sell_workspace_bytes(int64_t partial_rows, int64_t f);
 int gg_spmm_sell_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const float* w_sell,
                      const int32_t* vdst, const int32_t* rowptr, const int32_t* hub_rows, const int32_t* hub_pptr,

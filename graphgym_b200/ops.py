@@ -244,7 +244,8 @@ SELL_SEG = int(_os.environ.get("GG_SELL_SEG", "256"))   # rows longer than this 
 SELL_MAX_F = int(_os.environ.get("GG_SELL_MAX_F", "128"))
 # hub hint of the sliced-ELL aggregation: rows of the ~SELL_HUB_BYTES / (4 f) most referenced source nodes are kept in L2,
 # the rest is streamed (0 = off).  Only used when the gathered matrix does not fit the L2 anyway.
-SELL_HUB_BYTES = int(_os.environ.get("GG_SELL_HUB_MB", "64")) << 20   # auto: widths up to this run on the sliced-ELL kernel
+SELL_HUB_BYTES = int(_os.environ.get("GG_SELL_HUB_MB", "32")) << 20
+SELL_HUB_MIN_F = 64   # below this width the kernel is latency bound, not DRAM bound: the hint measures as noise   # auto: widths up to this run on the sliced-ELL kernel
 
 
 class SellLayout:
@@ -319,7 +320,7 @@ def _spmm_sell(csr, x, ldx, x_ptr, w_slot, reduce, x_self, ld_self, self_scale, 
     peers = (out_peers._arr, len(out_peers.ptrs), out_peers.rows_per_rank) if out_peers is not None else (None, 1, max(csr.num_nodes, 1))
     idx, flags = sl.idx, _spmm_flags()
     # hub hint: only when the gathered matrix is (much) larger than what the hint keeps resident
-    if SELL_HUB_BYTES and x.size(0) * f * 4 > 2 * SELL_HUB_BYTES and (flags & 4):
+    if SELL_HUB_BYTES and f >= SELL_HUB_MIN_F and x.size(0) * f * 4 > 2 * SELL_HUB_BYTES and (flags & 4):
         # hub count in powers of two: the hint array is rebuilt only when the width class changes
         hubs = 1 << max(10, (SELL_HUB_BYTES // (4 * f)).bit_length() - 1)
         idx, flags = sl.idx_hint(hubs), flags | 8

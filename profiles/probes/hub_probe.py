@@ -24,7 +24,7 @@ def timeit(fn, it=6):
 
 for f in (128, 64, 16):
     x = torch.randn(n, f, device=dev)
-    ops.SELL_HUB_BYTES = 0
+    ops.SELL_HUB_BYTES, ops.SELL_HUB_MIN_F = 0, 0
     ref = ops.spmm(csr, x, w, algo='sell')
     line = [f'f={f}: off {timeit(lambda: ops.spmm(csr, x, w, algo="sell")):.3f} ms']
     for mb in (16, 32, 48, 64, 96):

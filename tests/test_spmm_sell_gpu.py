@@ -115,3 +115,34 @@ def test_rank1_terms_nonfinite_row0_and_empty(cuda):
     empty = ops.layout_build(torch.zeros((2, 0), dtype=torch.int64, device=cuda), 7, 0, 0)
     out = ops.spmm(empty, torch.randn(7, 8, device=cuda), None, ops.SUM, bias=torch.ones(8, device=cuda), algo='sell')
     assert torch.equal(out, torch.ones(7, 8, device=cuda))
+
+
+def test_hub_hint_marks_the_most_referenced_sources_and_changes_nothing(cuda, monkeypatch):
+    """gg_sell_hub_hint: bit 30 set exactly on the entries whose source is referenced at least T times, T the smallest
+    count with #{count >= T} <= hubs; the aggregation with the hint is bitwise the one without."""
+    n, f = 30000, 64
+    ei = powerlaw_graph(5, n, 16)
+    csr = ops.layout_build(ei.to(cuda), n, 1, 0)
+    sl = ops.sell_layout(csr)
+    hubs = 1024
+    hint = sl.idx_hint(hubs).cpu().numpy()[:sl.total]
+    idx = sl.idx.cpu().numpy()[:sl.total]
+    freq = np.bincount(csr.nbr.cpu().numpy(), minlength=n)
+    counts = np.bincount(np.minimum(freq, 4095), minlength=4096)
+    above, t = 0, 4096
+    for b in range(4095, 0, -1):
+        if above + counts[b] > hubs:
+            break
+        above += counts[b]
+        t = b
+    valid = idx >= 0
+    assert (hint[~valid] == -1).all()
+    assert ((hint[valid] & ~(1 << 30)) == idx[valid]).all()
+    assert (((hint[valid] >> 30) & 1) == (freq[idx[valid]] >= t)).all()
+    assert 0 < ((hint[valid] >> 30) & 1).sum() < valid.sum()
+    x = torch.randn(n, f, device=cuda, generator=torch.Generator(device=cuda).manual_seed(0))
+    w = ops.gcn_norm(csr, ops.segment_degree(csr))
+    monkeypatch.setattr(ops, 'SELL_HUB_BYTES', 0)
+    ref = ops.spmm(csr, x, w, algo='sell')
+    monkeypatch.setattr(ops, 'SELL_HUB_BYTES', 1 << 18)       # 256 KB: far below the 7.7 MB matrix -> the hint engages
+    assert torch.equal(ops.spmm(csr, x, w, algo='sell'), ref)

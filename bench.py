@@ -136,10 +136,14 @@ class ClockSampler:
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index=0):
-        self.samples, self.proc, self.index = [], None, index
+    def __init__(self, index=0, enabled=True):
+        # only the rank that prints the line samples: eight nvidia-smi pollers at 20 ms contend for the driver and the
+        # host cores the ranks need to enqueue their own work
+        self.samples, self.proc, self.index, self.enabled = [], None, index, enabled
 
     def __enter__(self):
+        if not self.enabled:
+            return self
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
                                           '--format=csv,noheader,nounits', '-lms', '20'],
@@ -356,7 +360,7 @@ def run_aux(args, spec, dev, rank=0, world=1):
     from graphgym_b200.models import transform as gtr
     from graphgym_b200.models.layer import Batch, layer_dict
     peak, peak_src = load_peaks()
-    clocks = ClockSampler(dev.index or 0)
+    clocks = ClockSampler(dev.index or 0, enabled=(rank == 0))
     sync_all, max_over_ranks, sum_over_ranks = _aux_dist(world, dev)
     par = 'single GPU' if world == 1 else f'{world} GPUs, independent units per rank (no data-path collective)'
     if spec['aux'] == 'cycles':
@@ -685,7 +689,7 @@ def run_ours(args, spec, rank, world, dev):
     slots = slots_local if (multi and playout.sliced) else int(sum_over_ranks(slots_local))
     torch.cuda.synchronize()
     layout_first_s = time.time() - t0
-    clocks = ClockSampler(dev.index or 0)
+    clocks = ClockSampler(dev.index or 0, enabled=(rank == 0))
     clocks.__enter__()   # sampled at 20 ms from the warm-up on: short timed regions still get samples under load
     for _ in range(args.warmup):
         step(x_loc, ei, playout)

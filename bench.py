@@ -65,7 +65,7 @@ DEFAULT_HALO = 'sliced'
 # (profiles/r02_spmm_sell128_bench_ncu_raw.csv: spmm_sell_kernel<32,1,0> 18.58 + 1.27 GB in 3.26 ms = 6.1 TB/s = 0.93 of
 # the measured copy peak; the algorithmic figure is 34.7 GB — the L2 serves the rest).  Keyed by (workload, kernel): a
 # line produced with another aggregation kernel reports null.
-NCU_TRAFFIC = {('products_gcn', 'sell', 128): 19_850_000_000, ('products_gcn', 'mpg', 128): 18_829_800_000}
+NCU_TRAFFIC = {('products_gcn', 'sell'): 19_850_000_000, ('products_gcn', 'mpg'): 18_829_800_000}
 HALO_DESC = {
     'allgather': 'halo all-gather of the feature rows over NCCL, rank-local SpMM',
     'pipelined': 'P-1 NCCL send/recv rounds overlapped with the per-peer SpMMs',
@@ -573,8 +573,6 @@ def run_ours(args, spec, rank, world, dev):
     multi = world > 1
     from graphgym_b200.config import cfg as gg_cfg
     gg_cfg.b200.gather_dtype = args.gather_dtype
-    if args.gather_dtype == 'bf16':
-        gg_cfg.b200.gcn_order = 'transform_first'   # the bf16 gather needs f % 8 == 0: aggregate the 128-wide H as in round 1
     half = args.gather_dtype == 'bf16' and not multi
     if multi:
         if name not in parallel.ROW_PARTITIONED:
@@ -719,11 +717,7 @@ def run_ours(args, spec, rank, world, dev):
 
     spmm_ms = [s.elapsed_time(e) for s, e in spmm_events]
     weighted = name in ('gcnconv', 'gcnidconv', 'gatconv', 'gatidconv')
-    # width the aggregation kernel actually runs at: F/P per rank in the sliced exchange; single-GPU gcnconv aggregates on
-    # the narrower side (A(XW) = (AX)W, cfg.b200.gcn_order) — the roofline counts the bytes of the launched width, the
-    # metric keeps SURVEY §8d's definition (E' x F_out x 2 for GCN)
-    gcn_agg_first = (name == 'gcnconv' and not multi and gg_cfg.b200.gcn_order == 'auto' and fin < fout and fin % 4 == 0)
-    f_launch = f_agg // world if (multi and playout.sliced) else (fin if gcn_agg_first else f_agg)
+    f_launch = f_agg // world if (multi and playout.sliced) else f_agg
     per_launch_bytes = spmm_bytes(rows_local, slots_local, f_launch, weighted, 2 if half else 4)
     avg_spmm_ms = float(np.mean(spmm_ms)) if spmm_ms else float('nan')
     peak, peak_src = load_peaks()
@@ -734,7 +728,7 @@ def run_ours(args, spec, rank, world, dev):
                              'to their owners over NVLink)' % world if playout.sliced else 'rank-local rows') if multi else ''),
                 'achieved': round(achieved, 1), 'peak': peak, 'unit': 'GB/s',
                 'frac': round(achieved / peak, 4),
-                'traffic': NCU_TRAFFIC.get((args.workload, 'sell' if ops.SPMM_ALGO == 'auto' else ops.SPMM_ALGO, f_launch)) if not (multi or half) else None,
+                'traffic': NCU_TRAFFIC.get((args.workload, 'sell' if ops.SPMM_ALGO == 'auto' else ops.SPMM_ALGO)) if not (multi or half) else None,
                 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': per_launch_bytes,
                 'avg_launch_ms': round(avg_spmm_ms, 4), 'launches_timed': len(spmm_ms),
@@ -884,9 +878,6 @@ def run_ours(args, spec, rank, world, dev):
         'data': 'synthetic (seeded power-law / BA / uniform generators in bench.py; random-init glorot weights)',
         'config': {'workload': spec['desc'], 'layer': name, 'nodes': n, 'edges_directed': int(ei.size(1)),
                    'slots_after_loop_policy': slots, 'f_in': fin, 'f_out': fout, 'f_aggregated': f_agg,
-                   'aggregation_width_launched': f_launch,
-                   'operator_order': 'aggregate then transform, (A X) W — same output as the reference order A (X W) up to fp32 '
-                                     're-association; metric numerator per SURVEY 8d (F_out)' if gcn_agg_first else 'reference order',
                    'parallelism': ('row-partitioned x%d, exchange fwd and bwd: %s' % (world, HALO_DESC[halo])) if multi
                    else 'single GPU',
                    'l2_policy': 'inputs larger than L2 (feature matrix %.0f MB vs 126 MB L2)' % (n * f_agg * 4 / 1e6)

@@ -32,9 +32,7 @@ def _defaults():
     # not a reference key: storage type of the operand the aggregation gathers.  'f32' = the reference's arithmetic
     # (1e-5 parity); 'bf16' = the north star's 1e-2 mode (rows gathered in bf16, fp32 products and sums)
     # fused_postops: GeneralLayer's BN / activation / L2 as one fused pass (False = the nn modules one by one)
-    # gcn_order: 'auto' = gcnconv aggregates before the dense transform when dim_in < dim_out (A(XW) = (AX)W; the
-    # aggregation is HBM bound and follows the row width); 'transform_first' = the reference's order always
-    c.b200 = _Node(gather_dtype='f32', fused_postops=True, gcn_order='auto')
+    c.b200 = _Node(gather_dtype='f32', fused_postops=True)
     return c
 
 

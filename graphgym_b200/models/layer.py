@@ -44,15 +44,9 @@ class _GCNConvLayer(nn.Module):
 
     def forward(self, x, edge_index):
         n = x.size(0)
-        layout = get_layout(edge_index, n, ops.LOOPS_ADD_REMAINING)
-        if cfg.b200.gcn_order == 'auto' and self.in_channels < self.out_channels and self.in_channels % 4 == 0:
-            # A_hat (X W) = (A_hat X) W: aggregate on the NARROWER side, then transform (bias in the GEMM epilogue).  The
-            # aggregation is HBM bound, so its time follows the row width — 100 instead of 128 columns on the products
-            # workload, forward and backward (dX = A_hat^T (g W^T)).  Same layer output up to fp32 re-association.
-            z = F_.aggregate(x, layout, 'gcn_tgt')
-            return F_.seg_linear([z], [self.weight], [(0, 0, False)], None, self.bias)
         h = F_.seg_linear([x], [self.weight], [(0, 0, False)])
-        return F_.aggregate(h, layout, 'gcn_tgt', 0.0, self.bias)
+        return F_.aggregate(h, get_layout(edge_index, n, ops.LOOPS_ADD_REMAINING), 'gcn_tgt', 0.0,
+                            self.bias)
 
 
 class _SAGEConvLayer(nn.Module):

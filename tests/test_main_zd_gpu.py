@@ -53,7 +53,12 @@ def test_cfg_a_stack_matches_the_fp64_oracle(cuda, golden_dir):
     stage = GNNStackStage(1, 32, 3, 'gcnidconv').to(cuda)
     x = torch.ones(n_out, 1, device=cuda, requires_grad=True)
     gy = torch.randn(n_out, 32, generator=torch.Generator().manual_seed(1)).to(cuda)
-    out = stage(Batch(x, eo, ids)).node_feature
+    b = Batch(x, eo, ids)
+    gates = []
+    for layer in stage.children():      # the stage's own forward, layer by layer, to read the ReLU gates it took
+        b = layer(b)
+        gates.append((b.node_feature.detach() > 0).cpu().double())
+    out = b.node_feature
     out.backward(gy)
     # oracle
     P = {k: v.detach().cpu().double().requires_grad_(True) for k, v in stage.named_parameters()}
@@ -62,10 +67,18 @@ def test_cfg_a_stack_matches_the_fp64_oracle(cuda, golden_dir):
     for i in range(3):
         h = olayers.gcn_idconv(h, eo_c, ids_c, P[f'layer{i}.layer.model.weight'], P[f'layer{i}.layer.model.weight_id'], None)
         h = Fn.batch_norm(h, None, None, P[f'layer{i}.post_layer.0.weight'], P[f'layer{i}.post_layer.0.bias'], True, 0.1, 1e-5)
-        h = torch.relu(h)
+        # gradients are compared under the gates the implementation took (the rule of test_layers_gpu._check_gates): a
+        # pre-activation within rounding of zero may gate differently in fp32 and fp64; such disagreements must be tiny
+        flipped = (h.detach() > 0) != (gates[i] > 0)
+        if flipped.any():
+            assert float(h.detach()[flipped].abs().max() / h.detach().abs().max()) < 1e-4
+        h = h * gates[i]
     h = Fn.normalize(h, p=2, dim=1)
     h.backward(gy.cpu().double())
     assert rel_err(out.detach(), h.detach()) < 5e-5          # three BN + ReLU layers deep: 1e-5 per layer accumulates
     for k, v in stage.named_parameters():
-        assert rel_err(v.grad, P[k].grad) < 2e-4, k           # ReLU gates near zero may differ between fp32 and fp64
+        # layer 0 sees X = ones: its BatchNorm output is invariant to the scale of W, so dW is a difference of large
+        # terms (|dW| ~ 4e3 from O(1) rows) and amplifies the fp32 rounding of everything above it
+        tol = 2e-3 if k.startswith('layer0.layer') else 2e-4
+        assert rel_err(v.grad, P[k].grad) < tol, k
     reset_cfg()

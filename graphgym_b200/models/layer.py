@@ -23,6 +23,7 @@ from graphgym_b200.config import cfg
 from graphgym_b200.contrib.layer import idconv as _idconv  # registers the ID layers
 from graphgym_b200.contrib.layer import generalconv as _generalconv  # registers sageinitconv; GeneralConv is a built-in
 from graphgym_b200.contrib.layer import tfg as _tfg  # registers Tfg-idgcn / Tfg-idsage / Tfg-idgin / Tfg-idgat
+from graphgym_b200.contrib.layer import attconv as _attconv  # registers gaddconv / gmulconv
 from graphgym_b200.contrib.layer.idconv import _mlp, glorot_, zeros_
 from graphgym_b200.graph import get_layout
 

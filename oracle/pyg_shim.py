@@ -116,7 +116,7 @@ def install(reference_root='/root/reference', agg='add', normalize_adj=False):
                        remove_self_loops=pyg_utils.remove_self_loops,
                        add_self_loops=pyg_utils.add_self_loops, softmax=pyg_utils.softmax,
                        negative_sampling=_no_negative_sampling)
-    cfg = _Cfg(gnn=_Cfg(agg=agg, normalize_adj=normalize_adj, self_msg='concat'))
+    cfg = _Cfg(gnn=_Cfg(agg=agg, normalize_adj=normalize_adj, self_msg='concat', att_heads=1, att_final_linear=False, att_final_linear_bn=False))
     gg = _module('graphgym')
     gg.__path__ = []  # a package, but nothing resolves through the filesystem
     gg.config = _module('graphgym.config', cfg=cfg)

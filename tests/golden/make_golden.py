@@ -251,6 +251,11 @@ def contrib_layers(ns):
             tags.append(run_layer(ns, 'generalconv', kw, n=41, fin=12, fout=16, seed=500 + len(tags), out=out,
                                   suffix='_selfmsg-' + self_msg))
     tags.append(run_layer(ns, 'sageinitconv', {}, n=53, fin=20, fout=24, seed=600, out=out))
+    # gaddconv / gmulconv (attconv.py:14-240), default cfg (att_heads = 1, agg add, no normalisation); a wide case too
+    pyg_shim._load('graphgym.contrib.layer.attconv', os.path.join(root, 'contrib/layer/attconv.py'))
+    for name in ('gaddconv', 'gmulconv'):
+        tags.append(run_layer(ns, name, {}, n=47, fin=12, fout=16, seed=700 + len(tags), out=out))
+        tags.append(run_layer(ns, name, {}, n=61, fin=20, fout=136, seed=720 + len(tags), out=out, suffix='_wide'))
     tags.append(run_layer(ns, 'idconv', {'agg': 'mean', 'normalize_adj': True}, n=37, fin=12, fout=16, seed=601, out=out))
     out['tags'] = np.array(tags)
     np.savez_compressed(os.path.join(HERE, 'contrib_layers.npz'), **out)

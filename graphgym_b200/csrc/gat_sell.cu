@@ -65,6 +65,14 @@ struct GatSellArgs {
     float2* pstat;           // [partial rows]: fwd (max, sum); bwd: (sum, -)
     int* counter;
     int l2_hint;             // feature rows evict_last, index / map / dz streams evict_first (GG_GAT_L2HINT, default on)
+    const float* own;        // bwd_one: the row owner's matrix (h of the SOURCE rows); a.h holds the gathered g
+    int64_t ld_own;
+    // training forward: the part of the aggregation that comes through positive logits (see gat_sell_bwd_one_kernel)
+    float* out_pos;          // [n, ld_pos]: sum over {e : z_e > 0} alpha_e h_j
+    int64_t ld_pos;
+    float* a_pos;            // [n]: sum over {e : z_e > 0} alpha_e
+    float* pacc2;            // split rows
+    float* ps2;
 };
 
 __device__ __forceinline__ float gs_leaky(float z, float slope) { return z > 0.f ? z : slope * z; }
@@ -137,8 +145,11 @@ __device__ __forceinline__ float gs_bcast(const float (&loc)[GsOwn<G>::kPer], in
 }
 
 // ---- forward -------------------------------------------------------------------------------------------------------
-template <int G>
-__global__ void __launch_bounds__(kGsThreads, 3) gat_sell_fwd_kernel(const __grid_constant__ GatSellArgs a) {
+// TRAIN: also accumulates out_pos / a_pos, the share of the aggregation that arrives through positive logits.  The backward
+// needs da_tgt_i = sum_e dz_e; because sum_e alpha_e (dalpha_e - D_i) = 0 and lrelu' is 1 or `slope`, that sum equals
+// (1 - slope) (<g_i, out_pos_i> - D_i a_pos_i): a per-node dot product instead of a transposition of 62 M per-edge values.
+template <int G, bool TRAIN>
+__device__ __forceinline__ void gat_sell_fwd_body(const GatSellArgs& a) {
     constexpr int S = 32 / G, P = kGsRows / S;
     const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
     const int nvec = a.f >> 2;
@@ -173,8 +184,8 @@ __global__ void __launch_bounds__(kGsThreads, 3) gat_sell_fwd_kernel(const __gri
             const int row = gs_row_of(a, d);
             const float at = row >= 0 ? __ldg(a.a_tgt + row) : 0.f;
             const int4* __restrict__ ip = a.idx4 + base + q;
-            float m = -CUDART_INF_F, s = 0.f;
-            float4 acc = zero4;
+            float m = -CUDART_INF_F, s = 0.f, s2 = 0.f;
+            float4 acc = zero4, acc2 = zero4;
             for (int k4 = 0; k4 < nk; k4 += 2) {
                 const int4 ia = na, ib = nb;
                 {   // next pair: of this row, or the first of the chunk's next row
@@ -212,6 +223,22 @@ __global__ void __launch_bounds__(kGsThreads, 3) gat_sell_fwd_kernel(const __gri
                 fma4(acc, p0, v0); fma4(acc, p1, v1); fma4(acc, p2, v2); fma4(acc, p3, v3);
                 fma4(acc, p4, v4); fma4(acc, p5, v5); fma4(acc, p6, v6); fma4(acc, p7, v7);
                 s = fmaf(s, sc, ((p0 + p1) + (p2 + p3)) + ((p4 + p5) + (p6 + p7)));
+                if constexpr (TRAIN) {
+                    // which slots have a positive logit (leaky(z) > 0 <=> z > 0): one ballot per owned slot, read at the
+                    // owner's lane, instead of eight more broadcasts
+                    unsigned pm[GsOwn<G>::kPer];
+#pragma unroll
+                    for (int t = 0; t < GsOwn<G>::kPer; ++t) pm[t] = __ballot_sync(0xffffffffu, e[t] > 0.f);
+                    auto pos = [&](int k, float pk) {
+                        return ((pm[k / GsOwn<G>::kLanes] >> (grp * G + k % GsOwn<G>::kLanes)) & 1u) ? pk : 0.f;
+                    };
+                    const float q0 = pos(0, p0), q1 = pos(1, p1), q2 = pos(2, p2), q3 = pos(3, p3);
+                    const float q4 = pos(4, p4), q5 = pos(5, p5), q6 = pos(6, p6), q7 = pos(7, p7);
+                    acc2.x *= sc; acc2.y *= sc; acc2.z *= sc; acc2.w *= sc;
+                    fma4(acc2, q0, v0); fma4(acc2, q1, v1); fma4(acc2, q2, v2); fma4(acc2, q3, v3);
+                    fma4(acc2, q4, v4); fma4(acc2, q5, v5); fma4(acc2, q6, v6); fma4(acc2, q7, v7);
+                    s2 = fmaf(s2, sc, ((q0 + q1) + (q2 + q3)) + ((q4 + q5) + (q6 + q7)));
+                }
                 m = mn;
             }
             if (d >= 0) {
@@ -220,16 +247,37 @@ __global__ void __launch_bounds__(kGsThreads, 3) gat_sell_fwd_kernel(const __gri
                     float4 r = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
                     if (a.bias) add4(r, __ldg(reinterpret_cast<const float4*>(a.bias) + gl));
                     reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[gl] = r;
+                    if constexpr (TRAIN)
+                        reinterpret_cast<float4*>(a.out_pos + (int64_t)row * a.ld_pos)[gl] =
+                            make_float4(acc2.x * inv, acc2.y * inv, acc2.z * inv, acc2.w * inv);
                 }
-                if (gl == 0) a.rowstat[row] = make_float2(m, s);
+                if (gl == 0) {
+                    a.rowstat[row] = make_float2(m, s);
+                    if constexpr (TRAIN) a.a_pos[row] = s2 * inv;
+                }
             } else if (d != kGsNoRow) {
                 const int pr = -d - 1;
-                if (act) reinterpret_cast<float4*>(a.pacc + (int64_t)pr * a.f)[gl] = acc;
-                if (gl == 0) a.pstat[pr] = make_float2(m, s);
+                if (act) {
+                    reinterpret_cast<float4*>(a.pacc + (int64_t)pr * a.f)[gl] = acc;
+                    if constexpr (TRAIN) reinterpret_cast<float4*>(a.pacc2 + (int64_t)pr * a.f)[gl] = acc2;
+                }
+                if (gl == 0) {
+                    a.pstat[pr] = make_float2(m, s);
+                    if constexpr (TRAIN) a.ps2[pr] = s2;
+                }
             }
         }
         chunk = __shfl_sync(0xffffffffu, next, 0);
     }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kGsThreads, 3) gat_sell_fwd_eval_kernel(const __grid_constant__ GatSellArgs a) {
+    gat_sell_fwd_body<G, false>(a);
+}
+template <int G>
+__global__ void __launch_bounds__(kGsThreads, 3) gat_sell_fwd_train_kernel(const __grid_constant__ GatSellArgs a) {
+    gat_sell_fwd_body<G, true>(a);
 }
 
 // split rows: merge the pieces' (max, sum, accumulator) in piece order
@@ -241,13 +289,17 @@ __global__ void __launch_bounds__(256) gat_sell_fwd_fixup_kernel(const __grid_co
         const int p0 = __ldg(a.hub_pptr + hb), p1 = __ldg(a.hub_pptr + hb + 1);
         float M = -CUDART_INF_F;
         for (int p = p0; p < p1; ++p) M = fmaxf(M, a.pstat[p].x);
-        float S = 0.f;
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        float S = 0.f, S2 = 0.f;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f), r2 = r;
         for (int p = p0; p < p1; ++p) {
             const float2 st = a.pstat[p];
             const float w = gs_p(st.x, M);
             S = fmaf(st.y, w, S);
             fma4(r, w, reinterpret_cast<const float4*>(a.pacc + (int64_t)p * a.f)[gl]);
+            if (a.out_pos) {
+                S2 = fmaf(a.ps2[p], w, S2);
+                fma4(r2, w, reinterpret_cast<const float4*>(a.pacc2 + (int64_t)p * a.f)[gl]);
+            }
         }
         const float inv = 1.0f / (S + 1e-16f);
         r.x *= inv; r.y *= inv; r.z *= inv; r.w *= inv;
@@ -255,6 +307,11 @@ __global__ void __launch_bounds__(256) gat_sell_fwd_fixup_kernel(const __grid_co
         const int row = __ldg(a.hub_rows + hb);
         reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[gl] = r;
         if (gl == 0) a.rowstat[row] = make_float2(M, S);
+        if (a.out_pos) {
+            reinterpret_cast<float4*>(a.out_pos + (int64_t)row * a.ld_pos)[gl] =
+                make_float4(r2.x * inv, r2.y * inv, r2.z * inv, r2.w * inv);
+            if (gl == 0) a.a_pos[row] = S2 * inv;
+        }
     }
 }
 
@@ -486,6 +543,170 @@ __global__ void __launch_bounds__(256) gat_sell_bwd_src_fixup_kernel(const __gri
     }
 }
 
+
+// ---- backward in ONE heavy pass (CSC layout) -----------------------------------------------------------------------------
+// bwd_edge gathers h_j for every edge to form dalpha = <g_i, h_j>, bwd_src gathers g_i for every edge to form
+// dH_j = sum alpha g_i: 2 x 33 GB of gathers on the products graph.  Both need the same pair (g_i, h_j), so one walk over
+// the CSC layout does both: the row owner j keeps h_j in registers, every slot gathers g_i once, the dot product gives
+// dalpha, alpha is recomputed from the target's record (a_tgt, max, 1/sum, D_i) with D_i = <g_i, out_i - bias> =
+// sum_e alpha_e dalpha_e precomputed per node, dz_e = alpha_e (dalpha_e - D_i) lrelu'(z_e) is summed into da_src_j and
+// alpha_e g_i into dH_j.  dz never goes to memory: its other marginal, da_tgt_i = sum over the edges INTO i, is known
+// before the walk from the training forward's out_pos / a_pos (gat_tstat_d_kernel), so the epilogue also adds
+// da_tgt_j att_tgt.  (Two earlier versions moved dz through memory for that sum: scattered into CSR slot order from the
+// walk — 2 GB of 32-byte sector write-backs for 250 MB of values, +1.3 ms — or written in place and gathered by a CSR-side
+// pass through an inverse slot map — 100 bytes of DRAM per 4-byte read, 2.0 ms.)
+template <int G>
+__global__ void __launch_bounds__(kGsThreads, 3) gat_sell_bwd_one_kernel(const __grid_constant__ GatSellArgs a) {
+    constexpr int S = 32 / G, P = kGsRows / S;
+    const int lane = threadIdx.x & 31, grp = lane / G, gl = lane % G;
+    const int nvec = a.f >> 2;
+    const bool act = gl < nvec;
+    const char* __restrict__ xg = reinterpret_cast<const char*>(a.h) + (act ? gl : nvec - 1) * 16;   // a.h = g
+    uint32_t row_bytes = (uint32_t)a.ldh * 4u;
+    asm volatile("" : "+l"(xg), "+r"(row_bytes));
+    const uint64_t pol_keep = l2_policy(a.l2_hint ? 1 : 0), pol_stream = l2_policy(a.l2_hint ? 2 : 0);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto gather = [&](int j) {
+        float4 v = zero4;
+        if (j >= 0) v = ldg_nc_f4_hint(reinterpret_cast<const float4*>(xg + (uint64_t)(uint32_t)j * row_bytes), pol_keep);
+        return v;
+    };
+    const int kcls = ((gl & (G / 2)) ? 2 : 0) + ((gl & (G / 4)) ? 1 : 0);   // the slot of a unit this lane finishes
+    const bool writer = (gl & (G / 4 - 1)) == 0;                           // one lane per class and group
+    auto rep = [](int k) { return (k >> 1) * (G / 2) + (k & 1) * (G / 4); };  // group-relative writer lane of class k
+    int chunk = 0;
+    if (lane == 0) chunk = atomicAdd(a.counter, 1);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    while (chunk < a.chunks) {
+        int next = 0;
+        if (lane == 0) next = atomicAdd(a.counter, 1);
+        const uint32_t base = __ldg(a.chunk_ptr + chunk);
+        const int nk = (int)(__ldg(a.chunk_ptr + chunk + 1) - base) / kGsRows;
+        const int4 none4 = make_int4(-1, -1, -1, -1);
+        int4 na = none4, nb = none4;
+        for (int p = 0; p < P; ++p) {
+            const int q = p * S + grp;
+            const int d = __ldg(a.vdst + (int64_t)chunk * kGsRows + q);
+            const int row = gs_row_of(a, d);
+            const bool live = row >= 0;
+            const float as = live ? __ldg(a.a_src + row) : 0.f;
+            float4 hj = zero4;
+            if (live && act) hj = ldg_nc_f4_hint(reinterpret_cast<const float4*>(a.own + (int64_t)row * a.ld_own) + gl, pol_stream);
+            const int4* __restrict__ ip = a.idx4 + base + q;
+            float4 acc = zero4;
+            float dsum = 0.f;
+            if (p == 0) {
+                na = nk > 0 ? gs_ldg_i4(ip) : none4;
+                nb = nk > 1 ? gs_ldg_i4(ip + kGsRows) : none4;
+            }
+            for (int k4 = 0; k4 < nk; k4 += 2) {
+                const int4 ia = na, ib = nb;
+                {
+                    const bool same = k4 + 2 < nk;
+                    const int4* np_ = same ? ip + (int64_t)(k4 + 2) * kGsRows : ip + S;
+                    const bool more = same || p + 1 < P;
+                    na = more ? gs_ldg_i4(np_) : none4;
+                    nb = (same ? k4 + 3 < nk : (p + 1 < P && nk > 1)) ? gs_ldg_i4(np_ + kGsRows) : none4;
+                }
+                // this lane finishes slot kcls of both units: the targets' records and the edges' CSR slots travel with the rows
+                const int ta = gs_pick(ia, kcls), tb = gs_pick(ib, kcls);
+                float4 tsa = make_float4(0.f, 0.f, -1.f, 0.f), tsb = tsa;    // .z < 0 marks padding
+                if (ta >= 0) tsa = ldg_nc_f4_hint(a.tstat + ta, pol_keep);
+                if (tb >= 0) tsb = ldg_nc_f4_hint(a.tstat + tb, pol_keep);
+                const float4 v0 = gather(ia.x), v1 = gather(ia.y), v2 = gather(ia.z), v3 = gather(ia.w);
+                const float4 v4 = gather(ib.x), v5 = gather(ib.y), v6 = gather(ib.z), v7 = gather(ib.w);
+                const float da0 = gs_reduce4<G>(dot4(hj, v0), dot4(hj, v1), dot4(hj, v2), dot4(hj, v3), gl);
+                const float da1 = gs_reduce4<G>(dot4(hj, v4), dot4(hj, v5), dot4(hj, v6), dot4(hj, v7), gl);
+                float wa = 0.f, wb = 0.f;
+                if (tsa.z >= 0.f) {
+                    const float z = tsa.x + as;
+                    wa = __expf(gs_leaky(z, a.slope) - tsa.y) * tsa.z;
+                    if (writer) dsum += wa * (da0 - tsa.w) * (z > 0.f ? 1.f : a.slope);
+                }
+                if (tsb.z >= 0.f) {
+                    const float z = tsb.x + as;
+                    wb = __expf(gs_leaky(z, a.slope) - tsb.y) * tsb.z;
+                    if (writer) dsum += wb * (da1 - tsb.w) * (z > 0.f ? 1.f : a.slope);
+                }
+                fma4(acc, __shfl_sync(0xffffffffu, wa, rep(0), G), v0); fma4(acc, __shfl_sync(0xffffffffu, wa, rep(1), G), v1);
+                fma4(acc, __shfl_sync(0xffffffffu, wa, rep(2), G), v2); fma4(acc, __shfl_sync(0xffffffffu, wa, rep(3), G), v3);
+                fma4(acc, __shfl_sync(0xffffffffu, wb, rep(0), G), v4); fma4(acc, __shfl_sync(0xffffffffu, wb, rep(1), G), v5);
+                fma4(acc, __shfl_sync(0xffffffffu, wb, rep(2), G), v6); fma4(acc, __shfl_sync(0xffffffffu, wb, rep(3), G), v7);
+            }
+            dsum = gs_group_sum<G>(dsum);
+            if (d >= 0) {
+                if (act) {   // dH_j = sum alpha g_i + da_src_j att_src + da_tgt_j att_tgt
+                    fma4(acc, dsum, __ldg(reinterpret_cast<const float4*>(a.att_src) + gl));
+                    fma4(acc, __ldg(a.da_tgt_in + row), __ldg(reinterpret_cast<const float4*>(a.att_tgt) + gl));
+                    __stcs(reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo) + gl, acc);
+                }
+                if (gl == 0) a.da[row] = dsum;
+            } else if (d != kGsNoRow) {
+                const int pr = -d - 1;
+                if (act) reinterpret_cast<float4*>(a.pacc + (int64_t)pr * a.f)[gl] = acc;
+                if (gl == 0) a.pstat[pr] = make_float2(dsum, 0.f);
+            }
+        }
+        chunk = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+__global__ void __launch_bounds__(256) gat_sell_bwd_one_fixup_kernel(const __grid_constant__ GatSellArgs a) {
+    const int nvec = a.f >> 2;
+    const int64_t total = (int64_t)a.hubs * nvec;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int hb = (int)(e / nvec), gl = (int)(e - (int64_t)hb * nvec);
+        const int p0 = __ldg(a.hub_pptr + hb), p1 = __ldg(a.hub_pptr + hb + 1);
+        float dsum = 0.f;
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = p0; p < p1; ++p) {
+            dsum += a.pstat[p].x;
+            add4(r, reinterpret_cast<const float4*>(a.pacc + (int64_t)p * a.f)[gl]);
+        }
+        const int row = __ldg(a.hub_rows + hb);
+        fma4(r, dsum, __ldg(reinterpret_cast<const float4*>(a.att_src) + gl));
+        fma4(r, __ldg(a.da_tgt_in + row), __ldg(reinterpret_cast<const float4*>(a.att_tgt) + gl));
+        reinterpret_cast<float4*>(a.out + (int64_t)row * a.ldo)[gl] = r;
+        if (gl == 0) a.da[row] = dsum;
+    }
+}
+
+// per-target record with D_i = <g_i, out_i - bias>, and da_tgt_i = (1 - slope) (<g_i, out_pos_i> - D_i a_pos_i)
+// (one warp per row)
+__global__ void __launch_bounds__(256) gat_tstat_d_kernel(const float* __restrict__ a_tgt, const float2* __restrict__ rowstat,
+                                                          const float* __restrict__ g, int64_t ldg, const float* __restrict__ out,
+                                                          int64_t ldo, const float* __restrict__ bias,
+                                                          const float* __restrict__ out_pos, int64_t ld_pos,
+                                                          const float* __restrict__ a_pos, float slope, int64_t n, int f,
+                                                          float4* __restrict__ tstat, float* __restrict__ da_tgt) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * 8;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += warps) {
+        float dsum = 0.f, psum = 0.f;
+        for (int c = lane * 4; c < f; c += 128) {
+            const float4 gv = ldg_nc_f4(reinterpret_cast<const float4*>(g + i * ldg + c));
+            float4 ov = ldg_nc_f4(reinterpret_cast<const float4*>(out + i * ldo + c));
+            const float4 pv = ldg_nc_f4(reinterpret_cast<const float4*>(out_pos + i * ld_pos + c));
+            if (bias) {
+                const float4 b = *reinterpret_cast<const float4*>(bias + c);
+                ov.x -= b.x; ov.y -= b.y; ov.z -= b.z; ov.w -= b.w;
+            }
+            dsum += dot4(gv, ov);
+            psum += dot4(gv, pv);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+            psum += __shfl_xor_sync(0xffffffffu, psum, o);
+        }
+        if (lane == 0) {
+            const float2 st = rowstat[i];
+            tstat[i] = make_float4(a_tgt[i], st.x, 1.0f / (st.y + 1e-16f), dsum);
+            da_tgt[i] = (1.0f - slope) * (psum - dsum * a_pos[i]);
+        }
+    }
+}
+
 // per-target record of the source-side pass; composed slot map of the CSC layout
 __global__ void __launch_bounds__(256) gat_tstat_kernel(const float* __restrict__ a_tgt, const float2* __restrict__ rowstat,
                                                         int64_t n, float4* __restrict__ tstat) {
@@ -543,7 +764,8 @@ extern "C" {
 
 size_t gg_gat_sell_workspace_bytes(int64_t partial_rows, int64_t f) {
     const size_t pr = (size_t)(partial_rows > 0 ? partial_rows : 0);
-    return 512 + align_up(pr * (size_t)f * sizeof(float), 256) + align_up(pr * sizeof(float2), 256);
+    return 512 + 2 * align_up(pr * (size_t)f * sizeof(float), 256) + align_up(pr * sizeof(float2), 256) +
+           align_up(pr * sizeof(float), 256);
 }
 
 int gg_sell_compose_map(const int32_t* slot_of, int64_t total, const int32_t* map, int32_t* out, gg_stream_t stream) {
@@ -574,14 +796,19 @@ int gg_sell_compose_map(const int32_t* slot_of, int64_t total, const int32_t* ma
     int* counter = c.take<int>(64);                                                                                    \
     float* pacc = c.take<float>((size_t)partial_rows * f);                                                             \
     float2* pstat = c.take<float2>((size_t)partial_rows);                                                              \
+    float* pacc2 = c.take<float>((size_t)partial_rows * f);                                                            \
+    float* ps2 = c.take<float>((size_t)partial_rows);                                                                  \
+    (void)pacc2; (void)ps2;                                                                                            \
     GG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
 
 int gg_gat_sell_fwd_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const int32_t* vdst,
                         const int32_t* hub_rows, const int32_t* hub_pptr, int64_t hubs, int64_t partial_rows,
                         const float* h, int64_t ldh, const float* a_tgt, const float* a_src, int64_t n, int64_t f,
-                        float slope, const float* bias, float* out, int64_t ldo, float* rowstat, void* workspace,
-                        size_t workspace_bytes, gg_stream_t stream) {
+                        float slope, const float* bias, float* out, int64_t ldo, float* rowstat, float* out_pos,
+                        int64_t ld_pos, float* a_pos, void* workspace, size_t workspace_bytes, gg_stream_t stream) {
     GS_COMMON_CHECKS("gg_gat_sell_fwd_f32")
+    GG_REQUIRE((out_pos == nullptr) == (a_pos == nullptr) && (!out_pos || (gs_al16(out_pos) && ld_pos >= f && ld_pos % 4 == 0)),
+               "gg_gat_sell_fwd_f32: out_pos and a_pos come together, rows 16-byte aligned");
     GG_REQUIRE(h && a_tgt && a_src && out && rowstat && ldh >= f && ldh < ((int64_t)1 << 30) && ldh % 4 == 0 &&
                    ldo % 4 == 0 && gs_al16(h) && gs_al16(out) && gs_al16(idx) && (!bias || gs_al16(bias)) &&
                    (reinterpret_cast<uintptr_t>(rowstat) & 7) == 0,
@@ -591,7 +818,12 @@ int gg_gat_sell_fwd_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t
     a.hub_rows = hub_rows; a.hub_pptr = hub_pptr; a.hubs = (int)hubs; a.n = n; a.f = (int)f; a.slope = slope;
     a.h = h; a.ldh = ldh; a.a_tgt = a_tgt; a.a_src = a_src; a.bias = bias; a.out = out; a.ldo = ldo;
     a.rowstat = reinterpret_cast<float2*>(rowstat); a.pacc = pacc; a.pstat = pstat; a.counter = counter; a.l2_hint = gs_l2_hint();
-    GS_DISPATCH(gat_sell_fwd_kernel, g_lanes, gs_main_grid(chunks), st, a);
+    a.out_pos = out_pos; a.ld_pos = ld_pos; a.a_pos = a_pos; a.pacc2 = pacc2; a.ps2 = ps2;
+    if (out_pos) {
+        GS_DISPATCH(gat_sell_fwd_train_kernel, g_lanes, gs_main_grid(chunks), st, a);
+    } else {
+        GS_DISPATCH(gat_sell_fwd_eval_kernel, g_lanes, gs_main_grid(chunks), st, a);
+    }
     GG_LAUNCHED();
     if (hubs > 0) {
         gat_sell_fwd_fixup_kernel<<<gs_grid(hubs * (f / 4), 256), 256, 0, st>>>(a);
@@ -654,6 +886,40 @@ int gg_gat_sell_bwd_src_f32(const uint32_t* chunk_ptr, int64_t chunks, const int
     GG_LAUNCHED();
     if (hubs > 0) {
         gat_sell_bwd_src_fixup_kernel<<<gs_grid(hubs * (f / 4), 256), 256, 0, st>>>(a);
+        GG_LAUNCHED();
+    }
+    return GG_OK;
+}
+
+int gg_gat_sell_bwd_one_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const int32_t* vdst,
+                            const int32_t* hub_rows, const int32_t* hub_pptr, int64_t hubs, int64_t partial_rows,
+                            const float* h, int64_t ldh, const float* g, int64_t ldg, const float* fwd_out, int64_t ld_out,
+                            const float* bias, const float* out_pos, int64_t ld_pos, const float* a_pos, const float* a_tgt,
+                            const float* a_src, const float* rowstat, const float* att_src, const float* att_tgt, int64_t n,
+                            int64_t f, float slope, float* dh, int64_t ld_dh, float* da_tgt, float* da_src,
+                            float* tstat_scratch, void* workspace, size_t workspace_bytes, gg_stream_t stream) {
+    GS_COMMON_CHECKS("gg_gat_sell_bwd_one_f32")
+    GG_REQUIRE(h && g && fwd_out && out_pos && a_pos && a_tgt && a_src && rowstat && att_src && att_tgt && dh && da_tgt && da_src &&
+                   tstat_scratch && ldg >= f && ldg < ((int64_t)1 << 30) && ldg % 4 == 0 && ldh % 4 == 0 && ld_out % 4 == 0 &&
+                   ld_pos % 4 == 0 && ld_dh % 4 == 0 && gs_al16(h) && gs_al16(g) && gs_al16(fwd_out) && gs_al16(out_pos) &&
+                   gs_al16(dh) && gs_al16(idx) && gs_al16(att_src) && gs_al16(att_tgt) && gs_al16(tstat_scratch) &&
+                   (!bias || gs_al16(bias)),
+               "gg_gat_sell_bwd_one_f32: bad operands (rows must be 16-byte aligned)");
+    gat_tstat_d_kernel<<<gs_grid(n, 8), 256, 0, st>>>(a_tgt, reinterpret_cast<const float2*>(rowstat), g, ldg, fwd_out, ld_out,
+                                                      bias, out_pos, ld_pos, a_pos, slope, n, (int)f,
+                                                      reinterpret_cast<float4*>(tstat_scratch), da_tgt);
+    GG_LAUNCHED();
+    GatSellArgs a{};
+    a.chunk_ptr = chunk_ptr; a.chunks = (int)chunks; a.idx4 = reinterpret_cast<const int4*>(idx);
+    a.vdst = vdst; a.hub_rows = hub_rows; a.hub_pptr = hub_pptr;
+    a.hubs = (int)hubs; a.n = n; a.f = (int)f; a.slope = slope; a.h = g; a.ldh = ldg; a.own = h; a.ld_own = ldh;
+    a.a_src = a_src; a.tstat = reinterpret_cast<const float4*>(tstat_scratch); a.att_src = att_src; a.att_tgt = att_tgt;
+    a.out = dh; a.ldo = ld_dh; a.da_tgt_in = da_tgt; a.da = da_src; a.pacc = pacc; a.pstat = pstat; a.counter = counter;
+    a.l2_hint = gs_l2_hint();
+    GS_DISPATCH(gat_sell_bwd_one_kernel, g_lanes, gs_main_grid(chunks), st, a);
+    GG_LAUNCHED();
+    if (hubs > 0) {
+        gat_sell_bwd_one_fixup_kernel<<<gs_grid(hubs * (f / 4), 256), 256, 0, st>>>(a);
         GG_LAUNCHED();
     }
     return GG_OK;

@@ -190,18 +190,19 @@ class _GatAggregate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, att, bias, layout, heads, slope):
         h = h.contiguous()
-        out, alpha, a_tgt, a_src = ops.gat_forward(layout.csr, h, att, heads, slope, bias)
+        need_grad = any(ctx.needs_input_grad[:3])
+        out, alpha, a_tgt, a_src, pos = ops.gat_forward(layout.csr, h, att, heads, slope, bias, need_grad)
         ctx.layout, ctx.heads, ctx.slope = layout, heads, slope
-        ctx.save_for_backward(h, att, bias, alpha, a_tgt, a_src, out)
+        ctx.save_for_backward(h, att, bias, alpha, a_tgt, a_src, out, *(pos or ()))
         return out
 
     @staticmethod
     def backward(ctx, g):
-        h, att, bias, alpha, a_tgt, a_src, out = ctx.saved_tensors
+        h, att, bias, alpha, a_tgt, a_src, out, *pos = ctx.saved_tensors
         g = g.contiguous()
         lay = ctx.layout
         dh, datt = ops.gat_backward(lay.csr, lay.csc, lay.csc2csr, h, att, ctx.heads, ctx.slope, bias, alpha,
-                                    a_tgt, a_src, out, g)
+                                    a_tgt, a_src, out, g, tuple(pos) or None)
         gb = ops.colsum(g) if (bias is not None and ctx.needs_input_grad[2]) else None
         return dh, datt.view_as(att), gb, None, None, None
 

@@ -619,6 +619,7 @@ def _f32(shape, dev):
 
 
 GAT_ALGO = _os.environ.get("GG_GAT_ALGO", "auto")   # auto | sell (fused, sliced ELL) | mp (split passes, merge-path) | row
+GAT_BWD = _os.environ.get("GG_GAT_BWD", "one")      # fused backward: one (single CSC pass) | two (edge pass + source pass)
 
 
 def _gat_use_sell(csr, f, heads):
@@ -627,22 +628,28 @@ def _gat_use_sell(csr, f, heads):
     return GAT_ALGO == "sell" or csr.num_nodes + csr.num_slots >= 1 << 14
 
 
-def gat_sell_forward(csr, h, ldh, a_tgt, a_src, slope, bias):
-    """-> (out, rowstat [n, 2] = per-row (max, sum of exp)); alpha is never materialised (csrc/gat_sell.cu)."""
+def gat_sell_forward(csr, h, ldh, a_tgt, a_src, slope, bias, need_grad=False):
+    """-> (out, rowstat [n, 2] = per-row (max, sum of exp), pos); alpha is never materialised (csrc/gat_sell.cu).
+    ``pos`` = (out_pos [n, f], a_pos [n]) when ``need_grad`` (the sums over the positive-logit slots that the one-pass
+    backward turns into da_tgt), else None."""
     sl = sell_layout(csr)
     n, f = h.shape
     L = lib()
     out = torch.empty((n, f), dtype=torch.float32, device=h.device)
     rowstat = torch.empty((max(n, 1), 2), dtype=torch.float32, device=h.device)[:n]
+    pos = None
+    if need_grad and GAT_BWD == "one":
+        pos = (torch.empty((n, f), dtype=torch.float32, device=h.device), _f32((n,), h.device))
     ws_bytes = int(L.gg_gat_sell_workspace_bytes(sl.partial_rows, f))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=h.device)
     if bias is not None:
         bias = bias.contiguous()
     check(L.gg_gat_sell_fwd_f32(_ptr(sl.chunk_ptr), sl.chunks, _ptr(sl.idx), _ptr(sl.vdst), _ptr(sl.hub_rows),
                                 _ptr(sl.hub_pptr), sl.hubs, sl.partial_rows, _ptr(h), ldh, _ptr(a_tgt), _ptr(a_src), n, f,
-                                float(slope), _ptr(bias), _ptr(out), f, _ptr(rowstat), _ptr(ws), ws_bytes, _stream()),
+                                float(slope), _ptr(bias), _ptr(out), f, _ptr(rowstat), _ptr(pos[0]) if pos else None, f,
+                                _ptr(pos[1]) if pos else None, _ptr(ws), ws_bytes, _stream()),
           "gg_gat_sell_fwd_f32")
-    return out, rowstat
+    return out, rowstat, pos
 
 
 def _sell_edge_map(csc, csc2csr):
@@ -657,7 +664,7 @@ def _sell_edge_map(csc, csc2csr):
     return hit[1]
 
 
-def gat_sell_backward(csr, csc, csc2csr, h, att, slope, bias, rowstat, a_tgt, a_src, out, g):
+def gat_sell_backward(csr, csc, csc2csr, h, att, slope, bias, rowstat, a_tgt, a_src, out, g, pos=None):
     """-> dh [n, f], datt [1, 2c] (heads = 1)."""
     h, ldh = _rows(h, "h")
     g, ldg = _rows(g, "g")
@@ -669,10 +676,23 @@ def gat_sell_backward(csr, csc, csc2csr, h, att, slope, bias, rowstat, a_tgt, a_
     s1, s2 = sell_layout(csr), sell_layout(csc)
     if bias is not None:
         bias = bias.contiguous()
-    dz = _f32((csr.num_slots,), dev)
     da_tgt, da_src = _f32((n,), dev), _f32((n,), dev)
     ws_bytes = int(L.gg_gat_sell_workspace_bytes(max(s1.partial_rows, s2.partial_rows), f))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if pos is not None:
+        # one heavy pass over the CSC layout: each edge's g_i is gathered once for both dalpha and dH
+        out_pos, a_pos = pos
+        dh = torch.empty((n, f), dtype=torch.float32, device=dev)
+        tstat = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
+        att_tgt, att_src = att[0, :f].contiguous(), att[0, f:].contiguous()
+        check(L.gg_gat_sell_bwd_one_f32(_ptr(s2.chunk_ptr), s2.chunks, _ptr(s2.idx), _ptr(s2.vdst), _ptr(s2.hub_rows),
+                                        _ptr(s2.hub_pptr), s2.hubs, s2.partial_rows, _ptr(h), ldh, _ptr(g), ldg, _ptr(out),
+                                        ldo, _ptr(bias), _ptr(out_pos), out_pos.stride(0), _ptr(a_pos), _ptr(a_tgt),
+                                        _ptr(a_src), _ptr(rowstat), _ptr(att_src), _ptr(att_tgt), n, f, float(slope),
+                                        _ptr(dh), f, _ptr(da_tgt), _ptr(da_src), _ptr(tstat), _ptr(ws), ws_bytes,
+                                        _stream()), "gg_gat_sell_bwd_one_f32")
+        return dh, _gat_att_grad(h, ldh, da_tgt, da_src, n, f)
+    dz = _f32((csr.num_slots,), dev)
     check(L.gg_gat_sell_bwd_edge_f32(_ptr(s1.chunk_ptr), s1.chunks, _ptr(s1.idx), _ptr(s1.slot_of), _ptr(s1.vdst),
                                      _ptr(s1.hub_rows), _ptr(s1.hub_pptr), s1.hubs, s1.partial_rows, _ptr(h), ldh, _ptr(g),
                                      ldg, _ptr(out), ldo, _ptr(bias), _ptr(a_tgt), _ptr(a_src), _ptr(rowstat), n, f,
@@ -687,12 +707,17 @@ def gat_sell_backward(csr, csc, csc2csr, h, att, slope, bias, rowstat, a_tgt, a_
                                     _ptr(a_tgt), _ptr(a_src), _ptr(rowstat), _ptr(dz), _ptr(da_tgt), _ptr(att_src),
                                     _ptr(att_tgt), n, f, float(slope), _ptr(dh), f, _ptr(da_src), _ptr(tstat), _ptr(ws),
                                     ws_bytes, _stream()), "gg_gat_sell_bwd_src_f32")
-    datt = torch.empty((1, 2 * f), dtype=torch.float32, device=dev)
+    return dh, _gat_att_grad(h, ldh, da_tgt, da_src, n, f)
+
+
+def _gat_att_grad(h, ldh, da_tgt, da_src, n, f):
+    L = lib()
+    datt = torch.empty((1, 2 * f), dtype=torch.float32, device=h.device)
     ws2_bytes = int(L.gg_gat_att_grad_workspace_bytes(n, 1, f))
-    ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device=dev)
+    ws2 = torch.empty(ws2_bytes, dtype=torch.uint8, device=h.device)
     check(L.gg_gat_att_grad_f32(_ptr(h), ldh, _ptr(da_tgt), _ptr(da_src), n, 1, f, _ptr(datt), _ptr(ws2), ws2_bytes,
                                 _stream()), "gg_gat_att_grad_f32")
-    return dh, datt
+    return datt
 
 
 def _gat_use_mp(csr, f, heads):
@@ -701,8 +726,9 @@ def _gat_use_mp(csr, f, heads):
     return GAT_ALGO == "mp" or csr.num_nodes + csr.num_slots >= 1 << 14
 
 
-def gat_forward(csr, h, att, heads, slope, bias):
-    """-> out [n, heads*c], alpha [E', heads], a_tgt, a_src [n, heads]."""
+def gat_forward(csr, h, att, heads, slope, bias, need_grad=False):
+    """-> out [n, heads*c], alpha [E', heads], a_tgt, a_src [n, heads], pos (fused path with ``need_grad``: the extra
+    record of the one-pass backward, else None; hand it back to gat_backward)."""
     _need_cuda(h, att, bias)
     h, ldh = _rows(h, "h")
     n, f = h.shape
@@ -713,27 +739,28 @@ def gat_forward(csr, h, att, heads, slope, bias):
     check(L.gg_gat_scores_f32(_ptr(h), ldh, _ptr(att), n, heads, c, _ptr(a_tgt), _ptr(a_src), _stream()),
           "gg_gat_scores_f32")
     if _gat_use_sell(csr, f, heads) and ldh % 4 == 0:
-        out, rowstat = gat_sell_forward(csr, h, ldh, a_tgt, a_src, slope, bias)
-        return out, rowstat, a_tgt, a_src          # rowstat [n, 2] stands in for alpha [E', 1]
+        out, rowstat, pos = gat_sell_forward(csr, h, ldh, a_tgt, a_src, slope, bias, need_grad)
+        return out, rowstat, a_tgt, a_src, pos     # rowstat [n, 2] stands in for alpha [E', 1]
     alpha = _f32((csr.num_slots, heads), h.device)
     if _gat_use_mp(csr, f, heads):
         check(L.gg_gat_alpha_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(a_tgt), _ptr(a_src), n, float(slope),
                                  _ptr(alpha), _stream()), "gg_gat_alpha_f32")
         out = spmm(csr, h, alpha.view(-1), SUM, None, 0.0, bias)
-        return out, alpha, a_tgt, a_src
+        return out, alpha, a_tgt, a_src, None
     out = torch.empty((n, f), dtype=torch.float32, device=h.device)
     if bias is not None:
         bias = bias.contiguous()
     check(L.gg_gat_fwd_f32(_ptr(csr.rowptr), _ptr(csr.nbr), _ptr(h), ldh, _ptr(a_tgt), _ptr(a_src), n,
                            heads, c, float(slope), _ptr(bias), _ptr(alpha), _ptr(out), max(f, 1),
                            _stream()), "gg_gat_fwd_f32")
-    return out, alpha, a_tgt, a_src
+    return out, alpha, a_tgt, a_src, None
 
 
-def gat_backward(csr, csc, csc2csr, h, att, heads, slope, bias, alpha, a_tgt, a_src, out, g):
-    """-> dh [n, f], datt [heads, 2c].  ``alpha`` is the per-row (max, sum) record when the forward ran fused."""
+def gat_backward(csr, csc, csc2csr, h, att, heads, slope, bias, alpha, a_tgt, a_src, out, g, pos=None):
+    """-> dh [n, f], datt [heads, 2c].  ``alpha`` is the per-row (max, sum) record when the forward ran fused; ``pos`` is
+    gat_forward's fifth result (None: the fused backward runs as two passes)."""
     if alpha.dim() == 2 and alpha.size(0) == h.size(0) and alpha.size(1) == 2 and _gat_use_sell(csr, h.size(1), heads):
-        return gat_sell_backward(csr, csc, csc2csr, h, att, slope, bias, alpha, a_tgt, a_src, out, g)
+        return gat_sell_backward(csr, csc, csc2csr, h, att, slope, bias, alpha, a_tgt, a_src, out, g, pos)
     h, ldh = _rows(h, "h")
     g, ldg = _rows(g, "g")
     out, ldo = _rows(out, "out")

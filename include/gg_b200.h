@@ -497,7 +497,9 @@ int gg_segment_softmax_bwd_f32(const int32_t* rowptr, const float* alpha, const 
 
 /* GAT (heads = 1) fused into the sliced-ELL aggregation (csrc/gat_sell.cu): alpha never touches memory.
  *   gg_gat_sell_fwd_f32       CSR sliced-ELL layout (gg_sell_build): logits leaky_relu(a_tgt[i] + a_src[j]), online softmax
- *                             fused with out[i] = sum_j alpha_ij h_j (+ bias); rowstat[2 i .. 2 i + 1] = (max, sum of exp)
+ *                             fused with out[i] = sum_j alpha_ij h_j (+ bias); rowstat[2 i .. 2 i + 1] = (max, sum of exp);
+ *                             out_pos / a_pos (both or neither; training only): the same sums over the slots whose logit
+ *                             is positive, consumed by gg_gat_sell_bwd_one_f32
  *   gg_gat_sell_bwd_edge_f32  same layout: dalpha = <g_i, h_j>, alpha recomputed from rowstat, D_i = <g_i, out_i - bias>;
  *                             writes dz[CSR slot] (gradient of the pre-activation logits) and da_tgt[i] = sum_e dz_e
  *   gg_gat_sell_bwd_src_f32   CSC sliced-ELL layout + `edge_map` (gg_sell_compose_map(slot_of_csc, csc->csr slot map)):
@@ -509,8 +511,8 @@ int gg_sell_compose_map(const int32_t* slot_of, int64_t total, const int32_t* ma
 int gg_gat_sell_fwd_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const int32_t* vdst,
                         const int32_t* hub_rows, const int32_t* hub_pptr, int64_t hubs, int64_t partial_rows,
                         const float* h, int64_t ldh, const float* a_tgt, const float* a_src, int64_t n, int64_t f,
-                        float slope, const float* bias, float* out, int64_t ldo, float* rowstat, void* workspace,
-                        size_t workspace_bytes, gg_stream_t stream);
+                        float slope, const float* bias, float* out, int64_t ldo, float* rowstat, float* out_pos,
+                        int64_t ld_pos, float* a_pos, void* workspace, size_t workspace_bytes, gg_stream_t stream);
 int gg_gat_sell_bwd_edge_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const int32_t* slot_of,
                              const int32_t* vdst, const int32_t* hub_rows, const int32_t* hub_pptr, int64_t hubs,
                              int64_t partial_rows, const float* h, int64_t ldh, const float* g, int64_t ldg,
@@ -524,6 +526,21 @@ int gg_gat_sell_bwd_src_f32(const uint32_t* chunk_ptr, int64_t chunks, const int
                             const float* att_tgt, int64_t n, int64_t f, float slope, float* dh, int64_t ld_dh,
                             float* da_src, float* tstat_scratch, void* workspace, size_t workspace_bytes,
                             gg_stream_t stream);
+
+/* The whole GAT backward in ONE heavy pass over the CSC sliced-ELL layout (csrc/gat_sell.cu): every slot gathers g_i once,
+ * <g_i, h_j> gives dalpha, alpha is recomputed from the target's record, D_i = <g_i, out_i - bias> is precomputed per node;
+ * dz never goes to memory: da_src_j is summed in the walk, and da_tgt_i = (1 - slope) (<g_i, out_pos_i> - D_i a_pos_i) comes
+ * from the training forward's out_pos / a_pos (the share of the aggregation that arrives through positive logits; pass
+ * them to gg_gat_sell_fwd_f32 to have them written).  Writes da_tgt, da_src and
+ * dh = sum alpha g_i + da_src att_src + da_tgt att_tgt.  Replaces gg_gat_sell_bwd_edge_f32 + gg_gat_sell_bwd_src_f32 (two
+ * passes of gathers).  `tstat_scratch`: 4 n floats. */
+int gg_gat_sell_bwd_one_f32(const uint32_t* chunk_ptr, int64_t chunks, const int32_t* idx, const int32_t* vdst,
+                            const int32_t* hub_rows, const int32_t* hub_pptr, int64_t hubs, int64_t partial_rows,
+                            const float* h, int64_t ldh, const float* g, int64_t ldg, const float* fwd_out, int64_t ld_out,
+                            const float* bias, const float* out_pos, int64_t ld_pos, const float* a_pos, const float* a_tgt,
+                            const float* a_src, const float* rowstat, const float* att_src, const float* att_tgt, int64_t n,
+                            int64_t f, float slope, float* dh, int64_t ld_dh, float* da_tgt, float* da_src,
+                            float* tstat_scratch, void* workspace, size_t workspace_bytes, gg_stream_t stream);
 
 /* Row gather / scatter-add / ReLU gradient used by the GIN-ID branch (ref: idconv.py:372-375):
  *   gather:      out[r,:]      = x[id[r],:]

@@ -28,16 +28,18 @@ def timeit(fn, it=5):
     return s.elapsed_time(e) / it
 
 
-for algo in ('sell', 'mp'):
-    ops.GAT_ALGO = algo
-    out, al, a_tgt, a_src = ops.gat_forward(csr, h, att, 1, 0.2, bias)
-    t_f = timeit(lambda: ops.gat_forward(csr, h, att, 1, 0.2, bias))
-    t_b = timeit(lambda: ops.gat_backward(csr, csc, m, h, att, 1, 0.2, bias, al, a_tgt, a_src, out, g))
+for algo in ('sell', 'sell_two', 'mp'):
+    ops.GAT_ALGO = algo.split('_')[0]
+    ops.GAT_BWD = 'two' if algo.endswith('two') else 'one'
+    out, al, a_tgt, a_src, pos = ops.gat_forward(csr, h, att, 1, 0.2, bias, True)
+    t_f = timeit(lambda: ops.gat_forward(csr, h, att, 1, 0.2, bias, True))
+    t_b = timeit(lambda: ops.gat_backward(csr, csc, m, h, att, 1, 0.2, bias, al, a_tgt, a_src, out, g, pos))
     print(f'{algo}: forward {t_f:.3f} ms, backward {t_b:.3f} ms', flush=True)
 ops.GAT_ALGO = 'sell'
-out, rs, a_tgt, a_src = ops.gat_forward(csr, h, att, 1, 0.2, bias)
+ops.GAT_BWD = 'one'
+out, rs, a_tgt, a_src, pos = ops.gat_forward(csr, h, att, 1, 0.2, bias, True)
 at, asr = a_tgt.view(-1), a_src.view(-1)
-print('fwd kernel only', timeit(lambda: ops.gat_sell_forward(csr, h, f, at, asr, 0.2, bias)))
+print('fwd kernel only: eval', timeit(lambda: ops.gat_sell_forward(csr, h, f, at, asr, 0.2, bias)), 'train', timeit(lambda: ops.gat_sell_forward(csr, h, f, at, asr, 0.2, bias, True)))
 print('spmm sell weighted', timeit(lambda: ops.spmm(csr, h, torch.ones(csr.num_slots, device=dev), algo='sell')))
 L = ops.lib()
 import ctypes
@@ -53,3 +55,10 @@ a_t, a_s = att[0, 0, :f].contiguous(), att[0, 0, f:].contiguous()
 def src():
     check(L.gg_gat_sell_bwd_src_f32(_ptr(s2.chunk_ptr), s2.chunks, _ptr(s2.idx), _ptr(emap), _ptr(s2.vdst), _ptr(s2.hub_rows), _ptr(s2.hub_pptr), s2.hubs, s2.partial_rows, _ptr(g), f, _ptr(at), _ptr(asr), _ptr(rs), _ptr(dz), _ptr(da_t), _ptr(a_s), _ptr(a_t), n, f, 0.2, _ptr(dh), f, _ptr(da_s), _ptr(tstat), _ptr(ws), ws_bytes, _stream()), 'src')
 print('bwd edge kernel', timeit(edge)); print('bwd src kernel', timeit(src))
+
+da_t2 = torch.empty(n, device=dev); dh2 = torch.empty(n, f, device=dev); da_s2 = torch.empty(n, device=dev)
+def one():
+    check(L.gg_gat_sell_bwd_one_f32(_ptr(s2.chunk_ptr), s2.chunks, _ptr(s2.idx), _ptr(s2.vdst), _ptr(s2.hub_rows), _ptr(s2.hub_pptr), s2.hubs, s2.partial_rows, _ptr(h), f, _ptr(g), f, _ptr(out), f, _ptr(bias), _ptr(pos[0]), f, _ptr(pos[1]), _ptr(at), _ptr(asr), _ptr(rs), _ptr(a_s), _ptr(a_t), n, f, 0.2, _ptr(dh2), f, _ptr(da_t2), _ptr(da_s2), _ptr(tstat), _ptr(ws), ws_bytes, _stream()), 'one')
+edge(); src(); one(); torch.cuda.synchronize()
+rel = lambda a, b: float((a - b).norm() / b.norm())
+print('bwd one (three launches)', timeit(one), 'vs two-pass: dh', rel(dh2, dh), 'da_tgt', rel(da_t2, da_t), 'da_src', rel(da_s2, da_s))

@@ -17,8 +17,8 @@ h = torch.randn(n, f, device=dev); g = torch.randn(n, f, device=dev)
 att = torch.randn(1, 1, 2 * f, device=dev) * 0.1; bias = torch.zeros(f, device=dev)
 for algo in ('mp', 'sell'):
     ops.GAT_ALGO = algo
-    out, al, a_tgt, a_src = ops.gat_forward(csr, h, att, 1, 0.2, bias)
-    ops.gat_backward(csr, csc, m, h, att, 1, 0.2, bias, al, a_tgt, a_src, out, g)
+    out, al, a_tgt, a_src, pos = ops.gat_forward(csr, h, att, 1, 0.2, bias, True)
+    ops.gat_backward(csr, csc, m, h, att, 1, 0.2, bias, al, a_tgt, a_src, out, g, pos)
 torch.cuda.synchronize()
 del h, g, lay, csr, csc, m, out, al
 spec = bench.WORKLOADS['ego_idgin']

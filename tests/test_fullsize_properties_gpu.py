@@ -101,7 +101,7 @@ def test_edge_softmax_rows_sum_to_one(big):
     mp = pytest.MonkeyPatch()
     try:
         mp.setattr(ops, 'GAT_ALGO', 'mp')                       # split passes: alpha is materialised
-        out, alpha, _, _ = ops.gat_forward(lay.csr, h, att, 1, 0.2, None)
+        out, alpha, _, _, _ = ops.gat_forward(lay.csr, h, att, 1, 0.2, None)
     finally:
         mp.undo()
     sums = torch.zeros(n, device=ei.device, dtype=torch.float64).index_add_(0, lay.csr.rowid.long(),
@@ -112,12 +112,22 @@ def test_edge_softmax_rows_sum_to_one(big):
     assert float(out.max()) <= float(h.max()) + 1e-4 and float(out.min()) >= float(h.min()) - 1e-4
     # fused path (online softmax inside the sliced-ELL aggregation, alpha never stored): the same output, and on h = 1
     # every row is sum_e alpha_e = 1
-    fused, rowstat, a_tgt, a_src = ops.gat_forward(lay.csr, h, att, 1, 0.2, None)
+    fused, rowstat, a_tgt, a_src, _ = ops.gat_forward(lay.csr, h, att, 1, 0.2, None)
     assert rowstat.shape == (n, 2)
     assert float((fused - out).abs().max()) / float(out.abs().max()) < 1e-5
     ones = torch.ones(n, 128, device=ei.device)
-    one_out, _ = ops.gat_sell_forward(lay.csr, ones, 128, a_tgt.view(-1), a_src.view(-1), 0.2, None)
+    one_out, _, _ = ops.gat_sell_forward(lay.csr, ones, 128, a_tgt.view(-1), a_src.view(-1), 0.2, None)
     assert float((one_out - 1.0).abs().max()) < 1e-5
+    # training forward: the same output bit for bit, plus the positive-logit share (a_pos in [0, 1], out_pos inside h's
+    # range); the one-pass backward built on it agrees with the two-pass backward that moves dz through memory
+    out_t, rs_t, _, _, pos = ops.gat_forward(lay.csr, h, att, 1, 0.2, None, need_grad=True)
+    assert torch.equal(out_t, fused) and torch.equal(rs_t, rowstat) and pos is not None
+    assert float(pos[1].min()) >= 0.0 and float(pos[1].max()) <= 1.0 + 1e-5
+    gy = torch.randn(n, 128, device=ei.device, generator=g)
+    dh1, datt1 = ops.gat_backward(lay.csr, lay.csc, lay.csc2csr, h, att, 1, 0.2, None, rowstat, a_tgt, a_src, fused, gy, pos)
+    dh2, datt2 = ops.gat_backward(lay.csr, lay.csc, lay.csc2csr, h, att, 1, 0.2, None, rowstat, a_tgt, a_src, fused, gy)
+    assert float((dh1 - dh2).norm() / dh2.norm()) < 1e-5
+    assert float((datt1 - datt2).norm() / datt2.norm()) < 1e-4          # sums of 2.4 M cancelling terms
 
 
 def test_cycle_counts_and_ego_invariants_on_a_large_batch():

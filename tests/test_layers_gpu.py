@@ -225,16 +225,18 @@ def test_gat_multi_head(cuda, heads, c):
 
 
 @pytest.mark.parametrize('fout', [128, 16, 36])
-@pytest.mark.parametrize('algo', ['sell', 'sell_split', 'mp', 'row'])
+@pytest.mark.parametrize('algo', ['sell', 'sell_split', 'sell_two', 'sell_split_two', 'mp', 'row'])
 @pytest.mark.parametrize('name', ['gatconv', 'gatidconv'])
 def test_gat_merge_path_and_row_kernels_agree_with_oracle(cuda, monkeypatch, algo, name, fout):
     """heads = 1 GAT runs fused into the sliced-ELL aggregation ('sell': online softmax, alpha never stored; 'sell_split':
     the same with rows cut into virtual rows of 8 slots, so the (max, sum, accumulator) merge of split rows is exercised),
     as split passes on the merge-path kernels ('mp') or as the fused warp-per-row kernels ('row'); all must match the
-    oracle on a hub-heavy graph."""
+    oracle on a hub-heavy graph.  The fused backward is one pass over the CSC layout by default; '*_two' runs the older
+    edge pass + source pass."""
     from graphgym_b200 import ops
     monkeypatch.setattr(ops, 'GAT_ALGO', algo.split('_')[0])
-    if algo == 'sell_split':
+    monkeypatch.setattr(ops, 'GAT_BWD', 'two' if algo.endswith('_two') else 'one')
+    if 'split' in algo:
         monkeypatch.setattr(ops, 'SELL_SEG', 8)
     if fout != 128 and algo in ('mp', 'row'):
         pytest.skip('narrow widths: the sliced-ELL path only')

@@ -65,7 +65,9 @@ DEFAULT_HALO = 'sliced'
 # (profiles/r02_spmm_sell128_bench_ncu_raw.csv: spmm_sell_kernel<32,1,0> 18.58 + 1.27 GB in 3.26 ms = 6.1 TB/s = 0.93 of
 # the measured copy peak; the algorithmic figure is 34.7 GB — the L2 serves the rest).  Keyed by (workload, kernel): a
 # line produced with another aggregation kernel reports null.
-NCU_TRAFFIC = {('products_gcn', 'sell'): 19_850_000_000, ('products_gcn', 'mpg'): 18_829_800_000}
+NCU_TRAFFIC = {('products_gcn', 'sell'): 19_850_000_000, ('products_gcn', 'mpg'): 18_829_800_000,
+               # profiles/r02_gat_onepass_launches.csv: per-node pass + walk + fix-up; training forward + fix-up
+               ('products_gat', 'bwd_one'): 29_894_374_912, ('products_gat', 'fwd_train'): 24_095_261_440}
 HALO_DESC = {
     'allgather': 'halo all-gather of the feature rows over NCCL, rank-local SpMM',
     'pipelined': 'P-1 NCCL send/recv rounds overlapped with the per-peer SpMMs',
@@ -194,6 +196,17 @@ def spmm_bytes(n, slots, f, weighted, gather_bytes=4):
     """Algorithmic bytes of one aggregation launch: gathered rows + output rows + nbr
     indices + rowptr (+ per-slot weights); ``gather_bytes`` = 2 in the bf16-gather mode."""
     return slots * f * gather_bytes + n * f * 4 + slots * 4 + (n + 1) * 4 + (slots * 4 if weighted else 0)
+
+
+def gat_pass_bytes(kind, n, slots, f):
+    """Algorithmic bytes of the fused GAT passes (counted like spmm_bytes: every gathered row counts).
+    fwd (training): per slot the index, the source logit half and the gathered h row; per row a_tgt, out, out_pos,
+    (max, sum), a_pos.  bwd: the per-node pass reads g, out, out_pos rows and writes the 16-byte record and da_tgt; the
+    walk reads per slot the index, the target's record and the gathered g row, per row h_j, a_src, da_tgt and writes dh,
+    da_src."""
+    if kind == 'fwd':
+        return slots * (4 + 4 + f * 4) + n * (4 + 2 * f * 4 + 8 + 4) + (n + 1) * 4
+    return n * (3 * f * 4 + 8 + 4 + 4 + 16 + 4) + slots * (4 + 16 + f * 4) + n * (f * 4 + 4 + 4 + f * 4 + 4) + (n + 1) * 4
 
 
 def load_peaks():
@@ -631,6 +644,20 @@ def run_ours(args, spec, rank, world, dev):
         spmm_events.append((s, e))
         return out
 
+    # the fused GAT passes (single GPU, heads = 1) do not go through ops.spmm: time them the same way
+    gat_events = {'fwd': [], 'bwd': []}
+    orig_gat = (ops.gat_sell_forward, ops.gat_sell_backward_one)
+
+    def _timed(fn, key):
+        def run(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            out = fn(*a, **k)
+            e.record()
+            gat_events[key].append((s, e))
+            return out
+        return run
+
     def bias_grad():  # the small result read back by the e2e leg: the gradient of the layer's bias
         for pname, prm in layer.named_parameters():
             if pname.endswith('bias'):
@@ -695,6 +722,7 @@ def run_ours(args, spec, rank, world, dev):
         step(x_loc, ei, playout)
     sync_all()
     ops.spmm = timed_spmm
+    ops.gat_sell_forward, ops.gat_sell_backward_one = _timed(orig_gat[0], 'fwd'), _timed(orig_gat[1], 'bwd')
     if multi:
         parallel.trace_report()   # GG_PEER_TRACE: only the timed steps are reported
     launches0 = ops.launch_count()
@@ -708,6 +736,7 @@ def run_ours(args, spec, rank, world, dev):
     end.record()
     sync_all()
     ops.spmm = orig_spmm
+    ops.gat_sell_forward, ops.gat_sell_backward_one = orig_gat
     exchange_trace = parallel.trace_report() if (multi and parallel._TRACE) else None
     launches = int(sum_over_ranks(ops.launch_count() - launches0))
     ms = max_over_ranks(start.elapsed_time(end)) / args.steps
@@ -735,6 +764,28 @@ def run_ours(args, spec, rank, world, dev):
                 'frac_dram': None,   # filled below: ncu DRAM traffic / this run's launch time / peak
                 'share_of_step': round(sum(spmm_ms) / args.steps / ms, 3)}
 
+    if gat_events['bwd'] and not spmm_ms:
+        # fused GAT: the dominant launch group is the one-pass backward (per-node record + walk over the CSC layout +
+        # split-row fix-up); the training forward is reported beside it
+        fb = [s.elapsed_time(e) for s, e in gat_events['bwd']]
+        ff = [s.elapsed_time(e) for s, e in gat_events['fwd']]
+        bytes_b = gat_pass_bytes('bwd', rows_local, slots_local, f_agg)
+        bytes_f = gat_pass_bytes('fwd', rows_local, slots_local, f_agg)
+        ach_b, ach_f = bytes_b / (np.mean(fb) * 1e-3) / 1e9, bytes_f / (np.mean(ff) * 1e-3) / 1e9
+        roofline.update({'kernel': 'gat_tstat_d_kernel + gat_sell_bwd_one_kernel + fixup (the whole edge-softmax / '
+                                   'aggregation backward in one walk over the CSC sliced-ELL layout)',
+                         'achieved': round(ach_b, 1), 'frac': round(ach_b / peak, 4), 'traffic': NCU_TRAFFIC.get((args.workload, 'bwd_one')),
+                         'algorithmic_bytes_per_launch': bytes_b, 'avg_launch_ms': round(float(np.mean(fb)), 4),
+                         'launches_timed': len(fb), 'share_of_step': round(sum(fb) / args.steps / ms, 3),
+                         'also': {'kernel': 'gat_sell_fwd_train_kernel + fixup (online softmax fused into the CSR '
+                                            'aggregation, writes out and out_pos)',
+                                  'achieved': round(ach_f, 1), 'frac': round(ach_f / peak, 4),
+                                  'algorithmic_bytes_per_launch': bytes_f, 'avg_launch_ms': round(float(np.mean(ff)), 4),
+                                  'launches_timed': len(ff), 'share_of_step': round(sum(ff) / args.steps / ms, 3),
+                                  'traffic': NCU_TRAFFIC.get((args.workload, 'fwd_train'))}})
+        if roofline['also']['traffic']:
+            roofline['also']['frac_dram'] = round(roofline['also']['traffic'] / (np.mean(ff) * 1e-3) / 1e9 / peak, 4)
+        avg_spmm_ms = float(np.mean(fb))
     if roofline['traffic']:
         roofline['frac_dram'] = round(roofline['traffic'] / (avg_spmm_ms * 1e-3) / 1e9 / peak, 4)
     # ---- layout build alone (amortised over layers/epochs in training; reported, not in `value`) ---

@@ -681,25 +681,41 @@ __global__ void __launch_bounds__(256) gat_tstat_d_kernel(const float* __restric
                                                           float4* __restrict__ tstat, float* __restrict__ da_tgt) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * 8;
-    for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += warps) {
-        float dsum = 0.f, psum = 0.f;
+    // two rows per warp and trip: six 16-byte loads in flight per lane (one row per trip ran at 4.0 TB/s)
+    for (int64_t i0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i0 < n; i0 += 2 * warps) {
+        const int64_t i1 = i0 + warps;
+        const bool two = i1 < n;
+        float ds[2] = {0.f, 0.f}, ps[2] = {0.f, 0.f};
         for (int c = lane * 4; c < f; c += 128) {
-            const float4 gv = ldg_nc_f4(reinterpret_cast<const float4*>(g + i * ldg + c));
-            float4 ov = ldg_nc_f4(reinterpret_cast<const float4*>(out + i * ldo + c));
-            const float4 pv = ldg_nc_f4(reinterpret_cast<const float4*>(out_pos + i * ld_pos + c));
-            if (bias) {
-                const float4 b = *reinterpret_cast<const float4*>(bias + c);
-                ov.x -= b.x; ov.y -= b.y; ov.z -= b.z; ov.w -= b.w;
+            float4 gv[2], ov[2], pv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int64_t i = u ? i1 : i0;
+                if (u && !two) { gv[u] = ov[u] = pv[u] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+                gv[u] = ldg_nc_f4(reinterpret_cast<const float4*>(g + i * ldg + c));
+                ov[u] = ldg_nc_f4(reinterpret_cast<const float4*>(out + i * ldo + c));
+                pv[u] = ldg_nc_f4(reinterpret_cast<const float4*>(out_pos + i * ld_pos + c));
             }
-            dsum += dot4(gv, ov);
-            psum += dot4(gv, pv);
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) b = *reinterpret_cast<const float4*>(bias + c);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                ov[u].x -= b.x; ov[u].y -= b.y; ov[u].z -= b.z; ov[u].w -= b.w;
+                ds[u] += dot4(gv[u], ov[u]);
+                ps[u] += dot4(gv[u], pv[u]);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
-            psum += __shfl_xor_sync(0xffffffffu, psum, o);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                ds[u] += __shfl_xor_sync(0xffffffffu, ds[u], o);
+                ps[u] += __shfl_xor_sync(0xffffffffu, ps[u], o);
+            }
         }
-        if (lane == 0) {
+        if (lane < 2 && (lane == 0 || two)) {
+            const int64_t i = lane ? i1 : i0;
+            const float dsum = lane ? ds[1] : ds[0], psum = lane ? ps[1] : ps[0];
             const float2 st = rowstat[i];
             tstat[i] = make_float4(a_tgt[i], st.x, 1.0f / (st.y + 1e-16f), dsum);
             da_tgt[i] = (1.0f - slope) * (psum - dsum * a_pos[i]);

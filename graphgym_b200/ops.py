@@ -680,17 +680,8 @@ def gat_sell_backward(csr, csc, csc2csr, h, att, slope, bias, rowstat, a_tgt, a_
     ws_bytes = int(L.gg_gat_sell_workspace_bytes(max(s1.partial_rows, s2.partial_rows), f))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     if pos is not None:
-        # one heavy pass over the CSC layout: each edge's g_i is gathered once for both dalpha and dH
-        out_pos, a_pos = pos
-        dh = torch.empty((n, f), dtype=torch.float32, device=dev)
-        tstat = torch.empty((max(n, 1), 4), dtype=torch.float32, device=dev)
-        att_tgt, att_src = att[0, :f].contiguous(), att[0, f:].contiguous()
-        check(L.gg_gat_sell_bwd_one_f32(_ptr(s2.chunk_ptr), s2.chunks, _ptr(s2.idx), _ptr(s2.vdst), _ptr(s2.hub_rows),
-                                        _ptr(s2.hub_pptr), s2.hubs, s2.partial_rows, _ptr(h), ldh, _ptr(g), ldg, _ptr(out),
-                                        ldo, _ptr(bias), _ptr(out_pos), out_pos.stride(0), _ptr(a_pos), _ptr(a_tgt),
-                                        _ptr(a_src), _ptr(rowstat), _ptr(att_src), _ptr(att_tgt), n, f, float(slope),
-                                        _ptr(dh), f, _ptr(da_tgt), _ptr(da_src), _ptr(tstat), _ptr(ws), ws_bytes,
-                                        _stream()), "gg_gat_sell_bwd_one_f32")
+        dh = gat_sell_backward_one(s2, h, ldh, g, ldg, out, ldo, bias, pos, a_tgt, a_src, rowstat, att, slope, da_tgt,
+                                   da_src, ws, ws_bytes)
         return dh, _gat_att_grad(h, ldh, da_tgt, da_src, n, f)
     dz = _f32((csr.num_slots,), dev)
     check(L.gg_gat_sell_bwd_edge_f32(_ptr(s1.chunk_ptr), s1.chunks, _ptr(s1.idx), _ptr(s1.slot_of), _ptr(s1.vdst),
@@ -708,6 +699,23 @@ def gat_sell_backward(csr, csc, csc2csr, h, att, slope, bias, rowstat, a_tgt, a_
                                     _ptr(att_tgt), n, f, float(slope), _ptr(dh), f, _ptr(da_src), _ptr(tstat), _ptr(ws),
                                     ws_bytes, _stream()), "gg_gat_sell_bwd_src_f32")
     return dh, _gat_att_grad(h, ldh, da_tgt, da_src, n, f)
+
+
+def gat_sell_backward_one(s2, h, ldh, g, ldg, out, ldo, bias, pos, a_tgt, a_src, rowstat, att, slope, da_tgt, da_src, ws,
+                          ws_bytes):
+    """The one-pass backward's launches (per-node record, the walk over the CSC layout, split-row fix-up) -> dh."""
+    out_pos, a_pos = pos
+    n, f = h.shape
+    dh = torch.empty((n, f), dtype=torch.float32, device=h.device)
+    tstat = torch.empty((max(n, 1), 4), dtype=torch.float32, device=h.device)
+    att_tgt, att_src = att[0, :f].contiguous(), att[0, f:].contiguous()
+    check(lib().gg_gat_sell_bwd_one_f32(_ptr(s2.chunk_ptr), s2.chunks, _ptr(s2.idx), _ptr(s2.vdst), _ptr(s2.hub_rows),
+                                        _ptr(s2.hub_pptr), s2.hubs, s2.partial_rows, _ptr(h), ldh, _ptr(g), ldg, _ptr(out),
+                                        ldo, _ptr(bias), _ptr(out_pos), out_pos.stride(0), _ptr(a_pos), _ptr(a_tgt),
+                                        _ptr(a_src), _ptr(rowstat), _ptr(att_src), _ptr(att_tgt), n, f, float(slope),
+                                        _ptr(dh), f, _ptr(da_tgt), _ptr(da_src), _ptr(tstat), _ptr(ws), ws_bytes,
+                                        _stream()), "gg_gat_sell_bwd_one_f32")
+    return dh
 
 
 def _gat_att_grad(h, ldh, da_tgt, da_src, n, f):

@@ -20,6 +20,8 @@
 //     tcgen05.commit onto the stage's mma_done mbarrier; three stages, A rows four slabs ahead in registers;
 //   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> shared memory -> bias / ReLU / mask ->
 //     coalesced 512-byte row stores.
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace gg {
@@ -499,6 +501,326 @@ __global__ void __launch_bounds__(TC_BLOCK, GG_TC_CTAS_PER_SM) tc_gemm_kernel(Tc
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent NN kernel for the layer-sized transforms (one unscaled segment, K <= 128, F <= 128: X W and dH W^T of
+// gcnconv / gatconv / ginconv).  The per-tile kernel above is a chain of dependent latencies per CTA (barrier and
+// TMEM set-up, first slab from DRAM, seven slabs through a three-slot ring, accumulator drain, stores) with at most
+// three CTAs per SM to overlap them: 0.82 ms for 2.45 M x 100 -> 128 = 0.41 of the HBM copy peak, and every CTA
+// re-reads the 112 KB B image from L2.  Here one CTA per SM walks row tiles without ever draining its pipeline:
+//   warp 0     producer   the B image ONCE (resident in shared memory), then A slabs of 128 rows x 32 k by TMA
+//                         (2-D tensor map, SWIZZLE_128B) into a ring that stays full across tile boundaries
+//   warps 2-5  converters thread = row: the slab row into registers (the ring slot is free again at once), then
+//                         hi = x and lo = x - trunc_tf32(x) into TENSOR MEMORY (tcgen05.st, lane = row, column = k):
+//                         the A operand never goes back to shared memory
+//   warp 1     issuer     tcgen05.mma with A from TMEM and B from the resident image, into one of TWO 128-column
+//                         accumulators (the tensor core reads the TF32 bits of hi)
+//   warps 6-9  epilogue   TMEM -> registers (bias / ReLU) -> per-warp 4 KB staging -> ONE TMA store of 32 rows x 32
+//                         columns (the tensor map clips rows >= n and columns >= f), overlapped with the next tile's
+//                         MMAs through the second accumulator; with a ReLU mask: staged, coalesced 128-byte row pieces
+// Shared-memory traffic decides the design: an MMA of 8 k with both operands in shared memory reads 8 KB in its
+// 64 cycles — the whole 128 B/clk of the SM — so the first version (A hi = raw slab, A lo = a second shared slab:
+// 0.56 ms, 0.61 of the copy peak) had no bandwidth left for the TMA writes, the converters and the epilogue staging.
+// With A in TMEM the MMAs read 4 KB each, the lo slabs disappear (the ring grows from 4 to 6 slots) and a ring slot
+// is recycled after the converters' read instead of after the MMAs (0.52 ms).  ncu then showed the issuer waiting
+// for a free accumulator and the epilogue warps in a chain of shared loads, parameter loads and predicated row stores:
+// the stores went to TMA.  TMEM: 2 x 128 accumulator columns + 4 operand stages x (32 hi + 32 lo) columns = all 512.
+// ---------------------------------------------------------------------------------------------
+constexpr int PS_BK = 32;                              // k per A slab (one 128-byte swizzle row)
+constexpr int PS_SLAB_BYTES = TC_BM * PS_BK * 4;       // 16384
+constexpr int PS_A_STAGES = 4;                         // TMEM operand stages of 64 columns (hi | lo)
+constexpr int PS_MAX_RAW = 8;
+constexpr int PS_STAGING_BYTES = 4 * 32 * 32 * 4;      // four epilogue warps x 32 rows x 32 columns
+constexpr int PS_THREADS = 10 * 32;
+constexpr int PS_SMEM_MAX = 232448 - 2048;             // dynamic budget (static barriers and the base alignment aside)
+
+struct PsArgs {
+    const float* b_image;   // [k_slabs16][2][TC_TILE_BYTES / 4] of N-tile 0
+    int k;                  // reduction length (multiple of 4)
+    int k_slabs16;          // 16-k slabs of the B image
+    int raw_slots;
+    int64_t n;
+    int f;
+    const float* bias;
+    int act;
+    const float* relu_mask;
+    int64_t ld_mask;
+    float* out;
+    int64_t ldo;
+};
+
+// K-major SWIZZLE_128B descriptor: 8-row groups 1024 B apart, layout type 2; the k-step inside the 128-byte row is
+// selected by advancing the start address (32 B per 8 tf32)
+__device__ __forceinline__ uint64_t ps_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+__device__ __forceinline__ void ps_tma_load_2d(void* dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            tc_smem_u32(dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(tc_smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+__device__ __forceinline__ void ps_tma_store_2d(const void* tmap, int c0, int c1, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(tc_smem_u32(src))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+template <bool MASKED>
+__global__ void __launch_bounds__(PS_THREADS, 1) tc_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                        const __grid_constant__ CUtensorMap tmap_out,
+                                                                        const PsArgs g) {
+    extern __shared__ uint8_t ps_smem_raw[];
+    __shared__ __align__(8) uint64_t raw_full[PS_MAX_RAW], raw_free[PS_MAX_RAW];
+    __shared__ __align__(8) uint64_t a_full[PS_A_STAGES], a_free[PS_A_STAGES];
+    __shared__ __align__(8) uint64_t acc_full[2], acc_free[2];
+    __shared__ __align__(8) uint64_t b_ready;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* smem = ps_smem_raw + ((1024u - (tc_smem_u32(ps_smem_raw) & 1023u)) & 1023u);
+    const int R = g.raw_slots;
+    uint8_t* s_raw = smem;
+    uint8_t* s_b = s_raw + R * PS_SLAB_BYTES;
+    uint8_t* s_stage = s_b + g.k_slabs16 * 2 * TC_TILE_BYTES;
+
+    if (tid == 0) {
+        for (int i = 0; i < PS_MAX_RAW; ++i) {
+            tc_mbar_init(&raw_full[i], 1);
+            tc_mbar_init(&raw_free[i], 128);
+        }
+        for (int i = 0; i < PS_A_STAGES; ++i) {
+            tc_mbar_init(&a_full[i], 128);
+            tc_mbar_init(&a_free[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc_mbar_init(&acc_full[i], 1);
+            tc_mbar_init(&acc_free[i], 128);
+        }
+        tc_mbar_init(&b_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // all 512 columns: two accumulators + four operand stages
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         tc_smem_u32(&tmem_base_smem)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const int64_t tiles = (g.n + TC_BM - 1) / TC_BM;
+    const int slabs = (g.k + PS_BK - 1) / PS_BK;     // A slabs per tile
+    const int ksteps = (g.k + 7) / 8;                // MMAs of 8 k per operand pair and tile
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== producer =====
+            const uint32_t b_bytes = (uint32_t)g.k_slabs16 * 2u * TC_TILE_BYTES;
+            tc_expect_tx(&b_ready, b_bytes);
+            for (int s = 0; s < g.k_slabs16; ++s)
+                tc_bulk_g2s(s_b + s * 2 * TC_TILE_BYTES, g.b_image + (int64_t)s * (2 * TC_TILE_BYTES / 4), 2 * TC_TILE_BYTES,
+                            &b_ready);
+            int item = 0;
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+                for (int s = 0; s < slabs; ++s, ++item) {
+                    const int slot = item % R, use = item / R;
+                    if (use > 0) tc_mbar_wait(&raw_free[slot], (uint32_t)(use - 1) & 1u);
+                    tc_expect_tx(&raw_full[slot], PS_SLAB_BYTES);
+                    ps_tma_load_2d(s_raw + slot * PS_SLAB_BYTES, &tmap_a, s * PS_BK, (int)(t * TC_BM), &raw_full[slot]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== issuer =====
+            tc_mbar_wait(&b_ready, 0u);
+            int item = 0, it = 0;
+            for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+                const int buf = it & 1, buse = it >> 1;
+                if (buse > 0) tc_mbar_wait(&acc_free[buf], (uint32_t)(buse - 1) & 1u);
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_TMEM_COLS;
+                for (int s = 0; s < slabs; ++s, ++item) {
+                    const int stage = item % PS_A_STAGES;
+                    tc_mbar_wait(&a_full[stage], (uint32_t)(item / PS_A_STAGES) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = tmem_base + 2 * TC_TMEM_COLS + (uint32_t)stage * 64u, a_lo = a_hi + 32u;
+#pragma unroll
+                    for (int j = 0; j < PS_BK / 8; ++j) {
+                        const int gs = s * (PS_BK / 8) + j;          // k-step of the tile
+                        if (gs < ksteps) {
+                            const uint32_t b_hi = tc_smem_u32(s_b) + (uint32_t)(gs >> 1) * (2 * TC_TILE_BYTES) +
+                                                  (uint32_t)(gs & 1) * 2 * TC_LBO;
+                            const uint32_t b_lo = b_hi + TC_TILE_BYTES;
+                            tc_mma_ts(d_tmem, a_hi + j * 8, tc_smem_desc(b_hi), gs > 0 ? 1u : 0u);
+                            tc_mma_ts(d_tmem, a_hi + j * 8, tc_smem_desc(b_lo), 1u);
+                            tc_mma_ts(d_tmem, a_lo + j * 8, tc_smem_desc(b_hi), 1u);
+                        }
+                    }
+                    tc_commit(&a_free[stage]);
+                }
+                tc_commit(&acc_full[buf]);
+            }
+        }
+    } else if (warp < 6) {
+        // ===== converters: thread = row = TMEM lane (a warp reaches the lanes of its quarter, warp % 4) =====
+        const int q = warp & 3, row = q * 32 + lane;
+        const uint32_t t_lane = tmem_base + 2 * TC_TMEM_COLS + ((uint32_t)(q * 32) << 16);
+        int item = 0;
+        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int s = 0; s < slabs; ++s, ++item) {
+                const int slot = item % R, stage = item % PS_A_STAGES;
+                tc_mbar_wait(&raw_full[slot], (uint32_t)(item / R) & 1u);
+                const uint8_t* src = s_raw + slot * PS_SLAB_BYTES + row * 128;
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {   // logical 16-byte chunk c of the row sits at chunk c ^ (row % 8)
+                    const float4 v = *reinterpret_cast<const float4*>(src + ((c ^ (row & 7)) * 16));
+                    hi[4 * c] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+                    hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+                }
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const float x = __uint_as_float(hi[e]);
+                    lo[e] = __float_as_uint(x - trunc_tf32(x));
+                }
+                tc_arrive(&raw_free[slot]);      // the row is in registers: the producer may refill the slot
+                if (item >= PS_A_STAGES) {
+                    tc_mbar_wait(&a_free[stage], (uint32_t)(item / PS_A_STAGES - 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                tc_st32(t_lane + (uint32_t)stage * 64u, hi);
+                tc_st32(t_lane + (uint32_t)stage * 64u + 32u, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                tc_arrive(&a_full[stage]);
+            }
+        }
+    } else {
+        // ===== epilogue: warp q of the four reads TMEM lanes [32 q, 32 q + 32) =====
+        const int q = warp & 3;
+        uint8_t* stg = s_stage + (warp - 6) * (32 * 32 * 4);
+        int it = 0;
+        for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+            const int buf = it & 1;
+            tc_mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + (uint32_t)buf * TC_TMEM_COLS + ((uint32_t)(q * 32) << 16);
+            const int64_t row_base = t * TC_BM + q * 32;
+#pragma unroll 1
+            for (int part = 0; part < 4; ++part) {
+                if (part * 32 >= g.f) {   // columns past f: nothing to store (warp-uniform)
+                    if (part == 3) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        tc_arrive(&acc_free[buf]);
+                    }
+                    continue;
+                }
+                uint32_t acc[32];
+                tc_ld32(taddr + (uint32_t)(part * 32), acc);
+                if (part == 3 || (part + 1) * 32 >= g.f) {   // last read of this accumulator: hand it back to the issuer
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (part == 3) tc_arrive(&acc_free[buf]);
+                }
+                if constexpr (!MASKED) {
+                    // this thread's row, 32 columns: bias / ReLU in registers, then the swizzled staging row
+                    if (g.bias) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (part * 32 + e * 4 < g.f) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + part * 32 + e * 4));
+                            acc[4 * e] = __float_as_uint(__uint_as_float(acc[4 * e]) + b4.x);
+                            acc[4 * e + 1] = __float_as_uint(__uint_as_float(acc[4 * e + 1]) + b4.y);
+                            acc[4 * e + 2] = __float_as_uint(__uint_as_float(acc[4 * e + 2]) + b4.z);
+                            acc[4 * e + 3] = __float_as_uint(__uint_as_float(acc[4 * e + 3]) + b4.w);
+                        }
+                    }
+                    if (g.act == GG_ACT_RELU) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) acc[e] = __float_as_uint(fmaxf(__uint_as_float(acc[e]), 0.f));
+                    }
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read the staging
+                    __syncwarp();
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        *reinterpret_cast<float4*>(stg + lane * 128 + ((e ^ (lane & 7)) * 16)) =
+                            make_float4(__uint_as_float(acc[4 * e]), __uint_as_float(acc[4 * e + 1]),
+                                        __uint_as_float(acc[4 * e + 2]), __uint_as_float(acc[4 * e + 3]));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) ps_tma_store_2d(&tmap_out, part * 32, (int)row_base, stg);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        *reinterpret_cast<float4*>(stg + lane * 128 + ((e ^ (lane & 7)) * 16)) =
+                            make_float4(__uint_as_float(acc[4 * e]), __uint_as_float(acc[4 * e + 1]),
+                                        __uint_as_float(acc[4 * e + 2]), __uint_as_float(acc[4 * e + 3]));
+                    __syncwarp();
+                    const int piece = lane & 7;
+                    const int c = part * 32 + piece * 4;
+                    const bool col_ok = c < g.f;
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + c));
+                    float4 v[8], m[8];
+#pragma unroll
+                    for (int r4 = 0; r4 < 8; ++r4) {   // all loads first: eight independent shared and mask loads in flight
+                        const int rr = r4 * 4 + (lane >> 3);
+                        const int64_t r = row_base + rr;
+                        v[r4] = *reinterpret_cast<const float4*>(stg + rr * 128 + ((piece ^ (rr & 7)) * 16));
+                        m[r4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (r < g.n && col_ok) m[r4] = __ldg(reinterpret_cast<const float4*>(g.relu_mask + r * g.ld_mask + c));
+                    }
+#pragma unroll
+                    for (int r4 = 0; r4 < 8; ++r4) {
+                        const int64_t r = row_base + r4 * 4 + (lane >> 3);
+                        float4 x = v[r4];
+                        x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                        if (g.act == GG_ACT_RELU) {
+                            x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+                        }
+                        x.x = m[r4].x > 0.f ? x.x : 0.f; x.y = m[r4].y > 0.f ? x.y : 0.f;
+                        x.z = m[r4].z > 0.f ? x.z : 0.f; x.w = m[r4].w > 0.f ? x.w : 0.f;
+                        if (r < g.n && col_ok) *reinterpret_cast<float4*>(g.out + r * g.ldo + c) = x;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        if (!MASKED && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Weight gradient on the tensor cores:  partial[split][K,F] = sum_{r in split} A[row(r),:]^T G[row(r),:]
 // (dW = X^T dH; dW_id = X[id]^T dH[id]).  M = K, N = F, the reduction runs over matrix ROWS, so both
 // operands are transposed on their way to the operand stage:
@@ -785,6 +1107,83 @@ static int tc_plan(const gg_gemm_segment* segs, int num_segments, TcPiece* piece
 }
 constexpr int kTcMaxPieces = 256;
 
+// ---- persistent path: eligibility, tensor map, launch ----
+typedef CUresult (*PsEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PsEncodeTiled ps_encoder() {
+    static PsEncodeTiled fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<PsEncodeTiled>(p);
+    }();
+    return fn;
+}
+static int ps_raw_slots(int k_slabs16) {
+    const int64_t left = (int64_t)PS_SMEM_MAX - 1024 - (int64_t)k_slabs16 * 2 * TC_TILE_BYTES - PS_STAGING_BYTES;
+    int64_t r = left / PS_SLAB_BYTES;
+    return (int)(r > PS_MAX_RAW ? PS_MAX_RAW : r);
+}
+static bool ps_eligible(const gg_gemm_segment& s, const TcPiece& pc, int64_t n, int64_t f, const float* bias,
+                        const float* relu_mask, int64_t ld_mask, const float* out, int64_t ldo) {
+    static const bool on = [] { const char* e = getenv("GG_GEMM_PERSIST"); return !e || e[0] != '0'; }();
+    if (!on || s.scale || pc.k_off != 0 || pc.k_len != s.k) return false;
+    if (s.k < 4 || s.k > 128 || s.k % 4 || s.lda % 4 || (reinterpret_cast<uintptr_t>(s.a) & 15)) return false;
+    if (f > TC_BN || f % 4 || ldo % 4 || (reinterpret_cast<uintptr_t>(out) & 15)) return false;
+    if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return false;
+    if (relu_mask && (ld_mask % 4 || (reinterpret_cast<uintptr_t>(relu_mask) & 15))) return false;
+    if (n < (int64_t)TC_BM * kNumSMs || n >= ((int64_t)1 << 31)) return false;   // small problems: the per-tile kernel
+    return ps_raw_slots(tc_slabs(s.k)) >= 2 && ps_encoder() != nullptr;
+}
+static int ps_launch(const gg_gemm_segment& s, int b_trans, int64_t n, int64_t f, const float* bias, int act,
+                     const float* relu_mask, int64_t ld_mask, float* out, int64_t ldo, void* workspace, cudaStream_t st) {
+    PsEncodeTiled enc = ps_encoder();
+    if (!enc) return GG_ERR_UNSUPPORTED;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)s.k, (cuuint64_t)n};
+    const cuuint64_t gstride[1] = {(cuuint64_t)s.lda * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)PS_BK, (cuuint32_t)TC_BM};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(s.a), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return GG_ERR_UNSUPPORTED;
+    CUtensorMap tmap_out;
+    const cuuint64_t odim[2] = {(cuuint64_t)f, (cuuint64_t)n};
+    const cuuint64_t ostride[1] = {(cuuint64_t)ldo * 4};
+    const cuuint32_t obox[2] = {32, 32};
+    const CUresult ro = enc(&tmap_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, odim, ostride, obox, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (ro != CUDA_SUCCESS) return GG_ERR_UNSUPPORTED;
+    Carver c(workspace);
+    const int k16 = tc_slabs(s.k);
+    float* image = c.take<float>(tc_image_floats(s.k, f));
+    const int64_t chunks = (int64_t)k16 * (TC_BK / 4) * TC_BN;
+    b_image_kernel<<<(int)ceil_div(chunks, 256), 256, 0, st>>>(s.b, s.ldb, b_trans, (int)s.k, (int)f, k16, 1, image);
+    GG_LAUNCHED();
+    PsArgs g{};
+    g.b_image = image; g.k = (int)s.k; g.k_slabs16 = k16; g.raw_slots = ps_raw_slots(k16);
+    g.n = n; g.f = (int)f; g.bias = bias; g.act = act; g.relu_mask = relu_mask; g.ld_mask = ld_mask; g.out = out; g.ldo = ldo;
+    const int smem = 1024 + g.raw_slots * PS_SLAB_BYTES + k16 * 2 * TC_TILE_BYTES + PS_STAGING_BYTES;
+    static bool attr_done = false;
+    if (!attr_done) {
+        GG_CUDA(cudaFuncSetAttribute(tc_gemm_persist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM_MAX));
+        GG_CUDA(cudaFuncSetAttribute(tc_gemm_persist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_SMEM_MAX));
+        attr_done = true;
+    }
+    const int64_t tiles = ceil_div(n, TC_BM);
+    const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+    if (relu_mask) tc_gemm_persist_kernel<true><<<grid, PS_THREADS, smem, st>>>(tmap, tmap_out, g);
+    else tc_gemm_persist_kernel<false><<<grid, PS_THREADS, smem, st>>>(tmap, tmap_out, g);
+    GG_LAUNCHED();
+    return GG_OK;
+}
+
 extern "C" {
 
 size_t gg_id_gemm_tc_workspace_bytes(const gg_gemm_segment* segs, int num_segments, int64_t f) {
@@ -825,6 +1224,10 @@ int gg_id_gemm_tc_f32(const gg_gemm_segment* segs, int num_segments, int b_trans
         return GG_ERR_WORKSPACE;
     }
     cudaStream_t st = as_stream(stream);
+    if (np == 1 && ps_eligible(segs[pieces[0].seg], pieces[0], n, f, bias, relu_mask, ld_mask, out, ldo)) {
+        const int rc = ps_launch(segs[pieces[0].seg], b_trans, n, f, bias, act, relu_mask, ld_mask, out, ldo, workspace, st);
+        if (rc != GG_ERR_UNSUPPORTED) return rc;   // no tensor-map entry point in this driver: the per-tile kernel serves
+    }
     static bool attr_done = false;
     if (!attr_done) {
         GG_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NN_SMEM_BYTES));

@@ -107,3 +107,32 @@ def test_tc_gemm_four_segments_sage_id_shape(cuda):
     want = z @ w.double()
     want[ids] += z[ids] @ wid.double()
     assert rel_err(got, want) < FP32_TOL
+
+
+@pytest.mark.parametrize('n,k,f,b_trans', [(148 * 128, 100, 128, False), (148 * 128 + 77, 128, 100, True),
+                                           (60000, 36, 36, False), (33333, 4, 128, False), (40000, 64, 8, True),
+                                           (148 * 128 * 3 + 1, 100, 128, False)])
+def test_persistent_layer_gemm(cuda, gemm_mode, n, k, f, b_trans):
+    """One unscaled segment, K <= 128, F <= 128, at least one row tile per SM: the persistent tcgen05 kernel (B image
+    resident in shared memory, A slabs by TMA into a ring that never drains, two TMEM accumulators).  Strided A and
+    out, bias + ReLU and the ReLU-mask epilogue; fp64 reference evaluated on the device."""
+    g = torch.Generator(device=cuda).manual_seed(n + k + f)
+    xa = torch.randn(n, k + 4, generator=g, device=cuda)
+    x = xa[:, :k]                                              # row stride k + 4
+    w = torch.randn((f, k) if b_trans else (k, f), generator=g, device=cuda)
+    bias = torch.randn(f, generator=g, device=cuda)
+    m = torch.randn(n, f, generator=g, device=cuda)
+    wd = w.double().t() if b_trans else w.double()
+    want = x.double() @ wd
+    out = torch.full((n, f + 4), 7.0, device=cuda)
+    got = ops.id_gemm([(x, w, None)], n, f, b_trans=b_trans, out=out[:, :f])
+    assert rel_err(got, want) < FP32_TOL
+    assert bool((out[:, f:] == 7.0).all())                      # nothing written outside the F columns
+    got = ops.id_gemm([(x, w, None)], n, f, b_trans=b_trans, bias=bias, act=ops.ACT_RELU)
+    assert rel_err(got, (want + bias.double()).relu()) < FP32_TOL
+    got = ops.id_gemm([(x, w, None)], n, f, b_trans=b_trans, relu_mask=m)
+    assert rel_err(got, want * (m > 0)) < FP32_TOL
+    # row blocks are independent: the last rows equal a small-problem launch (per-tile kernel) of the same rows
+    tail = ops.id_gemm([(x[-300:], w, None)], 300, f, b_trans=b_trans)
+    full = ops.id_gemm([(x, w, None)], n, f, b_trans=b_trans)
+    assert rel_err(full[-300:], tail) < 2e-6

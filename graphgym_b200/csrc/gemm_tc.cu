@@ -1045,22 +1045,254 @@ __global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_tn_kernel(TnTcArgs g) {
     }
 }
 
-// out[e] = sum_s part[s][e] in fp64, s ascending (fixed order)
-__global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict__ part, int64_t splits, int64_t rows,
-                                                        int64_t cols, float* __restrict__ out, int64_t ldo) {
-    const int64_t total = rows * cols;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-         e += (int64_t)gridDim.x * blockDim.x) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int64_t p = 0;
-        for (; p + 3 < splits; p += 4) {
-            s0 += (double)part[p * total + e];
-            s1 += (double)part[(p + 1) * total + e];
-            s2 += (double)part[(p + 2) * total + e];
-            s3 += (double)part[(p + 3) * total + e];
+// ---------------------------------------------------------------------------------------------
+// Persistent weight-gradient kernel (dW = X^T dH for K <= 128, F <= 128, plain rows: every layer-sized call).
+// The kernel above moves each 16-row slab through shared memory five times (raw, two column reads, four operand
+// slabs, MMA reads of both operands: 110 KB per 16 rows = 0.47 ms of shared-memory time alone), keeps 32 KB in flight
+// per CTA and empties its whole pipeline every 256 rows to drain the accumulator: 0.83 ms for 2.45 M rows = 0.41 of
+// the copy peak.  Here, one CTA per SM:
+//   warp 0       producer     X and dH slabs of 32 rows x 128 columns by TMA (columns past K / F and rows past n
+//                             arrive as zeros), four 32 KB slots that stay full across segment boundaries
+//   warps 4-7    A side       thread m reads COLUMN m of the X slab (conflict-free), splits hi / lo and stores them
+//                             into tensor memory (lane = m, column = row of the slab): the transposed A operand
+//                             never goes back to shared memory
+//   warps 8-11   B side       thread c reads column c of the dH slab and writes the K-major hi / lo operand slabs
+//   warp 1       issuer       tcgen05.mma (A from TMEM), 256-row segments alternating between two accumulators
+//   warps 12-15  drain        accumulator -> registers -> 4 KB staging -> TMA store (first segment) or TMA
+//                             reduce-add (later ones) into the CTA's partial tile, which stays in L2; segment s is
+//                             drained while segment s + 1 is multiplied.  The adds of one tile are issued in segment
+//                             order and each is complete before the next is issued: deterministic.
+// The per-CTA partials are reduced in fp64 by tn_reduce_kernel as before.
+// ---------------------------------------------------------------------------------------------
+constexpr int TP_ROWS = 32;                              // reduction rows per slab
+constexpr int TP_HALF_BYTES = TP_ROWS * TC_BM * 4;       // 16384: one operand's raw slab, and one hi or lo B slab
+constexpr int TP_RAW_BYTES = 2 * TP_HALF_BYTES;
+constexpr int TP_RAW_SLOTS = 4;
+constexpr int TP_B_STAGES = 2;
+constexpr int TP_A_STAGES = 4;
+constexpr int TP_SEG_SLABS = kTnRowsPerSplit / TP_ROWS;  // 8 slabs per accumulator segment
+constexpr int TP_THREADS = 16 * 32;
+constexpr int TP_SMEM_BYTES = 1024 + TP_RAW_SLOTS * TP_RAW_BYTES + TP_B_STAGES * 2 * TP_HALF_BYTES + PS_STAGING_BYTES;
+static_assert(TP_SMEM_BYTES <= PS_SMEM_MAX, "persistent TN kernel: shared memory plan too large");
+
+struct TpArgs {
+    int64_t n;
+    int k, f;
+    int64_t rows_per_cta;   // multiple of kTnRowsPerSplit
+};
+
+__device__ __forceinline__ void tp_tma_reduce_add_2d(const void* tmap, int c0, int c1, const void* src) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap),
+                 "r"(c0), "r"(c1), "r"(tc_smem_u32(src))
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 1) tc_gemm_tn_persist_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                                                                           const __grid_constant__ CUtensorMap tmap_g,
+                                                                           const __grid_constant__ CUtensorMap tmap_part,
+                                                                           const TpArgs g) {
+    extern __shared__ uint8_t tp_smem_raw[];
+    __shared__ __align__(8) uint64_t raw_full[TP_RAW_SLOTS], raw_free[TP_RAW_SLOTS];
+    __shared__ __align__(8) uint64_t a_full[TP_A_STAGES], a_free[TP_A_STAGES];
+    __shared__ __align__(8) uint64_t b_full[TP_B_STAGES], b_free[TP_B_STAGES];
+    __shared__ __align__(8) uint64_t acc_full[2], acc_free[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* smem = tp_smem_raw + ((1024u - (tc_smem_u32(tp_smem_raw) & 1023u)) & 1023u);
+    uint8_t* s_raw = smem;
+    uint8_t* s_b = s_raw + TP_RAW_SLOTS * TP_RAW_BYTES;
+    uint8_t* s_stage = s_b + TP_B_STAGES * 2 * TP_HALF_BYTES;
+
+    if (tid == 0) {
+        for (int i = 0; i < TP_RAW_SLOTS; ++i) {
+            tc_mbar_init(&raw_full[i], 1);
+            tc_mbar_init(&raw_free[i], 256);
         }
-        for (; p < splits; ++p) s0 += (double)part[p * total + e];
-        out[(e / cols) * ldo + (e % cols)] = (float)((s0 + s1) + (s2 + s3));
+        for (int i = 0; i < TP_A_STAGES; ++i) {
+            tc_mbar_init(&a_full[i], 128);
+            tc_mbar_init(&a_free[i], 1);
+        }
+        for (int i = 0; i < TP_B_STAGES; ++i) {
+            tc_mbar_init(&b_full[i], 128);
+            tc_mbar_init(&b_free[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc_mbar_init(&acc_full[i], 1);
+            tc_mbar_init(&acc_free[i], 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         tc_smem_u32(&tmem_base_smem)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    const int64_t r_beg = (int64_t)blockIdx.x * g.rows_per_cta;
+    const int64_t r_end = r_beg + g.rows_per_cta < g.n ? r_beg + g.rows_per_cta : g.n;
+    const int total = r_end > r_beg ? (int)((r_end - r_beg + TP_ROWS - 1) / TP_ROWS) : 0;
+    const int nseg = (total + TP_SEG_SLABS - 1) / TP_SEG_SLABS;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== producer =====
+            for (int i = 0; i < total; ++i) {
+                const int slot = i % TP_RAW_SLOTS, use = i / TP_RAW_SLOTS;
+                if (use > 0) tc_mbar_wait(&raw_free[slot], (uint32_t)(use - 1) & 1u);
+                const int r0 = (int)(r_beg + (int64_t)i * TP_ROWS);
+                tc_expect_tx(&raw_full[slot], TP_RAW_BYTES);
+                ps_tma_load_2d(s_raw + slot * TP_RAW_BYTES, &tmap_a, 0, r0, &raw_full[slot]);
+                ps_tma_load_2d(s_raw + slot * TP_RAW_BYTES + TP_HALF_BYTES, &tmap_g, 0, r0, &raw_full[slot]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== issuer =====
+            for (int i = 0; i < total; ++i) {
+                const int seg = i / TP_SEG_SLABS, in_seg = i % TP_SEG_SLABS, buf = seg & 1;
+                if (in_seg == 0 && seg >= 2) tc_mbar_wait(&acc_free[buf], (uint32_t)((seg >> 1) - 1) & 1u);
+                const int as = i % TP_A_STAGES, bs = i % TP_B_STAGES;
+                tc_mbar_wait(&a_full[as], (uint32_t)(i / TP_A_STAGES) & 1u);
+                tc_mbar_wait(&b_full[bs], (uint32_t)(i / TP_B_STAGES) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * TC_TMEM_COLS;
+                const uint32_t a_hi = tmem_base + 2 * TC_TMEM_COLS + (uint32_t)as * 64u, a_lo = a_hi + 32u;
+                const uint32_t b_hi = tc_smem_u32(s_b + bs * 2 * TP_HALF_BYTES), b_lo = b_hi + TP_HALF_BYTES;
+#pragma unroll
+                for (int j = 0; j < TP_ROWS / 8; ++j) {
+                    const uint32_t ko = j * 2 * TC_LBO;
+                    tc_mma_ts(d_tmem, a_hi + j * 8, tc_smem_desc(b_hi + ko), (in_seg > 0 || j > 0) ? 1u : 0u);
+                    tc_mma_ts(d_tmem, a_hi + j * 8, tc_smem_desc(b_lo + ko), 1u);
+                    tc_mma_ts(d_tmem, a_lo + j * 8, tc_smem_desc(b_hi + ko), 1u);
+                }
+                tc_commit(&a_free[as]);
+                tc_commit(&b_free[bs]);
+                if (in_seg == TP_SEG_SLABS - 1 || i == total - 1) tc_commit(&acc_full[buf]);
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== A side: column m of the X slab -> TMEM lane m (hi | lo) =====
+        const int q = warp & 3, m = q * 32 + lane;
+        const uint32_t t_lane = tmem_base + 2 * TC_TMEM_COLS + ((uint32_t)(q * 32) << 16);
+        for (int i = 0; i < total; ++i) {
+            const int slot = i % TP_RAW_SLOTS, stage = i % TP_A_STAGES;
+            tc_mbar_wait(&raw_full[slot], (uint32_t)(i / TP_RAW_SLOTS) & 1u);
+            const float* raw = reinterpret_cast<const float*>(s_raw + slot * TP_RAW_BYTES);
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int r = 0; r < TP_ROWS; ++r) {
+                float h, l;
+                split_tf32(raw[r * TC_BM + m], h, l);
+                hi[r] = __float_as_uint(h);
+                lo[r] = __float_as_uint(l);
+            }
+            tc_arrive(&raw_free[slot]);
+            if (i >= TP_A_STAGES) {
+                tc_mbar_wait(&a_free[stage], (uint32_t)(i / TP_A_STAGES - 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            tc_st32(t_lane + (uint32_t)stage * 64u, hi);
+            tc_st32(t_lane + (uint32_t)stage * 64u + 32u, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tc_arrive(&a_full[stage]);
+        }
+    } else if (warp >= 8 && warp < 12) {
+        // ===== B side: column c of the dH slab -> K-major hi / lo operand slabs (chunk-major, no swizzle) =====
+        const int c = tid - 256;
+        for (int i = 0; i < total; ++i) {
+            const int slot = i % TP_RAW_SLOTS, stage = i % TP_B_STAGES;
+            tc_mbar_wait(&raw_full[slot], (uint32_t)(i / TP_RAW_SLOTS) & 1u);
+            const float* raw = reinterpret_cast<const float*>(s_raw + slot * TP_RAW_BYTES + TP_HALF_BYTES);
+            float v[TP_ROWS];
+#pragma unroll
+            for (int r = 0; r < TP_ROWS; ++r) v[r] = raw[r * TC_BN + c];
+            tc_arrive(&raw_free[slot]);
+            if (i >= TP_B_STAGES) tc_mbar_wait(&b_free[stage], (uint32_t)(i / TP_B_STAGES - 1) & 1u);
+            uint8_t* st = s_b + stage * 2 * TP_HALF_BYTES + c * 16;
+#pragma unroll
+            for (int ch = 0; ch < TP_ROWS / 4; ++ch) {
+                float4 h, l;
+                split_tf32(v[ch * 4 + 0], h.x, l.x);
+                split_tf32(v[ch * 4 + 1], h.y, l.y);
+                split_tf32(v[ch * 4 + 2], h.z, l.z);
+                split_tf32(v[ch * 4 + 3], h.w, l.w);
+                *reinterpret_cast<float4*>(st + ch * TC_LBO) = h;
+                *reinterpret_cast<float4*>(st + TP_HALF_BYTES + ch * TC_LBO) = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_arrive(&b_full[stage]);
+        }
+    } else if (warp >= 12) {
+        // ===== drain: warp q owns output rows [32 q, 32 q + 32) of the CTA's partial tile =====
+        const int q = warp & 3;
+        uint8_t* stg = s_stage + q * (32 * 32 * 4);
+        const int prow = (int)blockIdx.x * TC_BM + q * 32;      // row of the [ctas * 128, f] partial matrix
+        for (int seg = 0; seg < nseg; ++seg) {
+            const int buf = seg & 1;
+            tc_mbar_wait(&acc_full[buf], (uint32_t)(seg >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + (uint32_t)buf * TC_TMEM_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int part = 0; part < 4; ++part) {
+                const bool live = part * 32 < g.f && q * 32 < g.k;      // warp-uniform
+                uint32_t acc[32];
+                if (live) tc_ld32(taddr + (uint32_t)(part * 32), acc);
+                if (part == 3) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    tc_arrive(&acc_free[buf]);
+                }
+                if (!live) continue;
+                // first part of a segment: every earlier store / add of this warp is COMPLETE, so the adds to one tile stay
+                // in segment order; later parts (other columns) only need the staging buffer back
+                if (lane == 0) {
+                    if (part == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                __syncwarp();
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    *reinterpret_cast<float4*>(stg + lane * 128 + ((e ^ (lane & 7)) * 16)) =
+                        make_float4(__uint_as_float(acc[4 * e]), __uint_as_float(acc[4 * e + 1]),
+                                    __uint_as_float(acc[4 * e + 2]), __uint_as_float(acc[4 * e + 3]));
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (seg == 0) ps_tma_store_2d(&tmap_part, part * 32, prow, stg);
+                    else tp_tma_reduce_add_2d(&tmap_part, part * 32, prow, stg);
+                }
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// out[e] = sum_s part[s][e] in fp64; split s starts at part + s * split_stride.  One warp per output element: lane l
+// adds the splits l, l + 32, ... in ascending order, then a fixed shuffle tree (deterministic).  (One thread per element
+// walked up to 148 dependent L2 loads: 80 us for a 100 x 128 gradient.)
+__global__ void __launch_bounds__(256) tn_reduce_kernel(const float* __restrict__ part, int64_t splits, int64_t split_stride,
+                                                        int64_t rows, int64_t cols, float* __restrict__ out, int64_t ldo) {
+    const int64_t total = rows * cols;
+    const int lane = threadIdx.x & 31;
+    for (int64_t e = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); e < total; e += (int64_t)gridDim.x * 8) {
+        double s = 0.0;
+        for (int64_t p = lane; p < splits; p += 32) s += (double)part[p * split_stride + e];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) out[(e / cols) * ldo + (e % cols)] = (float)s;
     }
 }
 
@@ -1283,10 +1515,66 @@ static void tn_tc_plan(int64_t n, int64_t k, int64_t f, int64_t* ctas, int64_t* 
     *ctas = ceil_div(n > 0 ? n : 1, rpc);
 }
 
+static void tp_plan(int64_t n, int64_t* ctas, int64_t* rows_per_cta) {
+    const int64_t segs = ceil_div(n > 0 ? n : 1, kTnRowsPerSplit);
+    const int64_t rpc = ceil_div(segs, (int64_t)kNumSMs) * kTnRowsPerSplit;
+    *rows_per_cta = rpc;
+    *ctas = ceil_div(n > 0 ? n : 1, rpc);
+}
+static bool tp_eligible(const float* a, int64_t lda, const int64_t* row_index, const float* g, int64_t ldg, int64_t n, int64_t k,
+                        int64_t f) {
+    static const bool on = [] { const char* e = getenv("GG_GEMM_PERSIST"); return !e || e[0] != '0'; }();
+    if (!on || row_index || k < 4 || k > TC_BM || f < 4 || f > TC_BN || k % 4 || f % 4 || lda % 4 || ldg % 4) return false;
+    if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(g) & 15)) return false;
+    if (n < (int64_t)kNumSMs * kTnRowsPerSplit || n >= ((int64_t)1 << 31)) return false;
+    return ps_encoder() != nullptr;
+}
+
 size_t gg_gemm_tn_tc_workspace_bytes(int64_t n, int64_t k, int64_t f) {
     int64_t ctas, rpc;
     tn_tc_plan(n, k, f, &ctas, &rpc);
-    return (size_t)ctas * (size_t)k * (size_t)f * sizeof(float) + 256;
+    size_t b = (size_t)ctas * (size_t)k * (size_t)f * sizeof(float) + 256;
+    if (k <= TC_BM && f <= TC_BN) {   // the persistent kernel's padded partial tiles: [ctas][128][f]
+        tp_plan(n, &ctas, &rpc);
+        const size_t pb = (size_t)ctas * TC_BM * (size_t)f * sizeof(float) + 256;
+        if (pb > b) b = pb;
+    }
+    return b;
+}
+
+static int tp_launch(const float* a, int64_t lda, const float* g, int64_t ldg, int64_t n, int64_t k, int64_t f, float* out,
+                     int64_t ldo, void* workspace, cudaStream_t st) {
+    PsEncodeTiled enc = ps_encoder();
+    int64_t ctas, rpc;
+    tp_plan(n, &ctas, &rpc);
+    float* partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    CUtensorMap ta, tg, tp;
+    const cuuint32_t estr[2] = {1, 1};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BM, (cuuint32_t)TP_ROWS};
+    const cuuint64_t adim[2] = {(cuuint64_t)k, (cuuint64_t)n}, astr[1] = {(cuuint64_t)lda * 4};
+    const cuuint64_t gdim[2] = {(cuuint64_t)f, (cuuint64_t)n}, gstr[1] = {(cuuint64_t)ldg * 4};
+    const cuuint64_t pdim[2] = {(cuuint64_t)f, (cuuint64_t)ctas * TC_BM}, pstr[1] = {(cuuint64_t)f * 4};
+    const cuuint32_t pbox[2] = {32, 32};
+    if (enc(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a), adim, astr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+        enc(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+        enc(&tp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, partial, pdim, pstr, pbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return GG_ERR_UNSUPPORTED;
+    static bool attr_done = false;
+    if (!attr_done) {
+        GG_CUDA(cudaFuncSetAttribute(tc_gemm_tn_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM_BYTES));
+        attr_done = true;
+    }
+    TpArgs t{n, (int)k, (int)f, rpc};
+    tc_gemm_tn_persist_kernel<<<(int)ctas, TP_THREADS, TP_SMEM_BYTES, st>>>(ta, tg, tp, t);
+    GG_LAUNCHED();
+    const int64_t total = k * f;
+    const int blocks = (int)(ceil_div(total, 8) < kNumSMs * 16 ? ceil_div(total, 8) : kNumSMs * 16);
+    tn_reduce_kernel<<<blocks, 256, 0, st>>>(partial, ctas, (int64_t)TC_BM * f, k, f, out, ldo);
+    GG_LAUNCHED();
+    return GG_OK;
 }
 
 int gg_gemm_tn_tc_f32(const float* a, int64_t lda, const int64_t* row_index, const float* g, int64_t ldg,
@@ -1306,6 +1594,10 @@ int gg_gemm_tn_tc_f32(const float* a, int64_t lda, const int64_t* row_index, con
         set_error("gg_gemm_tn_tc_f32: workspace %zu < %zu", workspace_bytes, gg_gemm_tn_tc_workspace_bytes(n, k, f));
         return GG_ERR_WORKSPACE;
     }
+    if (tp_eligible(a, lda, row_index, g, ldg, n, k, f)) {
+        const int rc = tp_launch(a, lda, g, ldg, n, k, f, out, ldo, workspace, st);
+        if (rc != GG_ERR_UNSUPPORTED) return rc;
+    }
     int64_t ctas, rpc;
     tn_tc_plan(n, k, f, &ctas, &rpc);
     static bool attr_done = false;
@@ -1323,8 +1615,8 @@ int gg_gemm_tn_tc_f32(const float* a, int64_t lda, const int64_t* row_index, con
     else tc_gemm_tn_kernel<false><<<grid, TC_BLOCK, TN_SMEM_BYTES, st>>>(t);
     GG_LAUNCHED();
     const int64_t total = k * f;
-    int blocks = (int)(ceil_div(total, 256) < kNumSMs * 8 ? ceil_div(total, 256) : kNumSMs * 8);
-    tn_reduce_kernel<<<blocks, 256, 0, st>>>(t.partial, ctas, k, f, out, ldo);
+    int blocks = (int)(ceil_div(total, 8) < kNumSMs * 16 ? ceil_div(total, 8) : kNumSMs * 16);
+    tn_reduce_kernel<<<blocks, 256, 0, st>>>(t.partial, ctas, k * f, k, f, out, ldo);
     GG_LAUNCHED();
     return GG_OK;
 }

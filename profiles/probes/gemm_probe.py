@@ -33,3 +33,14 @@ for k, f, bt in ((100, 128, False), (128, 100, True), (128, 128, False), (64, 64
     err = float((got - ref).norm() / ref.norm())
     print(f'K={k} F={f} b_trans={bt}: ours {t:.3f} ms = {gb / t:.2f} TB/s ({gb / t / 6.5443:.2f} of copy peak); '
           f'cuBLAS fp32 {tc:.3f} ms; rel err {err:.2e}', flush=True)
+
+for k, f in ((100, 128), (128, 128), (64, 64)):
+    x = torch.randn(n, k, device=dev)
+    gr = torch.randn(n, f, device=dev)
+    t = timeit(lambda: ops.gemm_tn(x, gr))
+    gb = (n * k + n * f) * 4 / 1e9
+    tc = timeit(lambda: torch.matmul(x.t(), gr))
+    ref = x[:200000].double().t() @ gr[:200000].double()
+    got = ops.gemm_tn(x[:200000], gr[:200000])
+    print(f'TN K={k} F={f}: ours {t:.3f} ms = {gb / t:.2f} TB/s ({gb / t / 6.5443:.2f} of copy peak); cuBLAS fp32 {tc:.3f} ms; '
+          f'rel err {float((got - ref).norm() / ref.norm()):.2e}', flush=True)

@@ -136,3 +136,22 @@ def test_persistent_layer_gemm(cuda, gemm_mode, n, k, f, b_trans):
     tail = ops.id_gemm([(x[-300:], w, None)], 300, f, b_trans=b_trans)
     full = ops.id_gemm([(x, w, None)], n, f, b_trans=b_trans)
     assert rel_err(full[-300:], tail) < 2e-6
+
+
+@pytest.mark.parametrize('n,k,f', [(148 * 256, 100, 128), (148 * 256 + 333, 128, 100), (200000, 36, 36),
+                                   (50000, 4, 128), (148 * 256 * 3 + 31, 64, 8)])
+def test_persistent_weight_gradient(cuda, gemm_mode, n, k, f):
+    """dW = X^T G for K, F <= 128 and at least one 256-row segment per SM: the persistent TN kernel (TMA slabs, A operand
+    transposed into tensor memory, accumulator segments drained by TMA reduce-add into an L2-resident partial tile).
+    Strided operands; fp64 reference evaluated on the device; two runs give the same bits."""
+    g = torch.Generator(device=cuda).manual_seed(n + k + f)
+    a = torch.randn(n, k + 4, generator=g, device=cuda)[:, :k]
+    gr = torch.randn(n, f + 8, generator=g, device=cuda)[:, :f]
+    got = ops.gemm_tn(a, gr)
+    want = a.double().t() @ gr.double()
+    assert rel_err(got, want) < FP32_TOL
+    assert torch.equal(got, ops.gemm_tn(a, gr))
+    # a column of ones in X turns its row of dW into the column sums of G
+    ones = torch.ones(n, 4, device=cuda)
+    cs = ops.gemm_tn(ones, gr)
+    assert rel_err(cs[0], gr.double().sum(0)) < FP32_TOL

@@ -1063,6 +1063,10 @@ __global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_tn_kernel(TnTcArgs g) {
 //                             drained while segment s + 1 is multiplied.  The adds of one tile are issued in segment
 //                             order and each is complete before the next is issued: deterministic.
 // The per-CTA partials are reduced in fp64 by tn_reduce_kernel as before.
+// History: cvt.rna hi / lo splits 0.56 ms (ncu: the issuer waits for the B side, which is busy 80 % of the time;
+// cvt.rna runs at 16 per clock and SM) -> truncation splits 0.52 ms; eight warps per converter side instead of four:
+// slower (0.55 ms), dropped.  Tensor pipe 44 % active, shared-memory pipe 35 %: the remaining gap to the 0.34 ms DRAM
+// time is in the hand-offs between the roles (two B stages), not in any one unit.
 // ---------------------------------------------------------------------------------------------
 constexpr int TP_ROWS = 32;                              // reduction rows per slab
 constexpr int TP_HALF_BYTES = TP_ROWS * TC_BM * 4;       // 16384: one operand's raw slab, and one hi or lo B slab
@@ -1188,11 +1192,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_gemm_tn_persist_kernel(const
             const float* raw = reinterpret_cast<const float*>(s_raw + slot * TP_RAW_BYTES);
             uint32_t hi[32], lo[32];
 #pragma unroll
-            for (int r = 0; r < TP_ROWS; ++r) {
-                float h, l;
-                split_tf32(raw[r * TC_BM + m], h, l);
-                hi[r] = __float_as_uint(h);
-                lo[r] = __float_as_uint(l);
+            for (int r = 0; r < TP_ROWS; ++r) {   // hi = the raw bits (the tensor core reads the TF32 part), lo = x - trunc(x):
+                const float x = raw[r * TC_BM + m];   // two full-rate instructions per element (cvt.rna runs at 16 / clk / SM)
+                hi[r] = __float_as_uint(x);
+                lo[r] = __float_as_uint(x - trunc_tf32(x));
             }
             tc_arrive(&raw_free[slot]);
             if (i >= TP_A_STAGES) {
@@ -1220,11 +1223,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_gemm_tn_persist_kernel(const
             uint8_t* st = s_b + stage * 2 * TP_HALF_BYTES + c * 16;
 #pragma unroll
             for (int ch = 0; ch < TP_ROWS / 4; ++ch) {
-                float4 h, l;
-                split_tf32(v[ch * 4 + 0], h.x, l.x);
-                split_tf32(v[ch * 4 + 1], h.y, l.y);
-                split_tf32(v[ch * 4 + 2], h.z, l.z);
-                split_tf32(v[ch * 4 + 3], h.w, l.w);
+                const float4 h = make_float4(v[ch * 4], v[ch * 4 + 1], v[ch * 4 + 2], v[ch * 4 + 3]);
+                const float4 l = make_float4(h.x - trunc_tf32(h.x), h.y - trunc_tf32(h.y), h.z - trunc_tf32(h.z),
+                                             h.w - trunc_tf32(h.w));
                 *reinterpret_cast<float4*>(st + ch * TC_LBO) = h;
                 *reinterpret_cast<float4*>(st + TP_HALF_BYTES + ch * TC_LBO) = l;
             }

@@ -1071,8 +1071,8 @@ __global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_tn_kernel(TnTcArgs g) {
 constexpr int TP_ROWS = 32;                              // reduction rows per slab
 constexpr int TP_HALF_BYTES = TP_ROWS * TC_BM * 4;       // 16384: one operand's raw slab, and one hi or lo B slab
 constexpr int TP_RAW_BYTES = 2 * TP_HALF_BYTES;
-constexpr int TP_RAW_SLOTS = 4;
-constexpr int TP_B_STAGES = 2;
+constexpr int TP_RAW_SLOTS = 3;
+constexpr int TP_B_STAGES = 3;
 constexpr int TP_A_STAGES = 4;
 constexpr int TP_SEG_SLABS = kTnRowsPerSplit / TP_ROWS;  // 8 slabs per accumulator segment
 constexpr int TP_THREADS = 16 * 32;

@@ -162,6 +162,12 @@ __device__ __forceinline__ void tc_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void tc_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(bar)) : "memory");
 }
+// RULE for releasing a shared-memory slot that this thread has read with ld.shared (the producer refills it by TMA or
+// cp.async): arrive on the slot's barrier only AFTER an instruction that consumes the loaded registers has issued
+// (the tcgen05.st / st.shared that carries the data on).  An arrive placed right after the loads is NOT ordered behind
+// their execution: the refill landed under loads still in flight and whole warps' rows of the persistent kernels came out
+// wrong (0.3 % of the rows of a 2.45 M-row product with a 4-slot ring; found by profiles/probes/gemm_stress.py, pinned
+// down with profiles/probes/gemm_diag.py).  A fake register dependency in inline PTX does not help: ptxas folds it away.
 __device__ __forceinline__ void tc_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      tc_smem_u32(dst)),
@@ -709,13 +715,13 @@ __global__ void __launch_bounds__(PS_THREADS, 1) tc_gemm_persist_kernel(const __
                     const float x = __uint_as_float(hi[e]);
                     lo[e] = __float_as_uint(x - trunc_tf32(x));
                 }
-                tc_arrive(&raw_free[slot]);      // the row is in registers: the producer may refill the slot
                 if (item >= PS_A_STAGES) {
                     tc_mbar_wait(&a_free[stage], (uint32_t)(item / PS_A_STAGES - 1) & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 tc_st32(t_lane + (uint32_t)stage * 64u, hi);
                 tc_st32(t_lane + (uint32_t)stage * 64u + 32u, lo);
+                tc_arrive(&raw_free[slot]);      // the stores have consumed the loaded registers (see the RULE above)
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 tc_arrive(&a_full[stage]);
@@ -965,7 +971,6 @@ __global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_tn_kernel(TnTcArgs g) {
                 va[kk] = raw_a[kk * TC_BM + rt];
                 vg[kk] = raw_g[kk * TC_BM + rt];
             }
-            tc_arrive(&raw_empty[slot]);
             if (i >= TN_STAGES) tc_mbar_wait(&op_free[stage], tc_free_parity(i, TN_STAGES));
             uint8_t* st = smem + TN_OFF_OP + stage * TC_STAGE_BYTES;
 #pragma unroll
@@ -985,6 +990,7 @@ __global__ void __launch_bounds__(TC_BLOCK, 2) tc_gemm_tn_kernel(TnTcArgs g) {
                 *reinterpret_cast<float4*>(st + 2 * TC_TILE_BYTES + off) = h;
                 *reinterpret_cast<float4*>(st + 3 * TC_TILE_BYTES + off) = l;
             }
+            tc_arrive(&raw_empty[slot]);         // after the stores that consume the loaded registers (RULE above)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_arrive(&op_full[stage]);
             if (i % kSlabsPerSeg == kSlabsPerSeg - 1 || i == total - 1) drain(i / kSlabsPerSeg);
@@ -1197,13 +1203,13 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_gemm_tn_persist_kernel(const
                 hi[r] = __float_as_uint(x);
                 lo[r] = __float_as_uint(x - trunc_tf32(x));
             }
-            tc_arrive(&raw_free[slot]);
             if (i >= TP_A_STAGES) {
                 tc_mbar_wait(&a_free[stage], (uint32_t)(i / TP_A_STAGES - 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             }
             tc_st32(t_lane + (uint32_t)stage * 64u, hi);
             tc_st32(t_lane + (uint32_t)stage * 64u + 32u, lo);
+            tc_arrive(&raw_free[slot]);          // after the stores that consume the loaded registers (RULE above)
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             tc_arrive(&a_full[stage]);
@@ -1218,7 +1224,6 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_gemm_tn_persist_kernel(const
             float v[TP_ROWS];
 #pragma unroll
             for (int r = 0; r < TP_ROWS; ++r) v[r] = raw[r * TC_BN + c];
-            tc_arrive(&raw_free[slot]);
             if (i >= TP_B_STAGES) tc_mbar_wait(&b_free[stage], (uint32_t)(i / TP_B_STAGES - 1) & 1u);
             uint8_t* st = s_b + stage * 2 * TP_HALF_BYTES + c * 16;
 #pragma unroll
@@ -1229,6 +1234,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) tc_gemm_tn_persist_kernel(const
                 *reinterpret_cast<float4*>(st + ch * TC_LBO) = h;
                 *reinterpret_cast<float4*>(st + TP_HALF_BYTES + ch * TC_LBO) = l;
             }
+            tc_arrive(&raw_free[slot]);          // after the stores that consume the loaded registers (RULE above)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             tc_arrive(&b_full[stage]);
         }

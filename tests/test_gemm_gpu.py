@@ -155,3 +155,35 @@ def test_persistent_weight_gradient(cuda, gemm_mode, n, k, f):
     ones = torch.ones(n, 4, device=cuda)
     cs = ops.gemm_tn(ones, gr)
     assert rel_err(cs[0], gr.double().sum(0)) < FP32_TOL
+
+
+def test_persistent_gemms_are_deterministic_under_load(cuda, gemm_mode):
+    """Regression test of the slot-release race (persistent kernels): at 600 K rows every CTA walks ~30 tiles
+    with its rings full, which is where a refill landed under loads still in flight.  Repeated launches — bias + ReLU,
+    ReLU mask, weight gradient — interleaved with a per-tile launch must reproduce the first results bit for bit, and the
+    first results must be right."""
+    if gemm_mode != 'tc':
+        pytest.skip('tensor-core kernels only')
+    n, k, f = 600_000, 100, 128
+    gen = torch.Generator(device=cuda).manual_seed(11)
+    x = torch.randn(n, k, generator=gen, device=cuda)
+    g = torch.randn(n, f, generator=gen, device=cuda)
+    w = torch.randn(k, f, generator=gen, device=cuda)
+    b = torch.randn(f, generator=gen, device=cuda)
+    small = torch.randn(3000, k, generator=gen, device=cuda)
+
+    def launches():
+        ops.id_gemm([(small, w, None)], 3000, f)
+        return (ops.id_gemm([(x, w, None)], n, f, bias=b, act=ops.ACT_RELU),
+                ops.id_gemm([(g, w, None)], n, k, b_trans=True, relu_mask=x),
+                ops.gemm_tn(x, g))
+
+    ref = [t.clone() for t in launches()]
+    rows = slice(n - 70_000, n)                                   # the last tiles of every CTA
+    assert rel_err(ref[0][rows], (x[rows].double() @ w.double() + b.double()).relu()) < FP32_TOL
+    assert rel_err(ref[1][rows], (g[rows].double() @ w.double().t()) * (x[rows] > 0)) < FP32_TOL
+    assert rel_err(ref[2], x.double().t() @ g.double()) < FP32_TOL
+    for it in range(25):
+        got = launches()
+        for i, (a, r) in enumerate(zip(got, ref)):
+            assert torch.equal(a, r), (it, i, int((a != r).sum()))

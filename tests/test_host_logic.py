@@ -136,3 +136,22 @@ def test_bench_generators_are_seeded_and_well_formed():
     assert m == 5000 and e.shape == (2, 80000) and int(e.max()) < m
     assert bench.spmm_bytes(10, 100, 8, True) == 100 * 8 * 4 + 10 * 8 * 4 + 100 * 4 + 11 * 4 + 100 * 4
     assert bench.spmm_bytes(10, 100, 8, False, gather_bytes=2) == 100 * 8 * 2 + 10 * 8 * 4 + 100 * 4 + 11 * 4
+
+
+def test_every_environment_switch_is_documented():
+    """INTEGRATION.md §7 lists every GG_* variable the package, the C-ABI library sources and bench.py read."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    used = set()
+    pat = re.compile(r'''(?:getenv\(\s*"|environ\.get\(\s*['"])(GG_[A-Z0-9_]+)''')
+    for base, _, files in os.walk(os.path.join(root, 'graphgym_b200')):
+        if 'build' in base:
+            continue
+        for name in files:
+            if name.endswith(('.py', '.cu', '.cuh')):
+                used |= set(pat.findall(open(os.path.join(base, name), errors='ignore').read()))
+    used |= set(pat.findall(open(os.path.join(root, 'bench.py')).read()))
+    doc = open(os.path.join(root, 'INTEGRATION.md')).read()
+    missing = sorted(v for v in used if v not in doc)
+    assert used and not missing, missing
